@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- GMG V-cycle throughput on B200 (BASELINE.json metric: "V-cycle DoF/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n N] [--levels L]
+
+One "step" = one driver iteration of the reference (GeometricMultigrid/src/main.cpp:84-90):
+2 pre-sweeps on the fine grid, one sawtooth multigrid cycle, one residual norm.
+  value  = fine DoF x K / device time of K steps, inputs resident in HBM (CUDA events on the
+           library's own stream; max over ranks).
+  e2e    = the same metric through the C ABI with HOST buffers: upload f and u0 from pinned host
+           memory, K steps each reading its residual norm back (the step's result), download u.
+  roofline = the dominant kernel (fine-level red-black GS colour pass) timed alone, live.
+  cpu_baseline = the reference's own CPU classes (oracle/_ref, compiled from /root/reference) on the
+           box's host cores, on a bounded sample of the same workload.
+Workloads: N=1 -> config C3 (8193^2, L=13); N>1 -> config C4 (16385^2, L=14) in row slabs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LENGTH, ALPHA, TEST = 10.0, 1.0, 1
+METRIC, UNIT = "gmg_vcycle_dof_per_s", "DoF/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference(n, levels, cycles, threads=None):
+    """times the reference's own classes (oracle/_ref) -- the checker, never the product"""
+    import oracle
+    r = oracle.ref_gmg()
+    kind = "reference"
+    ncores = os.cpu_count() or 1
+    if r is None:
+        o = oracle.gmg()
+        b = o.rhs(n, LENGTH, TEST)
+        t = time.perf_counter()
+        o.solve(n, LENGTH, ALPHA, levels, oracle.GS, b, maxiter=cycles, tol=0.0)
+        dt = time.perf_counter() - t
+        return n * n * cycles / dt, 1, "port", dt
+    threads = threads or ncores
+    r.set_threads(threads)
+    b = r.rhs(n, LENGTH, TEST)
+    t = time.perf_counter()
+    r.solve(n, LENGTH, ALPHA, levels, 0, b, maxiter=cycles, tol=0.0)
+    dt = time.perf_counter() - t
+    return n * n * cycles / dt, threads, kind, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on the host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, levels = 1025, 10
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, kind, dt = cpu_reference(n, levels, 1)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = n * n * len(vals) / sum(d for _, d in vals)
+    workload = workload_name(args)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"each step = 1 driver iteration (2 GS + sawtooth cycle + residual) of the "
+                                   f"reference's GS solver on {n}^2, L={levels}, test {TEST}; throughput per DoF is "
+                                   f"size-independent (SURVEY.md section 6: 0.72/0.67 MDoF*cyc/s at 1025^2/2049^2); "
+                                   f"only the residual loops are OpenMP-parallel, lexicographic GS is serial"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(args):
+    n, L = problem(args)
+    return (f"GMG 2D Poisson {n}x{n} ({n * n / 1e6:.0f}M DoF), L={L}, test {TEST}, alpha={ALPHA}, W={LENGTH}, "
+            f"u0=0; {args.mode} mode")
+
+
+def problem(args):
+    if args.n:
+        n = args.n
+        L = args.levels or max(1, int(np.log2(n - 1)))
+        return n, L
+    return (8193, 13) if args.gpus == 1 else (16385, 14)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--levels", type=int, default=0)
+    ap.add_argument("--mode", default="fast", choices=["fast", "parity-jacobi", "parity-gs"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from multigrid_prj_b200 import Gmg, GmgConfig
+    from multigrid_prj_b200 import gmg as G
+    from multigrid_prj_b200.gmg import Timer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun", file=sys.stderr)
+        return 2
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+
+    n, L = problem(args)
+    if args.mode == "fast":
+        cfg = GmgConfig.fast(n, L, length=LENGTH, alpha=ALPHA, device=local)
+    elif args.mode == "parity-jacobi":
+        cfg = GmgConfig(n=n, levels=L, length=LENGTH, alpha=ALPHA, smoother=G.JACOBI, device=local)
+    else:
+        cfg = GmgConfig(n=n, levels=L, length=LENGTH, alpha=ALPHA, smoother=G.GS_LEX, device=local)
+    cfg.rank, cfg.n_ranks = rank, world
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    g = Gmg(cfg)
+    g.set_rhs_test(TEST)
+    g.set_u(None)
+    timer = Timer()
+    st = g.stream()
+    # ---- device-resident throughput ------------------------------------------------------------
+    g.run_cycles(args.warmup)
+    g.sync(); barrier()
+    g.reset_stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    timer.start(st)
+    g.run_cycles(args.steps, want_relres=False)
+    timer.stop(st)
+    ms = timer.elapsed_ms()
+    g.sync(); barrier()
+    clocks = sampler.stop() if sampler else None
+    stats = g.stats()
+    relres = g.run_cycles(0)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    dof = float(n) * float(n)
+    value = dof * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel alone: fine-level smoothing pass ------------------------------------------
+    peak, peak_src = peaks()
+    reps = 10
+    kind = cfg.smoother if cfg.smoother != G.GS_LEX else G.GS_RB
+    g.smooth(0, kind, sweeps=2, sol=G.VEC_E, rhs=G.VEC_R)
+    g.sync()
+    g.reset_stats()
+    timer.start(st)
+    g.smooth(0, kind, sweeps=reps, sol=G.VEC_E, rhs=G.VEC_R)
+    timer.stop(st)
+    kms = timer.elapsed_ms()
+    ks = g.stats()
+    rows0 = g.rows(0)[1]
+    launches = ks["kernel_launches"]
+    alg_bytes = ks["bytes_algorithmic"] / launches           # per launch (12 B/pt per colour pass, 24 B/pt Jacobi)
+    achieved = alg_bytes / (kms * 1e-3 / launches) / 1e9
+    kname = {G.GS_RB: "k_rbgs_colour (one colour pass, 12 B/pt)", G.JACOBI: "k_jacobi (24 B/pt)"}[kind]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": kname, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kms / launches,
+                "step_algorithmic_gbs": stats["bytes_algorithmic"] / (ms * 1e-3) / 1e9,
+                "step_frac": stats["bytes_algorithmic"] / (ms * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import torch
+        r0, rows = g.rows(0)
+        f_host = torch.empty((n, n), dtype=torch.float64).pin_memory() if world == 1 else None
+        if f_host is not None:
+            fh = f_host.numpy()
+            fh[:] = g.get_level(0, G.VEC_F)
+            u_host = torch.zeros((n, n), dtype=torch.float64).pin_memory()
+            uh = u_host.numpy()
+            g.sync(); barrier()
+            t0 = time.perf_counter()
+            g.set_rhs(fh)
+            g.set_u(uh)
+            hist = g.solve(tol=0.0, maxiter=args.steps, check_every=1)
+            g.get_u(uh)
+            dt = time.perf_counter() - t0
+            e2e = {"value": dof * args.steps / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": 2 * dof * 8 / args.steps, "d2h_bytes_per_step": dof * 8 / args.steps + 8,
+                   "what": f"mgb_gmg_set_rhs + set_u (pinned host -> HBM), {args.steps} steps each reading its residual "
+                           f"norm back, mgb_gmg_get_u (HBM -> pinned host); wall clock", "final_relres": float(hist[-1])}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cn, cl, cc = 2049, 11, 2
+        v, cores, ckind, dt = cpu_reference(cn, cl, cc)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": ckind,
+               "sample": f"{cc} driver iterations of the reference's GS solver on {cn}^2, L={cl} ({dt:.1f} s); "
+                         f"lexicographic GS is serial, only the residual loops use the {cores} OpenMP threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "smoother": cfg.smoother, "restriction": cfg.restriction,
+                       "l2": "inputs larger than L2 (5 x 537 MB fine arrays vs 126 MB L2)", "final_relres": relres},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

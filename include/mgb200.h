@@ -1,0 +1,162 @@
+/*
+ * mgb200.h -- C ABI of the B200-native multigrid solve phase (libmgb200.so).
+ *
+ * This is the drop-in boundary for the reference's solver entry points
+ * (Stefo01/multigrid_prj; citations relative to the reference tree).  The reference has no FFI:
+ * its boundary is the C++ class API its two drivers use.  The facade headers
+ * under multigrid_prj_b200/dropin/ re-declare those classes on top of the functions below, so the
+ * reference's GeometricMultigrid/src/main.cpp and AMG/src/main.cpp compile against them unchanged.
+ *
+ * Conventions: plain pointers and sizes, opaque handles, int status (0 = ok, nonzero = error,
+ * text from mgb_last_error()), no exceptions cross the boundary, one host thread per handle.
+ * All host arrays are fp64, row-major.  There is NO CPU fallback: every compute entry point
+ * fails with MGB_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    MGB_OK = 0,
+    MGB_ERR_ARG = 1,      /* bad argument (e.g. (N-1) not divisible by 2^(levels-1)) */
+    MGB_ERR_CUDA = 2,     /* CUDA runtime error / no device */
+    MGB_ERR_NCCL = 3,
+    MGB_ERR_STATE = 4     /* call sequence error (e.g. solve before set_rhs) */
+};
+
+/* smoother ids: 0..2 follow GeometricMultigrid/include/utilities.hpp:9-14 (enum SMOOTHERS) */
+enum {
+    MGB_SMOOTH_GS_LEX = 0,   /* lexicographic Gauss-Seidel, solvers.hpp:24-49 (exact wavefront order)   */
+    MGB_SMOOTH_JACOBI = 1,   /* Jacobi, omega = 1, solvers.hpp:53-84                                       */
+    MGB_SMOOTH_BICGSTAB = 2, /* accepted and routed to Jacobi exactly as main.cpp:103-106 does            */
+    MGB_SMOOTH_GS_RB = 3     /* red-black Gauss-Seidel (reordered; the B200 fast path)                    */
+};
+
+/* restriction of the fine residual to the coarse levels */
+enum {
+    MGB_RESTRICT_INJECTION = 0,      /* the reference's: res read at stride 2^l (solvers.hpp:35,46,69,80) */
+    MGB_RESTRICT_HALF_INJECTION = 1, /* 0.5 * injection (pairs with red-black GS)                           */
+    MGB_RESTRICT_FULL_WEIGHTING = 2  /* [1 2 1;2 4 2;1 2 1]/16 cascaded level by level (north_star)         */
+};
+
+/* which device-resident vector of a level an operator call refers to */
+enum {
+    MGB_VEC_U = 0,   /* fine solution u           (main.cpp:49)              level 0 only */
+    MGB_VEC_F = 1,   /* fine right-hand side fvec (main.cpp:45)              level 0 only */
+    MGB_VEC_E = 2,   /* err restricted to a level (multigrid.hpp:94)                       */
+    MGB_VEC_R = 3    /* res restricted to a level (multigrid.hpp:93)                       */
+};
+
+typedef struct mgb_gmg_config {
+    size_t n;             /* points per side of the fine grid            (-n,  utilities.hpp:16) */
+    double length;        /* side of the square                          (-w)                    */
+    double alpha;         /* diffusion constant                          (-a)                    */
+    int levels;           /* multigrid levels L                          (-ml)                   */
+    int smoother;         /* smoother inside the cycle                   (-smt)                  */
+    int pre_smoother;     /* driver pre-smoother (main.cpp:62: always GS) */
+    int n_pre;            /* driver pre-sweeps per cycle (main.cpp:85: 2) */
+    int nu;               /* post-sweeps per level (multigrid.hpp:105: 5) */
+    int restriction;      /* MGB_RESTRICT_*                                */
+    double coarse_tol;    /* multigrid.hpp:123: 1e-1                       */
+    int coarse_maxit;     /* multigrid.hpp:123: 2000                       */
+    int device;           /* CUDA device ordinal                           */
+    /* slab decomposition over one box (rank r owns a contiguous block of fine rows) */
+    int rank, n_ranks;
+    unsigned char nccl_id[128];   /* ncclUniqueId from mgb_nccl_unique_id(), same on all ranks */
+    int tail_max_width;   /* levels with width <= this run inside the persistent coarse-tail kernel */
+    int use_graph;        /* capture the static part of the cycle in a CUDA graph */
+    int reserved[8];
+} mgb_gmg_config;
+
+typedef struct mgb_gmg *mgb_gmg_t;
+
+/* fills cfg with the reference's defaults (utilities.hpp:16-21, multigrid.hpp:105,123, main.cpp:85) */
+void mgb_gmg_config_default(mgb_gmg_config *cfg);
+/* same, but the B200 fast path: red-black GS everywhere + full weighting */
+void mgb_gmg_config_fast(mgb_gmg_config *cfg);
+
+/* replaces: L x SquareDomain (domain.cpp:4-13) + L x PoissonMatrix (linear_system.hpp:16-17)
+ * + SawtoothMGIteration ctor (multigrid.hpp:108-124) + Residual/GS objects of main.cpp:58-62 */
+int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out);
+void mgb_gmg_destroy(mgb_gmg_t h);
+
+/* geometry queries (domain.hpp:82,90,94) */
+int mgb_gmg_level_width(mgb_gmg_t h, int level, size_t *width);
+/* local slab of level `level`: first global row and number of rows owned by this rank */
+int mgb_gmg_level_rows(mgb_gmg_t h, int level, size_t *row0, size_t *rows);
+
+/* replaces DataVector (linear_system.hpp:85-92): b_host is the n*n row-major fvec (global array;
+ * each rank copies its slab).  mgb_gmg_set_rhs_test samples f,g of utilities.cpp:138-147 on device. */
+int mgb_gmg_set_rhs(mgb_gmg_t h, const double *b_host);
+int mgb_gmg_set_rhs_test(mgb_gmg_t h, int test);
+int mgb_gmg_set_u(mgb_gmg_t h, const double *u_host);          /* n*n global, NULL = zeros */
+int mgb_gmg_get_u(mgb_gmg_t h, double *u_host);                /* n*n global; each rank writes its slab */
+
+/* compact w_l x w_l level arrays, for the facade and the per-operator parity tests */
+int mgb_gmg_set_level(mgb_gmg_t h, int level, int which, const double *host);
+int mgb_gmg_get_level(mgb_gmg_t h, int level, int which, double *host);
+
+/* replaces SmootherClass::apply_iteration_to_vec (solvers.hpp:33-48, 64-83): `sweeps` sweeps of
+ * `kind` on `level`, solution vector `sol` (MGB_VEC_U or MGB_VEC_E), rhs `rhs` (MGB_VEC_F or MGB_VEC_R) */
+int mgb_gmg_smooth(mgb_gmg_t h, int level, int kind, int sweeps, int sol, int rhs);
+/* replaces Residual::apply_iteration_to_vec + Norm (solvers.hpp:257-307): r = rhs - A sol on `level`;
+ * store != 0 writes r into MGB_VEC_R of that level; sumsq = sum r^2 (all ranks) */
+int mgb_gmg_residual(mgb_gmg_t h, int level, int sol, int rhs, int store, double *sumsq);
+/* sum of squares of a level vector (Residual ctor / refresh_normalization_constant, solvers.hpp:230-254) */
+int mgb_gmg_sumsq(mgb_gmg_t h, int level, int which, double *sumsq);
+/* restriction of MGB_VEC_R from level 0 to every coarser level with the configured operator */
+int mgb_gmg_restrict(mgb_gmg_t h);
+/* replaces InterpolationClass::interpolate (multigrid.cpp:3-27): E(level_coarse) -> E(level_coarse-1) */
+int mgb_gmg_prolong(mgb_gmg_t h, int level_coarse);
+
+/* replaces SawtoothMGIteration::apply_iteration_to_vec (multigrid.hpp:126-145) applied to u.
+ * coarse_relres = the value the reference prints per cycle; coarse_iters = coarse-solve sweeps. */
+int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters);
+
+/* replaces the driver loop main.cpp:73-116: hist[0] = ||f-Au||/||f||, then per iteration n_pre
+ * pre-sweeps, one cycle, one residual norm; stops when hist <= tol or after maxiter cycles.
+ * hist must hold maxiter+1 doubles. check_every: read the norm back (one double, one sync) every
+ * k-th cycle only (1 = the reference's behaviour). */
+int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double *hist, int *n_hist);
+/* runs exactly `cycles` driver iterations without any host readback; writes the final relative
+ * residual.  This is the timed region of bench.py. */
+int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres);
+
+/* measurement hooks */
+typedef struct mgb_gmg_stats {
+    uint64_t kernel_launches;      /* kernels launched by this handle since create/reset */
+    uint64_t graph_launches;
+    uint64_t coarse_iters_total;
+    uint64_t cycles;
+    double bytes_algorithmic;      /* SURVEY.md section 8d accounting, summed over the launches */
+    int reserved[8];
+} mgb_gmg_stats;
+int mgb_gmg_get_stats(mgb_gmg_t h, mgb_gmg_stats *s);
+int mgb_gmg_reset_stats(mgb_gmg_t h);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller */
+void *mgb_gmg_stream(mgb_gmg_t h);
+int mgb_gmg_sync(mgb_gmg_t h);
+
+/* CUDA-event timer on a stream of this library (stream = mgb_gmg_stream()/mgb_amg_stream()) */
+typedef struct mgb_timer *mgb_timer_t;
+int mgb_timer_create(mgb_timer_t *t);
+void mgb_timer_destroy(mgb_timer_t t);
+int mgb_timer_start(mgb_timer_t t, void *stream);
+int mgb_timer_stop(mgb_timer_t t, void *stream);
+int mgb_timer_elapsed_ms(mgb_timer_t t, double *ms);   /* synchronises on the stop event */
+
+int mgb_nccl_unique_id(unsigned char id[128]);
+const char *mgb_last_error(void);
+const char *mgb_version(void);
+int mgb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB200_H */

@@ -1,0 +1,96 @@
+"""ctypes loader of libmgb200.so.  Fails loudly if the library is missing: no fallback path."""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(PKG, "lib", "libmgb200.so")
+
+
+class MgbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mgb200 error {code}: {msg}")
+        self.code = code
+
+
+class GmgConfigStruct(C.Structure):
+    # mirrors mgb_gmg_config in include/mgb200.h
+    _fields_ = [("n", C.c_size_t), ("length", C.c_double), ("alpha", C.c_double),
+                ("levels", C.c_int), ("smoother", C.c_int), ("pre_smoother", C.c_int),
+                ("n_pre", C.c_int), ("nu", C.c_int), ("restriction", C.c_int),
+                ("coarse_tol", C.c_double), ("coarse_maxit", C.c_int), ("device", C.c_int),
+                ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
+                ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("reserved", C.c_int * 8)]
+
+
+class GmgStatsStruct(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64),
+                ("coarse_iters_total", C.c_uint64), ("cycles", C.c_uint64),
+                ("bytes_algorithmic", C.c_double), ("reserved", C.c_int * 8)]
+
+
+# every symbol include/mgb200.h declares: name -> (restype, argtypes)
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+SYMBOLS = {
+    "mgb_gmg_config_default": (None, [C.POINTER(GmgConfigStruct)]),
+    "mgb_gmg_config_fast": (None, [C.POINTER(GmgConfigStruct)]),
+    "mgb_gmg_create": (_i, [C.POINTER(GmgConfigStruct), C.POINTER(_vp)]),
+    "mgb_gmg_destroy": (None, [_vp]),
+    "mgb_gmg_level_width": (_i, [_vp, _i, C.POINTER(C.c_size_t)]),
+    "mgb_gmg_level_rows": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mgb_gmg_set_rhs": (_i, [_vp, _vp]),
+    "mgb_gmg_set_rhs_test": (_i, [_vp, _i]),
+    "mgb_gmg_set_u": (_i, [_vp, _vp]),
+    "mgb_gmg_get_u": (_i, [_vp, _vp]),
+    "mgb_gmg_set_level": (_i, [_vp, _i, _i, _vp]),
+    "mgb_gmg_get_level": (_i, [_vp, _i, _i, _vp]),
+    "mgb_gmg_smooth": (_i, [_vp, _i, _i, _i, _i, _i]),
+    "mgb_gmg_residual": (_i, [_vp, _i, _i, _i, _i, _pd]),
+    "mgb_gmg_sumsq": (_i, [_vp, _i, _i, _pd]),
+    "mgb_gmg_restrict": (_i, [_vp]),
+    "mgb_gmg_prolong": (_i, [_vp, _i]),
+    "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
+    "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),
+    "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),
+    "mgb_gmg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
+    "mgb_gmg_reset_stats": (_i, [_vp]),
+    "mgb_gmg_stream": (_vp, [_vp]),
+    "mgb_gmg_sync": (_i, [_vp]),
+    "mgb_nccl_unique_id": (_i, [C.POINTER(C.c_ubyte * 128)]),
+    "mgb_last_error": (C.c_char_p, []),
+    "mgb_version": (C.c_char_p, []),
+    "mgb_device_count": (_i, []),
+    "mgb_timer_create": (_i, [C.POINTER(_vp)]),
+    "mgb_timer_destroy": (None, [_vp]),
+    "mgb_timer_start": (_i, [_vp, _vp]),
+    "mgb_timer_stop": (_i, [_vp, _vp]),
+    "mgb_timer_elapsed_ms": (_i, [_vp, _pd]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _LIB
+
+
+def load():
+    """Loads libmgb200.so and binds every declared symbol.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise MgbError(-1, f"{_LIB} is not built: run `python -m multigrid_prj_b200.build` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(_LIB, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MgbError(rc, load().mgb_last_error().decode())

@@ -1,0 +1,59 @@
+"""Builds libmgb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m multigrid_prj_b200.build          # or: from multigrid_prj_b200.build import build_lib
+
+The shared library is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "lib", "libmgb200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",
+]
+
+
+def _nvcc():
+    n = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(n):
+        raise RuntimeError("nvcc not found")
+    return n
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mgb200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [_nvcc()] + flags + ["-shared", "-o", LIB, "-I", os.path.join(ROOT, "include")] + sources()
+    cmd += ["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "1") == "1" else []
+    if verbose:
+        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    env = dict(os.environ)
+    # the image's $CC/$CXX wrappers are not usable as nvcc host compilers for shared objects
+    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,366 @@
+// gmg_kernels.cuh -- sm_100a kernels of the geometric-multigrid solve phase.
+//
+// Data layout (HBM): every level l keeps COMPACT fp64 arrays of (rows_l + 2) x pitch_l doubles:
+// rows_l owned rows of this rank's slab plus one halo row above and below; pitch_l is a multiple
+// of 16 doubles (128 B) so that column 0 of every row is 128-B aligned and every thread can move
+// 16-B (double2) words.  There is no shared fine-sized vector and no mask() indirection as in the
+// reference (GeometricMultigrid/include/domain.hpp:78-80); level l point (I,J) is the reference's
+// fine entry (2^l I, 2^l J).
+//
+// Arithmetic: every stencil formula is evaluated in the reference's source order with the
+// round-to-nearest intrinsics (__dmul_rn, __dadd_rn, __ddiv_rn ...), which nvcc never contracts
+// into FMAs.  The x86-64 reference build contains no FMA either, so sweeps, residuals and grid
+// transfers are bit-identical to the reference, not merely within 1e-12.  The kernels are
+// HBM-bound (24 B per point against ~30 flops), so the unfused arithmetic is free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgb {
+
+struct LevelGeom {
+    int w;        // points per side of this level (global)          domain.hpp:49 width
+    int rows;     // rows owned by this rank
+    int row0;     // global index of the first owned row
+    int pitch;    // doubles per stored row (multiple of 16)
+    double diag;  // 4*alpha/k, k = (h*2^l)^2                        linear_system.hpp:27-28
+    double off;   // -alpha/k                                        linear_system.hpp:38
+};
+
+constexpr int kTPB = 128;      // threads per CTA in the marching kernels: 256 columns per CTA
+constexpr int kRowsPerCta = 32;
+
+// ---- reference arithmetic, never contracted ------------------------------------------------
+// solvers.hpp:33-48 / 64-83: sum = off*up + off*left + off*right + off*down (that order, from 0);
+// u = (b - sum) / diag
+__device__ __forceinline__ double smooth_point(double b, double up, double left, double right,
+                                               double down, double off, double diag)
+{
+    double sum = __dmul_rn(off, up);
+    sum = __dadd_rn(sum, __dmul_rn(off, left));
+    sum = __dadd_rn(sum, __dmul_rn(off, right));
+    sum = __dadd_rn(sum, __dmul_rn(off, down));
+    return __ddiv_rn(__dsub_rn(b, sum), diag);
+}
+// solvers.hpp:257-296: sum over up,left,centre,right,down; r = b - sum
+__device__ __forceinline__ double resid_point(double b, double up, double left, double c,
+                                              double right, double down, double off, double diag)
+{
+    double sum = __dmul_rn(off, up);
+    sum = __dadd_rn(sum, __dmul_rn(off, left));
+    sum = __dadd_rn(sum, __dmul_rn(diag, c));
+    sum = __dadd_rn(sum, __dmul_rn(off, right));
+    sum = __dadd_rn(sum, __dmul_rn(off, down));
+    return __dsub_rn(b, sum);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the CTA, result valid in thread 0.  `red` holds >= blockDim.x/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.;
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        t = lane < nw ? red[lane] : 0.;
+        t = warp_sum(t);
+    }
+    __syncthreads();
+    return t;
+}
+
+// ---- marching frame ------------------------------------------------------------------------
+// A thread owns two adjacent columns (one double2) and marches down kRowsPerCta rows with the
+// rows i-1, i, i+1 in registers, so every row of u is requested from L2/HBM once per CTA
+// (plus one halo row at each end of the chunk).  Left/right neighbours come from the adjacent
+// lanes by shuffle; only the two edge lanes of a warp issue an extra scalar load.
+struct March {
+    int j0, jl, lane, i0, i1;
+    bool has0, has1;
+    __device__ __forceinline__ March(const LevelGeom &g)
+    {
+        j0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+        lane = threadIdx.x & 31;
+        jl = min(j0, g.pitch - 2);           // clamped column for loads of idle threads
+        has0 = j0 < g.w;
+        has1 = j0 + 1 < g.w;
+        i0 = blockIdx.y * kRowsPerCta;
+        i1 = min(i0 + kRowsPerCta, g.rows);
+    }
+    // left neighbour of column j0 and right neighbour of column j0+1 on the row held in `c`
+    __device__ __forceinline__ void sides(const LevelGeom &g, const double *row, double2 c,
+                                          double &left, double &right) const
+    {
+        left = __shfl_up_sync(0xffffffffu, c.y, 1);
+        right = __shfl_down_sync(0xffffffffu, c.x, 1);
+        if (lane == 0) left = (j0 > 0 && has0) ? row[j0 - 1] : 0.;
+        if (lane == 31) right = (j0 + 2 < g.w) ? row[j0 + 2] : 0.;
+    }
+};
+
+__device__ __forceinline__ bool on_bdry(const LevelGeom &g, int gi, int j)
+{
+    return gi == 0 || gi == g.w - 1 || j == 0 || j == g.w - 1;      // domain.cpp:20-23
+}
+
+// ---- Jacobi sweep, out of place (solvers.hpp:64-83; the reference writes `temp` then swaps) --
+__global__ void __launch_bounds__(kTPB)
+k_jacobi(LevelGeom g, const double *__restrict__ u, const double *__restrict__ b, double *__restrict__ out)
+{
+    March m(g);
+    if (m.i0 >= g.rows) return;
+    const size_t P = g.pitch;
+    const double *ur = u + (size_t)m.i0 * P;
+    double2 up = ld2(ur - P + m.jl), ce = ld2(ur + m.jl);
+#pragma unroll 4
+    for (int i = m.i0; i < m.i1; ++i, ur += P) {
+        double2 dn = ld2(ur + P + m.jl);
+        double2 bb = ld2(b + (size_t)i * P + m.jl);
+        double left, right;
+        m.sides(g, ur, ce, left, right);
+        const int gi = g.row0 + i;
+        double2 o;
+        o.x = on_bdry(g, gi, m.j0) ? bb.x : smooth_point(bb.x, up.x, left, ce.y, dn.x, g.off, g.diag);
+        o.y = on_bdry(g, gi, m.j0 + 1) ? bb.y : smooth_point(bb.y, up.y, ce.x, right, dn.y, g.off, g.diag);
+        if (m.has1) st2(out + (size_t)i * P + m.j0, o);
+        else if (m.has0) out[(size_t)i * P + m.j0] = o.x;
+        up = ce; ce = dn;
+    }
+}
+
+// ---- red-black Gauss-Seidel, one colour, in place ---------------------------------------------
+// colour of (gi, j) = (gi + j) & 1 with gi the GLOBAL row: slabs agree on the colouring.
+// All four neighbours of a point have the other colour and are not written by this launch.
+__global__ void __launch_bounds__(kTPB)
+k_rbgs_colour(LevelGeom g, double *u, const double *__restrict__ b, int colour)
+{
+    March m(g);
+    if (m.i0 >= g.rows) return;
+    const size_t P = g.pitch;
+    double *ur = u + (size_t)m.i0 * P;
+    double2 up = ld2(ur - P + m.jl), ce = ld2(ur + m.jl);
+#pragma unroll 2
+    for (int i = m.i0; i < m.i1; ++i, ur += P) {
+        double2 dn = ld2(ur + P + m.jl);
+        double2 bb = ld2(b + (size_t)i * P + m.jl);
+        double left, right;
+        m.sides(g, ur, ce, left, right);
+        const int gi = g.row0 + i;
+        double2 o = ce;
+        if (((gi + colour) & 1) == 0) {       // column j0 (even) has this colour
+            o.x = on_bdry(g, gi, m.j0) ? bb.x : smooth_point(bb.x, up.x, left, ce.y, dn.x, g.off, g.diag);
+            if (m.has0) ur[m.j0] = o.x;
+        } else {
+            o.y = on_bdry(g, gi, m.j0 + 1) ? bb.y : smooth_point(bb.y, up.y, ce.x, right, dn.y, g.off, g.diag);
+            if (m.has1) ur[m.j0 + 1] = o.y;
+        }
+        up = o; ce = dn;
+    }
+}
+
+// ---- residual (solvers.hpp:257-296) -------------------------------------------------------------
+// r = b - A u on every owned point; optionally stored; sum r^2 per CTA -> partial[cta]
+template <bool STORE>
+__global__ void __launch_bounds__(kTPB)
+k_residual(LevelGeom g, const double *__restrict__ u, const double *__restrict__ b,
+           double *__restrict__ r, double *__restrict__ partial)
+{
+    __shared__ double red[kTPB / 32];
+    March m(g);
+    double acc = 0.;
+    if (m.i0 < g.rows) {
+        const size_t P = g.pitch;
+        const double *ur = u + (size_t)m.i0 * P;
+        double2 up = ld2(ur - P + m.jl), ce = ld2(ur + m.jl);
+#pragma unroll 4
+        for (int i = m.i0; i < m.i1; ++i, ur += P) {
+            double2 dn = ld2(ur + P + m.jl);
+            double2 bb = ld2(b + (size_t)i * P + m.jl);
+            double left, right;
+            m.sides(g, ur, ce, left, right);
+            const int gi = g.row0 + i;
+            double2 o;
+            // boundary rows are identity rows: sum = 1*u (solvers.hpp:265-266)
+            o.x = on_bdry(g, gi, m.j0) ? __dsub_rn(bb.x, ce.x)
+                                       : resid_point(bb.x, up.x, left, ce.x, ce.y, dn.x, g.off, g.diag);
+            o.y = on_bdry(g, gi, m.j0 + 1) ? __dsub_rn(bb.y, ce.y)
+                                           : resid_point(bb.y, up.y, ce.x, ce.y, right, dn.y, g.off, g.diag);
+            if (STORE) {
+                if (m.has1) st2(r + (size_t)i * P + m.j0, o);
+                else if (m.has0) r[(size_t)i * P + m.j0] = o.x;
+            }
+            if (m.has0) acc += o.x * o.x;
+            if (m.has1) acc += o.y * o.y;
+            up = ce; ce = dn;
+        }
+    }
+    double t = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+}
+
+// sum of squares of a level vector (solvers.hpp:244-254)
+__global__ void __launch_bounds__(kTPB)
+k_sumsq(LevelGeom g, const double *__restrict__ v, double *__restrict__ partial)
+{
+    __shared__ double red[kTPB / 32];
+    March m(g);
+    double acc = 0.;
+    for (int i = m.i0; i < m.i1; ++i) {
+        double2 x = ld2(v + (size_t)i * g.pitch + m.jl);
+        if (m.has0) acc += x.x * x.x;
+        if (m.has1) acc += x.y * x.y;
+    }
+    double t = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+}
+
+// deterministic second stage: one CTA adds the per-CTA partials in a fixed order.
+// out[0] = sum (or out[0] += sum when accumulate).
+__global__ void __launch_bounds__(1024)
+k_reduce_partials(const double *__restrict__ partial, int n, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    double t = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+// ---- restriction of the residual to the next coarser level ------------------------------------------
+// MODE 0: injection (what the reference's mask() read amounts to), scale = 1 or 0.5 on interior
+//         points (half injection); boundary points are copied unscaled.
+// MODE 2: full weighting [1 2 1; 2 4 2; 1 2 1]/16 on interior points, boundary points copied.
+// One thread per coarse point; gc = coarse level, gf = fine level (gf.w = 2*gc.w - 1).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_restrict(LevelGeom gf, LevelGeom gc, const double *__restrict__ rf, double *__restrict__ rc, double scale)
+{
+    int J = blockIdx.x * blockDim.x + threadIdx.x;
+    int I = blockIdx.y;                         // local coarse row
+    if (J >= gc.w || I >= gc.rows) return;
+    int gI = gc.row0 + I;
+    int fi = 2 * gI - gf.row0;                  // local fine row of the coincident point
+    const size_t P = gf.pitch;
+    const double *c = rf + (size_t)fi * P + 2 * J;
+    double v;
+    if (on_bdry(gc, gI, J)) v = c[0];
+    else if (MODE == 0) v = __dmul_rn(scale, c[0]);
+    else {
+        double edge = __dadd_rn(__dadd_rn(__dadd_rn(c[-(ptrdiff_t)P], c[-1]), c[1]), c[P]);
+        double corner = __dadd_rn(__dadd_rn(__dadd_rn(c[-(ptrdiff_t)P - 1], c[-(ptrdiff_t)P + 1]), c[P - 1]), c[P + 1]);
+        v = __dadd_rn(__dadd_rn(__dmul_rn(0.25, c[0]), __dmul_rn(0.125, edge)), __dmul_rn(0.0625, corner));
+    }
+    rc[(size_t)I * gc.pitch + J] = v;
+}
+
+// ---- bilinear prolongation (multigrid.cpp:3-27), coarse level gc -> fine level gf, overwrite ---
+// even row, even col: copy; odd row, even col: 0.5*(N+S); even row, odd col: 0.5*(W+E) of the
+// copied values; odd row, odd col: 0.5*(vm_W + vm_E) with vm = the vertical midpoints -- the same
+// two-stage order as the reference's in-place loops, hence bit-identical.
+__global__ void __launch_bounds__(kTPB)
+k_prolong(LevelGeom gc, LevelGeom gf, const double *__restrict__ ec, double *__restrict__ ef)
+{
+    int j0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // even fine column
+    int i = blockIdx.y * 4;                                   // 4 fine rows per CTA row-group
+    if (j0 >= gf.w) return;
+    const int J = j0 >> 1;
+    const bool has1 = j0 + 1 < gf.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k, ++i) {
+        if (i >= gf.rows) return;
+        int gi = gf.row0 + i;
+        int I = (gi >> 1) - gc.row0;                          // local coarse row (north)
+        const double *cn = ec + (size_t)I * gc.pitch + J;
+        double a, c;                                          // values at fine cols j0 and j0+2
+        if ((gi & 1) == 0) { a = cn[0]; c = has1 ? cn[1] : 0.; }
+        else {
+            const double *cs = cn + gc.pitch;
+            a = __dmul_rn(0.5, __dadd_rn(cn[0], cs[0]));
+            c = has1 ? __dmul_rn(0.5, __dadd_rn(cn[1], cs[1])) : 0.;
+        }
+        double *o = ef + (size_t)i * gf.pitch + j0;
+        if (has1) st2(o, make_double2(a, __dmul_rn(0.5, __dadd_rn(a, c))));
+        else o[0] = a;
+    }
+}
+
+// ---- u += e (multigrid.hpp:141-144) -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_axpy_rows(LevelGeom g, double *__restrict__ u, const double *__restrict__ e)
+{
+    int j0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (j0 >= g.pitch) return;
+    for (int i = blockIdx.y; i < g.rows; i += gridDim.y) {
+        size_t o = (size_t)i * g.pitch + j0;
+        double2 a = ld2(u + o), b = ld2(e + o);
+        a.x = __dadd_rn(a.x, b.x); a.y = __dadd_rn(a.y, b.y);
+        st2(u + o, a);
+    }
+}
+
+// ---- lexicographic Gauss-Seidel, exact order (solvers.hpp:33-48) -------------------------------------
+// Parity mode.  One CTA sweeps a band of <= 1024 rows as a skewed wavefront: thread t owns row
+// band0+t and at step s updates column s-t, so (i-1,j) and (i,j-1) are already new and (i,j+1),
+// (i+1,j) still old -- exactly the lexicographic dependency pattern.  Bands run as consecutive
+// launches.  The result is bit-identical to the reference's serial loop.
+__global__ void __launch_bounds__(1024)
+k_gs_lex_band(LevelGeom g, double *u, const double *__restrict__ b, int band0, int band_rows)
+{
+    const int t = threadIdx.x;
+    const int i = band0 + t;
+    const bool rowok = t < band_rows;
+    const int gi = g.row0 + i;
+    const bool brow = gi == 0 || gi == g.w - 1;
+    const size_t P = g.pitch;
+    double *ur = u + (size_t)i * P;
+    const double *br = b + (size_t)i * P;
+    double left = 0.;
+    const int nsteps = g.w + band_rows - 1;
+    for (int s = 0; s < nsteps; ++s) {
+        const int j = s - t;
+        if (rowok && j >= 0 && j < g.w) {
+            double bv = br[j], nv;
+            if (brow || j == 0 || j == g.w - 1) nv = bv;      // (b - 0) / 1
+            else {
+                double up = ur[j - (ptrdiff_t)P];
+                nv = smooth_point(bv, up, left, ur[j + 1], ur[j + P], g.off, g.diag);
+            }
+            ur[j] = nv;
+            left = nv;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- rhs sampling on device (linear_system.hpp:85-92 with utilities.cpp:138-147) -------------------
+__global__ void __launch_bounds__(256)
+k_sample_rhs(LevelGeom g, double *__restrict__ b, double length, int test)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= g.w || i >= g.rows) return;
+    int gi = g.row0 + i;
+    double h = length / (double)(g.w - 1);
+    double x = (double)j * h, y = length - (double)gi * h;
+    bool bd = on_bdry(g, gi, j);
+    double v;
+    if (test == 1) { double e = exp(x) * exp(-2.0 * y); v = bd ? e : -5.0 * e; }
+    else if (test == 2) {
+        double rr = sqrt(x * x + y * y);
+        v = bd ? sin(30. * rr) : (rr != 0.0 ? -30. * (cos(30. * rr) / rr - 30. * sin(30. * rr)) : 0.0);
+    } else v = bd ? 0. : 1.;
+    b[(size_t)i * g.pitch + j] = v;
+}
+
+}  // namespace mgb
