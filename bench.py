@@ -47,10 +47,17 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def wait_started(self, timeout=5.0):
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -198,16 +205,17 @@ def main():
     timer = Timer()
     st = g.stream()
     # ---- device-resident throughput ------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
     g.run_cycles(args.warmup)
     g.sync(); barrier()
     g.reset_stats()
-    sampler = ClockSampler(local) if rank == 0 else None
     timer.start(st)
     g.run_cycles(args.steps, want_relres=False)
     timer.stop(st)
     ms = timer.elapsed_ms()
     g.sync(); barrier()
-    clocks = sampler.stop() if sampler else None
     stats = g.stats()
     relres = g.run_cycles(0)
     if dist is not None:
@@ -222,19 +230,23 @@ def main():
     peak, peak_src = peaks()
     reps = 10
     kind = cfg.smoother if cfg.smoother != G.GS_LEX else G.GS_RB
-    g.smooth(0, kind, sweeps=2, sol=G.VEC_E, rhs=G.VEC_R)
+    group = cfg.nu if (kind == G.GS_RB and cfg.rb_fused) else 1
+    g.smooth(0, kind, sweeps=2 * group, sol=G.VEC_E, rhs=G.VEC_R)
     g.sync()
     g.reset_stats()
     timer.start(st)
-    g.smooth(0, kind, sweeps=reps, sol=G.VEC_E, rhs=G.VEC_R)
+    g.smooth(0, kind, sweeps=reps * group, sol=G.VEC_E, rhs=G.VEC_R)
     timer.stop(st)
     kms = timer.elapsed_ms()
+    clocks = sampler.stop() if sampler else None
     ks = g.stats()
     rows0 = g.rows(0)[1]
     launches = ks["kernel_launches"]
     alg_bytes = ks["bytes_algorithmic"] / launches           # per launch (12 B/pt per colour pass, 24 B/pt Jacobi)
     achieved = alg_bytes / (kms * 1e-3 / launches) / 1e9
-    kname = {G.GS_RB: "k_rbgs_colour (one colour pass, 12 B/pt)", G.JACOBI: "k_jacobi (24 B/pt)"}[kind]
+    kname = {G.GS_RB: (f"k_rb_stream<{2 * group}> ({group} fused red-black sweeps per launch; algorithmic bytes "
+                       f"counted as ONE sweep's 24 B/pt)") if cfg.rb_fused else "k_rbgs_colour (one colour pass, 12 B/pt)",
+             G.JACOBI: "k_jacobi (24 B/pt)"}[kind]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kname, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kms / launches,

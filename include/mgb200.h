@@ -71,7 +71,12 @@ typedef struct mgb_gmg_config {
     unsigned char nccl_id[128];   /* ncclUniqueId from mgb_nccl_unique_id(), same on all ranks */
     int tail_max_width;   /* levels with width <= this run inside the persistent coarse-tail kernel */
     int use_graph;        /* capture the static part of the cycle in a CUDA graph */
-    int reserved[8];
+    int rb_fast_arith;    /* red-black kernels: 0 = the reference's formula, unfused IEEE ops and a true
+                             division (bit-identical to the CPU statement of the same ordering);
+                             1 = u = b/diag + (sum of neighbours)/4 with FMA (a few ulp away) */
+    int rb_fused;         /* 1 = streaming temporally-blocked red-black kernel (all sweeps of a group in one
+                             pass over HBM); 0 = one launch per colour */
+    int reserved[6];
 } mgb_gmg_config;
 
 typedef struct mgb_gmg *mgb_gmg_t;

@@ -19,7 +19,8 @@ class GmgConfigStruct(C.Structure):
                 ("n_pre", C.c_int), ("nu", C.c_int), ("restriction", C.c_int),
                 ("coarse_tol", C.c_double), ("coarse_maxit", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
-                ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("reserved", C.c_int * 8)]
+                ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("rb_fast_arith", C.c_int),
+                ("rb_fused", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class GmgStatsStruct(C.Structure):

@@ -363,4 +363,131 @@ k_sample_rhs(LevelGeom g, double *__restrict__ b, double length, int test)
     b[(size_t)i * g.pitch + j] = v;
 }
 
+
+// =====================================================================================================
+// Streaming red-black Gauss-Seidel with temporal blocking: S half-sweeps (S/2 full sweeps) in ONE pass
+// over HBM -- 24 B per point for the whole group of sweeps instead of 24 B per sweep.
+//
+// A CTA owns a strip of OW = TW - 2S columns (plus S halo columns on each side, recomputed
+// redundantly) and marches down a chunk of rows.  Shared memory holds a ring of 2S+3 rows of u
+// and of the rhs.  When row i arrives, half-sweep s (s = 1..S; odd s = red, even s = black) is
+// applied to row i-2s.  With a lag of TWO rows per half-sweep all S updates of a step read only
+// values produced in earlier steps, so one __syncthreads per row suffices and the S updates of a
+// thread are independent (ILP).  Row i-2S is final after the step and is written out.
+// Red-black GS does not depend on the traversal order inside a colour, so the result is identical
+// -- bit for bit with EXACT arithmetic -- to S/2 plain red-then-black sweeps.
+//
+// Shared-memory rows are stored de-interleaved (even columns | odd columns) so that a half-sweep,
+// which touches every other point, reads and writes CONTIGUOUS doubles (no bank conflicts).
+// Input and output arrays differ (neighbouring CTAs re-read the halo from the input).
+// =====================================================================================================
+constexpr int kStreamTW = 256;            // tile columns held in shared memory
+constexpr int kStreamNT = kStreamTW / 2;  // threads: one per column pair
+constexpr int kStreamPF = 4;              // rows in flight from HBM per thread (register staged)
+
+template <int S>
+constexpr int stream_smem_bytes() { return (2 * S + 3) * kStreamTW * 2 * (int)sizeof(double); }
+
+// fast arithmetic: off/diag == -1/4 exactly, so u = b/diag + (up+down+left+right)/4
+template <bool EXACT>
+__device__ __forceinline__ double rb_point(double b, double up, double left, double right, double down,
+                                           double off, double diag, double inv_diag)
+{
+    if (EXACT) return smooth_point(b, up, left, right, down, off, diag);
+    return fma(b, inv_diag, 0.25 * ((up + down) + (left + right)));
+}
+
+template <int S, bool EXACT>
+__global__ void __launch_bounds__(kStreamNT)
+k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
+            double *__restrict__ uout, int rows_per_chunk)
+{
+    constexpr int TW = kStreamTW, NT = kStreamNT, PF = kStreamPF, H = TW / 2;
+    constexpr int WR = 2 * S + 3;
+    extern __shared__ double smem[];
+    double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
+    double *sb = smem + WR * TW;
+
+    const int t = threadIdx.x;
+    const int OW = TW - 2 * S;
+    const int jbase = blockIdx.x * OW - S;           // global column of tile column 0 (even)
+    const int j0 = jbase + 2 * t;                    // this thread's even column
+    const int jl = min(max(j0, 0), g.pitch - 2);     // clamped for loads
+    const int i0 = blockIdx.y * rows_per_chunk;
+    const int i1 = min(i0 + rows_per_chunk, g.rows);
+    if (i0 >= g.rows) return;
+    const bool top_is_domain = (g.row0 == 0), bot_is_domain = (g.row0 + g.rows == g.w);
+    const int lo = top_is_domain ? 0 : -S, hi = bot_is_domain ? g.rows - 1 : g.rows - 1 + S;
+    const int ifirst = max(i0 - S, lo), ilast = min(i1 - 1 + S, hi);
+    const bool first_is_bdry = (g.row0 + ifirst == 0), last_is_bdry = (g.row0 + ilast == g.w - 1);
+    const size_t P = g.pitch;
+    const double inv_diag = 1.0 / g.diag;
+    const bool own = (2 * t >= S) && (2 * t < TW - S) && (j0 < g.w) && (j0 >= 0);
+
+    double2 pu[PF], pb[PF];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        int r = min(ifirst + p, ilast);
+        pu[p] = ld2(uin + (ptrdiff_t)r * (ptrdiff_t)P + jl);
+        pb[p] = ld2(b + (ptrdiff_t)r * (ptrdiff_t)P + jl);
+    }
+    const int ksteps = (i1 - 1 + 2 * S) - ifirst + 1;
+    int base = 0;                                    // ring slot of the row loaded at this step
+    for (int k0 = 0; k0 < ksteps; k0 += PF) {
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int k = k0 + p;
+            if (k >= ksteps) break;
+            const int i = ifirst + k;                // row arriving at this step
+            // stage the row that was requested PF steps ago, request the one PF steps ahead
+            su[base * TW + t] = pu[p].x; su[base * TW + H + t] = pu[p].y;
+            sb[base * TW + t] = pb[p].x; sb[base * TW + H + t] = pb[p].y;
+            {
+                int r = min(i + PF, ilast);
+                pu[p] = ld2(uin + (ptrdiff_t)r * (ptrdiff_t)P + jl);
+                pb[p] = ld2(b + (ptrdiff_t)r * (ptrdiff_t)P + jl);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 1; s <= S; ++s) {
+                const int r = i - 2 * s;
+                const int vlo = first_is_bdry ? ifirst : ifirst + s;
+                const int vhi = last_is_bdry ? ilast : ilast - s;
+                if (r < vlo || r > vhi) continue;
+                int sl = base - 2 * s; if (sl < 0) sl += WR;
+                int su_ = sl - 1; if (su_ < 0) su_ += WR;     // row r-1
+                int sd_ = sl + 1; if (sd_ >= WR) sd_ -= WR;   // row r+1
+                const int gi = g.row0 + r;
+                const int which = (gi + (s - 1)) & 1;          // 0: even column of the pair, 1: odd
+                const int j = j0 + which;
+                const bool edge_ok = which ? (t < NT - 1) : (t > 0);
+                if (!edge_ok || j < 0 || j >= g.w) continue;
+                const int c = which * H + t;                   // this point inside a de-interleaved row
+                const int o = (1 - which) * H + t;             // other-colour half row, same pair
+                const double bv = sb[sl * TW + c];
+                double nv;
+                if (on_bdry(g, gi, j)) nv = bv;
+                else {
+                    const double up = su[su_ * TW + c], down = su[sd_ * TW + c];
+                    // even column 2t: left = odd[t-1], right = odd[t]; odd column 2t+1: left = even[t], right = even[t+1]
+                    const double left = su[sl * TW + o - (1 - which)];
+                    const double right = su[sl * TW + o + which];
+                    nv = rb_point<EXACT>(bv, up, left, right, down, g.off, g.diag, inv_diag);
+                }
+                su[sl * TW + c] = nv;
+            }
+            {
+                const int r = i - 2 * S;                       // final after this step
+                if (r >= i0 && r < i1 && own) {
+                    int sl = base - 2 * S; if (sl < 0) sl += WR;
+                    double2 o2 = make_double2(su[sl * TW + t], su[sl * TW + H + t]);
+                    double *dst = uout + (ptrdiff_t)r * (ptrdiff_t)P + j0;
+                    if (j0 + 1 < g.w) st2(dst, o2); else dst[0] = o2.x;
+                }
+            }
+            if (++base == WR) base = 0;
+        }
+    }
+}
+
 }  // namespace mgb

@@ -51,6 +51,7 @@ struct mgb_gmg {
     double *h_scal = nullptr;         // pinned mirror
     double norm_f = 0.;               // sum f^2 on the fine grid (Residual ctor, solvers.hpp:237-242)
     bool have_rhs = false;
+    int n_sm = 148;
     mgb_gmg_stats stats{};
 
     double **vec(int level, int which)
@@ -100,6 +101,42 @@ int read_scalar(mgb_gmg *h, int slot, double *out)
     return MGB_OK;
 }
 
+template <int S, bool EXACT>
+int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out)
+{
+    static bool attr_set = false;
+    constexpr int smem = mgb::stream_smem_bytes<S>();
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int OW = mgb::kStreamTW - 2 * S;
+    const int nx = (g.w + OW - 1) / OW;
+    const int occ = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));
+    const int slots = h->n_sm * occ;
+    int ny = std::max(1, (slots + nx / 2) / nx);
+    ny = std::min(ny, std::max(1, g.rows / (8 * S)));
+    const int rc = (g.rows + ny - 1) / ny;
+    ny = (g.rows + rc - 1) / rc;
+    mgb::k_rb_stream<S, EXACT><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc);
+    count(h, 24. * npts(g));
+    CK(cudaGetLastError());
+    return MGB_OK;
+}
+
+// `sweeps` (1, 2 or 5) full red-black sweeps in one pass: in -> out
+int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out)
+{
+    const LevelGeom &g = h->lv[level].g;
+    const bool ex = !h->cfg.rb_fast_arith;
+    switch (sweeps) {
+    case 1: return ex ? launch_rb_stream_t<2, true>(h, g, in, rhs, out) : launch_rb_stream_t<2, false>(h, g, in, rhs, out);
+    case 2: return ex ? launch_rb_stream_t<4, true>(h, g, in, rhs, out) : launch_rb_stream_t<4, false>(h, g, in, rhs, out);
+    case 5: return ex ? launch_rb_stream_t<10, true>(h, g, in, rhs, out) : launch_rb_stream_t<10, false>(h, g, in, rhs, out);
+    default: return fail(MGB_ERR_ARG, "unsupported sweep group");
+    }
+}
+
 int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs)
 {
     Level &L = h->lv[level];
@@ -111,6 +148,14 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
             mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, L.t);
             count(h, 24. * npts(g));
             std::swap(*sol, L.t);                                   // solvers.hpp:83 sol.swap(temp)
+            if (int rc = halo_exchange(h, level, *sol)) return rc;
+        } else if (kind == MGB_SMOOTH_GS_RB && h->cfg.rb_fused) {
+            // group the remaining sweeps: 5, 2 or 1 full sweeps per pass over HBM
+            const int left = sweeps - s;
+            const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
+            if (int rc = launch_rb_stream(h, level, grp, *sol, rhs, L.t)) return rc;
+            std::swap(*sol, L.t);
+            s += grp - 1;
             if (int rc = halo_exchange(h, level, *sol)) return rc;
         } else if (kind == MGB_SMOOTH_GS_RB) {
             for (int colour = 0; colour < 2; ++colour) {
@@ -267,6 +312,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
     c->tail_max_width = 0; c->use_graph = 0;
+    c->rb_fast_arith = 0; c->rb_fused = 1;
 }
 
 void mgb_gmg_config_fast(mgb_gmg_config *c)
@@ -275,6 +321,7 @@ void mgb_gmg_config_fast(mgb_gmg_config *c)
     c->smoother = MGB_SMOOTH_GS_RB;
     c->pre_smoother = MGB_SMOOTH_GS_RB;
     c->restriction = MGB_RESTRICT_FULL_WEIGHTING;
+    c->rb_fast_arith = 1;
 }
 
 int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
@@ -299,6 +346,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     mgb_gmg *h = new mgb_gmg();
     h->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     h->lv.resize(L);
     size_t w = N;
     const double m_h = cfg->length / (double)(N - 1);                     // domain.cpp:5

@@ -51,6 +51,42 @@ def test_sweeps_bit_exact_per_level(orc, N, L, alpha, kind):
             assert np.array_equal(got, strided(ref, N, s)), (level, np.abs(got - strided(ref, N, s)).max())
 
 
+@pytest.mark.parametrize("N,L", [(33, 3), (257, 2), (513, 3), (1025, 1), (2049, 1)])
+@pytest.mark.parametrize("sweeps", [1, 2, 5, 8])
+@pytest.mark.parametrize("fused", [0, 1])
+def test_red_black_fused_and_unfused_bit_exact(orc, N, L, sweeps, fused):
+    """the streaming temporally-blocked kernel (1, 2 or 5 sweeps per pass over HBM) and the
+    one-launch-per-colour kernels both equal the CPU statement of red-black GS, bit for bit"""
+    rng = np.random.default_rng(N + sweeps)
+    u0, b0 = rng.standard_normal(N * N), rng.standard_normal(N * N)
+    with Gmg(GmgConfig(n=N, levels=L, alpha=0.7, rb_fused=fused)) as g:
+        for level in range(L):
+            s = 2 ** level
+            g.set_level(level, G.VEC_E, strided(u0, N, s))
+            g.set_level(level, G.VEC_R, strided(b0, N, s))
+            g.smooth(level, G.GS_RB, sweeps=sweeps)
+            got = g.get_level(level, G.VEC_E)
+            ref = u0.copy()
+            for _ in range(sweeps):
+                orc.sweep(oracle.RBGS, N, W, 0.7, level, ref, b0)
+            assert np.array_equal(got, strided(ref, N, s)), (level, np.abs(got - strided(ref, N, s)).max())
+
+
+def test_red_black_fast_arithmetic_within_ulps(orc):
+    """rb_fast_arith: u = b/diag + sum/4 with FMA -- a few ulp from the reference formula"""
+    N, sweeps = 513, 5
+    rng = np.random.default_rng(3)
+    u0, b0 = rng.standard_normal(N * N), rng.standard_normal(N * N)
+    with Gmg(GmgConfig(n=N, levels=1, rb_fast_arith=1)) as g:
+        g.set_level(0, G.VEC_E, u0.reshape(N, N)); g.set_level(0, G.VEC_R, b0.reshape(N, N))
+        g.smooth(0, G.GS_RB, sweeps=sweeps)
+        got = g.get_level(0, G.VEC_E).reshape(-1)
+    ref = u0.copy()
+    for _ in range(sweeps):
+        orc.sweep(oracle.RBGS, N, W, 1.0, 0, ref, b0)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("N,L", [(33, 4), (257, 5), (1025, 3)])
 def test_residual_and_norms(orc, N, L):
     rng = np.random.default_rng(N)
