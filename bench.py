@@ -244,8 +244,8 @@ def main():
     launches = ks["kernel_launches"]
     alg_bytes = ks["bytes_algorithmic"] / launches           # per launch (12 B/pt per colour pass, 24 B/pt Jacobi)
     achieved = alg_bytes / (kms * 1e-3 / launches) / 1e9
-    kname = {G.GS_RB: (f"k_rb_stream<{2 * group}> ({group} fused red-black sweeps per launch; algorithmic bytes "
-                       f"counted as ONE sweep's 24 B/pt)") if cfg.rb_fused else "k_rbgs_colour (one colour pass, 12 B/pt)",
+    kname = {G.GS_RB: (f"k_rb_stream<{2 * group}> ({group} fused red-black sweeps per launch = {group} x 24 B/pt "
+                       f"algorithmic; the launch itself moves ~24 B/pt through HBM)") if cfg.rb_fused else "k_rbgs_colour (one colour pass, 12 B/pt)",
              G.JACOBI: "k_jacobi (24 B/pt)"}[kind]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kname, "peak_source": peak_src,

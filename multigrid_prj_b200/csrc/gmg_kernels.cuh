@@ -423,6 +423,13 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const size_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;
     const bool own = (2 * t >= S) && (2 * t < TW - S) && (j0 < g.w) && (j0 >= 0);
+    // per-thread column predicates for the even (0) and odd (1) column of the pair:
+    // may it be updated inside this tile, and is it a Dirichlet column
+    const bool can0 = (t > 0) && (j0 >= 0) && (j0 < g.w);
+    const bool can1 = (t < NT - 1) && (j0 + 1 >= 0) && (j0 + 1 < g.w);
+    const bool bc0 = (j0 == 0) || (j0 == g.w - 1);
+    const bool bc1 = (j0 + 1 == 0) || (j0 + 1 == g.w - 1);
+    const int glast = g.w - 1 - g.row0;              // local index of the global last row
 
     double2 pu[PF], pb[PF];
 #pragma unroll
@@ -448,41 +455,48 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
                 pb[p] = ld2(b + (ptrdiff_t)r * (ptrdiff_t)P + jl);
             }
             __syncthreads();
+            // The S half-sweep updates of this step are mutually independent (see above): read
+            // all operands first, then compute, then write, so the shared-memory latency is paid once.
+            double bv[S], up[S], dn[S], lf[S], rt[S];
+            bool act[S], isb[S];
+            int dst[S];
+            const int par = (g.row0 + i) & 1;        // parity of the arriving row
 #pragma unroll
             for (int s = 1; s <= S; ++s) {
                 const int r = i - 2 * s;
                 const int vlo = first_is_bdry ? ifirst : ifirst + s;
                 const int vhi = last_is_bdry ? ilast : ilast - s;
-                if (r < vlo || r > vhi) continue;
                 int sl = base - 2 * s; if (sl < 0) sl += WR;
-                int su_ = sl - 1; if (su_ < 0) su_ += WR;     // row r-1
-                int sd_ = sl + 1; if (sd_ >= WR) sd_ -= WR;   // row r+1
-                const int gi = g.row0 + r;
-                const int which = (gi + (s - 1)) & 1;          // 0: even column of the pair, 1: odd
-                const int j = j0 + which;
-                const bool edge_ok = which ? (t < NT - 1) : (t > 0);
-                if (!edge_ok || j < 0 || j >= g.w) continue;
+                int sup = sl - 1; if (sup < 0) sup += WR;      // row r-1
+                int sdn = sl + 1; if (sdn >= WR) sdn -= WR;    // row r+1
+                const int which = (par + (s - 1)) & 1;         // rows i-2s share the parity of row i
                 const int c = which * H + t;                   // this point inside a de-interleaved row
                 const int o = (1 - which) * H + t;             // other-colour half row, same pair
-                const double bv = sb[sl * TW + c];
-                double nv;
-                if (on_bdry(g, gi, j)) nv = bv;
-                else {
-                    const double up = su[su_ * TW + c], down = su[sd_ * TW + c];
+                act[s - 1] = (r >= vlo) && (r <= vhi) && (which ? can1 : can0);
+                isb[s - 1] = (which ? bc1 : bc0) || (r + g.row0 == 0) || (r == glast);
+                dst[s - 1] = sl * TW + c;
+                if (act[s - 1]) {
+                    bv[s - 1] = sb[sl * TW + c];
+                    up[s - 1] = su[sup * TW + c];
+                    dn[s - 1] = su[sdn * TW + c];
                     // even column 2t: left = odd[t-1], right = odd[t]; odd column 2t+1: left = even[t], right = even[t+1]
-                    const double left = su[sl * TW + o - (1 - which)];
-                    const double right = su[sl * TW + o + which];
-                    nv = rb_point<EXACT>(bv, up, left, right, down, g.off, g.diag, inv_diag);
+                    lf[s - 1] = su[sl * TW + o - (1 - which)];
+                    rt[s - 1] = su[sl * TW + o + which];
                 }
-                su[sl * TW + c] = nv;
             }
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (act[s]) {
+                    double nv = rb_point<EXACT>(bv[s], up[s], lf[s], rt[s], dn[s], g.off, g.diag, inv_diag);
+                    su[dst[s]] = isb[s] ? bv[s] : nv;
+                }
             {
                 const int r = i - 2 * S;                       // final after this step
                 if (r >= i0 && r < i1 && own) {
                     int sl = base - 2 * S; if (sl < 0) sl += WR;
                     double2 o2 = make_double2(su[sl * TW + t], su[sl * TW + H + t]);
-                    double *dst = uout + (ptrdiff_t)r * (ptrdiff_t)P + j0;
-                    if (j0 + 1 < g.w) st2(dst, o2); else dst[0] = o2.x;
+                    double *dstp = uout + (ptrdiff_t)r * (ptrdiff_t)P + j0;
+                    if (j0 + 1 < g.w) st2(dstp, o2); else dstp[0] = o2.x;
                 }
             }
             if (++base == WR) base = 0;

@@ -119,7 +119,7 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
     const int rc = (g.rows + ny - 1) / ny;
     ny = (g.rows + rc - 1) / rc;
     mgb::k_rb_stream<S, EXACT><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc);
-    count(h, 24. * npts(g));
+    count(h, 24. * (S / 2) * npts(g));     // 24 B per point per sweep, S/2 sweeps per launch
     CK(cudaGetLastError());
     return MGB_OK;
 }
