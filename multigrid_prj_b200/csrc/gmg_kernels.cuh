@@ -397,13 +397,75 @@ __device__ __forceinline__ double rb_point(double b, double up, double left, dou
     return fma(b, inv_diag, 0.25 * ((up + down) + (left + right)));
 }
 
+// One step of the stream: row i arrives in `nu`/`nb`; half-sweep s is applied to row i-2s.
+// The thread keeps ITS OWN column pair of the whole row window in registers (uw[d] = row i-d), so
+// up, down and the neighbour inside the pair never touch shared memory; only the neighbour that
+// belongs to the adjacent thread, and the rhs, are read from the ring, and the new value is
+// published to the ring for the adjacent threads.  3 shared-memory words per update instead of 6.
+// PAR = parity of the global row index of row i (static: the main loop is unrolled by 4 rows).
+template <int S, bool EXACT, int PAR, bool GUARD>
+__device__ __forceinline__ void rb_stream_step(
+    const LevelGeom &g, double2 (&uw)[2 * S + 2], double2 nu, double2 nb, double *su, double *sb, int base,
+    int i, int t, bool can0, bool can1, bool bc0, bool bc1, int ifirst, int ilast, bool first_is_bdry,
+    bool last_is_bdry, int glast, double inv_diag)
+{
+    constexpr int TW = kStreamTW, H = TW / 2, WR = 2 * S + 3;
+    // rotate the register window by one row and publish the arriving row
+#pragma unroll
+    for (int d = 2 * S + 1; d > 0; --d) uw[d] = uw[d - 1];
+    uw[0] = nu;
+    su[base * TW + t] = nu.x; su[base * TW + H + t] = nu.y;
+    sb[base * TW + t] = nb.x; sb[base * TW + H + t] = nb.y;
+    __syncthreads();
+    double bv[S], ob[S];
+    int off[S];
+#pragma unroll
+    for (int s = 1; s <= S; ++s) {
+        int sl = base - 2 * s; if (sl < 0) sl += WR;
+        constexpr int dummy = 0; (void)dummy;
+        const int which = (PAR + (s - 1)) & 1;        // rows i-2s have the parity of row i
+        off[s - 1] = sl * TW + which * H + t;
+        bv[s - 1] = sb[off[s - 1]];
+        // neighbour held by the adjacent thread: even column 2t -> odd[t-1]; odd column 2t+1 -> even[t+1]
+        const int nb_idx = sl * TW + (which ? (t + 1) : (H + t - 1));
+        const bool can = which ? can1 : can0;
+        ob[s - 1] = can ? su[nb_idx] : 0.;
+    }
+#pragma unroll
+    for (int s = 1; s <= S; ++s) {
+        const int which = (PAR + (s - 1)) & 1;
+        const int d = 2 * s;
+        const bool can = which ? can1 : can0;
+        bool act = can;
+        bool isb = which ? bc1 : bc0;
+        if (GUARD) {
+            const int r = i - d;
+            const int vlo = first_is_bdry ? ifirst : ifirst + s;
+            const int vhi = last_is_bdry ? ilast : ilast - s;
+            act = act && (r >= vlo) && (r <= vhi);
+            isb = isb || (r + g.row0 == 0) || (r == glast);
+        }
+        const double up = which ? uw[d + 1].y : uw[d + 1].x;
+        const double dn = which ? uw[d - 1].y : uw[d - 1].x;
+        const double left = which ? uw[d].x : ob[s - 1];
+        const double right = which ? ob[s - 1] : uw[d].y;
+        double nv = rb_point<EXACT>(bv[s - 1], up, left, right, dn, g.off, g.diag, inv_diag);
+        nv = isb ? bv[s - 1] : nv;
+        if (act) {
+            if (which) uw[d].y = nv; else uw[d].x = nv;
+            su[off[s - 1]] = nv;
+        }
+    }
+}
+
 template <int S, bool EXACT>
 __global__ void __launch_bounds__(kStreamNT)
 k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
             double *__restrict__ uout, int rows_per_chunk)
 {
-    constexpr int TW = kStreamTW, NT = kStreamNT, PF = kStreamPF, H = TW / 2;
+    constexpr int TW = kStreamTW, NT = kStreamNT, PF = kStreamPF;
     constexpr int WR = 2 * S + 3;
+    static_assert(PF == 4, "the main loop is unrolled by 4 rows");
     extern __shared__ double smem[];
     double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
     double *sb = smem + WR * TW;
@@ -413,95 +475,67 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const int jbase = blockIdx.x * OW - S;           // global column of tile column 0 (even)
     const int j0 = jbase + 2 * t;                    // this thread's even column
     const int jl = min(max(j0, 0), g.pitch - 2);     // clamped for loads
-    const int i0 = blockIdx.y * rows_per_chunk;
+    const int i0 = blockIdx.y * rows_per_chunk;      // rows_per_chunk is even (host)
     const int i1 = min(i0 + rows_per_chunk, g.rows);
     if (i0 >= g.rows) return;
     const bool top_is_domain = (g.row0 == 0), bot_is_domain = (g.row0 + g.rows == g.w);
     const int lo = top_is_domain ? 0 : -S, hi = bot_is_domain ? g.rows - 1 : g.rows - 1 + S;
-    const int ifirst = max(i0 - S, lo), ilast = min(i1 - 1 + S, hi);
+    const int ifirst = max(i0 - S, lo), ilast = min(i1 - 1 + S, hi);   // row0 + ifirst is even
     const bool first_is_bdry = (g.row0 + ifirst == 0), last_is_bdry = (g.row0 + ilast == g.w - 1);
-    const size_t P = g.pitch;
+    const ptrdiff_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;
     const bool own = (2 * t >= S) && (2 * t < TW - S) && (j0 < g.w) && (j0 >= 0);
-    // per-thread column predicates for the even (0) and odd (1) column of the pair:
-    // may it be updated inside this tile, and is it a Dirichlet column
     const bool can0 = (t > 0) && (j0 >= 0) && (j0 < g.w);
     const bool can1 = (t < NT - 1) && (j0 + 1 >= 0) && (j0 + 1 < g.w);
     const bool bc0 = (j0 == 0) || (j0 == g.w - 1);
     const bool bc1 = (j0 + 1 == 0) || (j0 + 1 == g.w - 1);
     const int glast = g.w - 1 - g.row0;              // local index of the global last row
+    const int i_lo = ifirst + (first_is_bdry ? 2 * S + 1 : 3 * S), i_hi = ilast + 1;   // steady steps
 
+    double2 uw[2 * S + 2];
+#pragma unroll
+    for (int d = 0; d < 2 * S + 2; ++d) uw[d] = make_double2(0., 0.);
     double2 pu[PF], pb[PF];
 #pragma unroll
     for (int p = 0; p < PF; ++p) {
         int r = min(ifirst + p, ilast);
-        pu[p] = ld2(uin + (ptrdiff_t)r * (ptrdiff_t)P + jl);
-        pb[p] = ld2(b + (ptrdiff_t)r * (ptrdiff_t)P + jl);
+        pu[p] = ld2(uin + (ptrdiff_t)r * P + jl);
+        pb[p] = ld2(b + (ptrdiff_t)r * P + jl);
     }
     const int ksteps = (i1 - 1 + 2 * S) - ifirst + 1;
-    int base = 0;                                    // ring slot of the row loaded at this step
-    for (int k0 = 0; k0 < ksteps; k0 += PF) {
-#pragma unroll
-        for (int p = 0; p < PF; ++p) {
-            const int k = k0 + p;
-            if (k >= ksteps) break;
-            const int i = ifirst + k;                // row arriving at this step
-            // stage the row that was requested PF steps ago, request the one PF steps ahead
-            su[base * TW + t] = pu[p].x; su[base * TW + H + t] = pu[p].y;
-            sb[base * TW + t] = pb[p].x; sb[base * TW + H + t] = pb[p].y;
-            {
-                int r = min(i + PF, ilast);
-                pu[p] = ld2(uin + (ptrdiff_t)r * (ptrdiff_t)P + jl);
-                pb[p] = ld2(b + (ptrdiff_t)r * (ptrdiff_t)P + jl);
-            }
-            __syncthreads();
-            // The S half-sweep updates of this step are mutually independent (see above): read
-            // all operands first, then compute, then write, so the shared-memory latency is paid once.
-            double bv[S], up[S], dn[S], lf[S], rt[S];
-            bool act[S], isb[S];
-            int dst[S];
-            const int par = (g.row0 + i) & 1;        // parity of the arriving row
-#pragma unroll
-            for (int s = 1; s <= S; ++s) {
-                const int r = i - 2 * s;
-                const int vlo = first_is_bdry ? ifirst : ifirst + s;
-                const int vhi = last_is_bdry ? ilast : ilast - s;
-                int sl = base - 2 * s; if (sl < 0) sl += WR;
-                int sup = sl - 1; if (sup < 0) sup += WR;      // row r-1
-                int sdn = sl + 1; if (sdn >= WR) sdn -= WR;    // row r+1
-                const int which = (par + (s - 1)) & 1;         // rows i-2s share the parity of row i
-                const int c = which * H + t;                   // this point inside a de-interleaved row
-                const int o = (1 - which) * H + t;             // other-colour half row, same pair
-                act[s - 1] = (r >= vlo) && (r <= vhi) && (which ? can1 : can0);
-                isb[s - 1] = (which ? bc1 : bc0) || (r + g.row0 == 0) || (r == glast);
-                dst[s - 1] = sl * TW + c;
-                if (act[s - 1]) {
-                    bv[s - 1] = sb[sl * TW + c];
-                    up[s - 1] = su[sup * TW + c];
-                    dn[s - 1] = su[sdn * TW + c];
-                    // even column 2t: left = odd[t-1], right = odd[t]; odd column 2t+1: left = even[t], right = even[t+1]
-                    lf[s - 1] = su[sl * TW + o - (1 - which)];
-                    rt[s - 1] = su[sl * TW + o + which];
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-                if (act[s]) {
-                    double nv = rb_point<EXACT>(bv[s], up[s], lf[s], rt[s], dn[s], g.off, g.diag, inv_diag);
-                    su[dst[s]] = isb[s] ? bv[s] : nv;
-                }
-            {
-                const int r = i - 2 * S;                       // final after this step
-                if (r >= i0 && r < i1 && own) {
-                    int sl = base - 2 * S; if (sl < 0) sl += WR;
-                    double2 o2 = make_double2(su[sl * TW + t], su[sl * TW + H + t]);
-                    double *dstp = uout + (ptrdiff_t)r * (ptrdiff_t)P + j0;
-                    if (j0 + 1 < g.w) st2(dstp, o2); else dstp[0] = o2.x;
-                }
-            }
-            if (++base == WR) base = 0;
-        }
+    int base = 0;                                    // ring slot of the row arriving at this step
+#define MGB_STREAM_STEP(p)                                                                                  \
+    {                                                                                                       \
+        const int i = ifirst + k0 + (p);             /* row arriving at this step */                         \
+        const double2 nu = pu[p], nb = pb[p];                                                               \
+        {                                                                                                   \
+            int r = min(i + PF, ilast);                                                                     \
+            pu[p] = ld2(uin + (ptrdiff_t)r * P + jl);                                                       \
+            pb[p] = ld2(b + (ptrdiff_t)r * P + jl);                                                         \
+        }                                                                                                   \
+        const bool steady = (i >= i_lo) && (i <= i_hi);                                                     \
+        if (steady)                                                                                         \
+            rb_stream_step<S, EXACT, ((p) & 1), false>(g, uw, nu, nb, su, sb, base, i, t, can0, can1, bc0,  \
+                                                       bc1, ifirst, ilast, first_is_bdry, last_is_bdry,     \
+                                                       glast, inv_diag);                                    \
+        else                                                                                                \
+            rb_stream_step<S, EXACT, ((p) & 1), true>(g, uw, nu, nb, su, sb, base, i, t, can0, can1, bc0,   \
+                                                      bc1, ifirst, ilast, first_is_bdry, last_is_bdry,      \
+                                                      glast, inv_diag);                                     \
+        const int r = i - 2 * S;                     /* final after this step */                             \
+        if (r >= i0 && r < i1 && own) {                                                                     \
+            double *dstp = uout + (ptrdiff_t)r * P + j0;                                                    \
+            if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                             \
+        }                                                                                                   \
+        if (++base == WR) base = 0;                                                                         \
     }
+    for (int k0 = 0; k0 < ksteps; k0 += PF) {
+        MGB_STREAM_STEP(0)
+        MGB_STREAM_STEP(1)
+        MGB_STREAM_STEP(2)
+        MGB_STREAM_STEP(3)
+    }
+#undef MGB_STREAM_STEP
 }
 
 }  // namespace mgb

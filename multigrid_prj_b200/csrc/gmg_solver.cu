@@ -116,7 +116,8 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
     const int slots = h->n_sm * occ;
     int ny = std::max(1, (slots + nx / 2) / nx);
     ny = std::min(ny, std::max(1, g.rows / (8 * S)));
-    const int rc = (g.rows + ny - 1) / ny;
+    int rc = (g.rows + ny - 1) / ny;
+    rc += rc & 1;                                  // even chunks keep (row0 + first streamed row) even
     ny = (g.rows + rc - 1) / rc;
     mgb::k_rb_stream<S, EXACT><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc);
     count(h, 24. * (S / 2) * npts(g));     // 24 B per point per sweep, S/2 sweeps per launch
