@@ -402,11 +402,18 @@ __device__ __forceinline__ double rb_point(double b, double up, double left, dou
 // up, down and the neighbour inside the pair never touch shared memory; only the neighbour that
 // belongs to the adjacent thread, and the rhs, are read from the ring, and the new value is
 // published to the ring for the adjacent threads.  3 shared-memory words per update instead of 6.
+// ro[s] = element offset of [ring slot of row i-2s][t] (ro[0]: the arriving row), carried from
+// step to step so that no index arithmetic is left in the loop.
 // PAR = parity of the global row index of row i (static: the main loop is unrolled by 4 rows).
+// GUARD = false is the steady state: every half-sweep row is an interior row inside the
+// streamed range, so the only predicate left is the per-thread Dirichlet-column flag.  Threads
+// at the tile edge / outside the domain compute harmless garbage there: tile-edge columns are
+// halo (invalid after s half-sweeps by construction) and the Dirichlet columns j=0, j=w-1 never
+// read their neighbours, so nothing crosses into the domain.
 template <int S, bool EXACT, int PAR, bool GUARD>
 __device__ __forceinline__ void rb_stream_step(
-    const LevelGeom &g, double2 (&uw)[2 * S + 2], double2 nu, double2 nb, double *su, double *sb, int base,
-    int i, int t, bool can0, bool can1, bool bc0, bool bc1, int ifirst, int ilast, bool first_is_bdry,
+    const LevelGeom &g, double2 (&uw)[2 * S + 2], int (&ro)[S + 1], double2 nu, double2 nb, double *su,
+    double *sb, int i, bool bc0, bool bc1, int ifirst, int ilast, bool first_is_bdry,
     bool last_is_bdry, int glast, double inv_diag)
 {
     constexpr int TW = kStreamTW, H = TW / 2, WR = 2 * S + 3;
@@ -414,35 +421,29 @@ __device__ __forceinline__ void rb_stream_step(
 #pragma unroll
     for (int d = 2 * S + 1; d > 0; --d) uw[d] = uw[d - 1];
     uw[0] = nu;
-    su[base * TW + t] = nu.x; su[base * TW + H + t] = nu.y;
-    sb[base * TW + t] = nb.x; sb[base * TW + H + t] = nb.y;
+    su[ro[0]] = nu.x; su[ro[0] + H] = nu.y;
+    sb[ro[0]] = nb.x; sb[ro[0] + H] = nb.y;
     __syncthreads();
     double bv[S], ob[S];
-    int off[S];
 #pragma unroll
     for (int s = 1; s <= S; ++s) {
-        int sl = base - 2 * s; if (sl < 0) sl += WR;
         constexpr int dummy = 0; (void)dummy;
         const int which = (PAR + (s - 1)) & 1;        // rows i-2s have the parity of row i
-        off[s - 1] = sl * TW + which * H + t;
-        bv[s - 1] = sb[off[s - 1]];
+        bv[s - 1] = sb[ro[s] + which * H];
         // neighbour held by the adjacent thread: even column 2t -> odd[t-1]; odd column 2t+1 -> even[t+1]
-        const int nb_idx = sl * TW + (which ? (t + 1) : (H + t - 1));
-        const bool can = which ? can1 : can0;
-        ob[s - 1] = can ? su[nb_idx] : 0.;
+        ob[s - 1] = su[ro[s] + (which ? 1 : (H - 1))];
     }
 #pragma unroll
     for (int s = 1; s <= S; ++s) {
         const int which = (PAR + (s - 1)) & 1;
         const int d = 2 * s;
-        const bool can = which ? can1 : can0;
-        bool act = can;
+        bool act = true;
         bool isb = which ? bc1 : bc0;
         if (GUARD) {
             const int r = i - d;
             const int vlo = first_is_bdry ? ifirst : ifirst + s;
             const int vhi = last_is_bdry ? ilast : ilast - s;
-            act = act && (r >= vlo) && (r <= vhi);
+            act = (r >= vlo) && (r <= vhi);
             isb = isb || (r + g.row0 == 0) || (r == glast);
         }
         const double up = which ? uw[d + 1].y : uw[d + 1].x;
@@ -453,8 +454,14 @@ __device__ __forceinline__ void rb_stream_step(
         nv = isb ? bv[s - 1] : nv;
         if (act) {
             if (which) uw[d].y = nv; else uw[d].x = nv;
-            su[off[s - 1]] = nv;
+            su[ro[s] + which * H] = nv;
         }
+    }
+    // advance every carried ring offset by one row
+#pragma unroll
+    for (int s = 0; s <= S; ++s) {
+        ro[s] += TW;
+        if (ro[s] >= WR * TW) ro[s] -= WR * TW;
     }
 }
 
@@ -485,10 +492,9 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const ptrdiff_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;
     const bool own = (2 * t >= S) && (2 * t < TW - S) && (j0 < g.w) && (j0 >= 0);
-    const bool can0 = (t > 0) && (j0 >= 0) && (j0 < g.w);
-    const bool can1 = (t < NT - 1) && (j0 + 1 >= 0) && (j0 + 1 < g.w);
-    const bool bc0 = (j0 == 0) || (j0 == g.w - 1);
-    const bool bc1 = (j0 + 1 == 0) || (j0 + 1 == g.w - 1);
+    // Dirichlet-column flags of the pair; columns outside the domain are frozen the same way
+    const bool bc0 = (j0 <= 0) || (j0 >= g.w - 1);
+    const bool bc1 = (j0 + 1 <= 0) || (j0 + 1 >= g.w - 1);
     const int glast = g.w - 1 - g.row0;              // local index of the global last row
     const int i_lo = ifirst + (first_is_bdry ? 2 * S + 1 : 3 * S), i_hi = ilast + 1;   // steady steps
 
@@ -503,7 +509,9 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
         pb[p] = ld2(b + (ptrdiff_t)r * P + jl);
     }
     const int ksteps = (i1 - 1 + 2 * S) - ifirst + 1;
-    int base = 0;                                    // ring slot of the row arriving at this step
+    int ro[S + 1];                                   // ring offsets of rows i-2s (s = 0: arriving row)
+#pragma unroll
+    for (int s = 0; s <= S; ++s) ro[s] = ((WR - 2 * s) % WR) * TW + t;
 #define MGB_STREAM_STEP(p)                                                                                  \
     {                                                                                                       \
         const int i = ifirst + k0 + (p);             /* row arriving at this step */                         \
@@ -515,19 +523,16 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
         }                                                                                                   \
         const bool steady = (i >= i_lo) && (i <= i_hi);                                                     \
         if (steady)                                                                                         \
-            rb_stream_step<S, EXACT, ((p) & 1), false>(g, uw, nu, nb, su, sb, base, i, t, can0, can1, bc0,  \
-                                                       bc1, ifirst, ilast, first_is_bdry, last_is_bdry,     \
-                                                       glast, inv_diag);                                    \
+            rb_stream_step<S, EXACT, ((p) & 1), false>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst,      \
+                                                       ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         else                                                                                                \
-            rb_stream_step<S, EXACT, ((p) & 1), true>(g, uw, nu, nb, su, sb, base, i, t, can0, can1, bc0,   \
-                                                      bc1, ifirst, ilast, first_is_bdry, last_is_bdry,      \
-                                                      glast, inv_diag);                                     \
+            rb_stream_step<S, EXACT, ((p) & 1), true>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst,       \
+                                                      ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         const int r = i - 2 * S;                     /* final after this step */                             \
         if (r >= i0 && r < i1 && own) {                                                                     \
             double *dstp = uout + (ptrdiff_t)r * P + j0;                                                    \
             if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                             \
         }                                                                                                   \
-        if (++base == WR) base = 0;                                                                         \
     }
     for (int k0 = 0; k0 < ksteps; k0 += PF) {
         MGB_STREAM_STEP(0)
