@@ -384,6 +384,12 @@ k_sample_rhs(LevelGeom g, double *__restrict__ b, double length, int test)
 constexpr int kStreamTW = 256;            // tile columns held in shared memory
 constexpr int kStreamNT = kStreamTW / 2;  // threads: one per column pair
 constexpr int kStreamPF = 4;              // rows in flight from HBM per thread (register staged)
+constexpr int kStreamL2Ahead = 24;        // rows ahead that are prefetched into L2 (one 128-B line per 8 threads)
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 template <int S>
 constexpr int stream_smem_bytes() { return (2 * S + 3) * kStreamTW * 2 * (int)sizeof(double); }
@@ -417,17 +423,27 @@ __device__ __forceinline__ void rb_stream_step(
     bool last_is_bdry, int glast, double inv_diag)
 {
     constexpr int TW = kStreamTW, H = TW / 2, WR = 2 * S + 3;
+    // fast arithmetic: the ring holds bq = b/diag (or b itself on Dirichlet points) and the update is
+    // u = bq + q * (sum of neighbours) with q = 1/4 (0 on Dirichlet points): 3 DADD + 1 DFMA, no select.
+    const double q0 = bc0 ? 0. : 0.25, q1 = bc1 ? 0. : 0.25;
+    if (!EXACT) {
+        const bool brow = (i + g.row0 == 0) || (i == glast);   // the ARRIVING row may be a Dirichlet row in any step
+        nb.x = (bc0 || brow) ? nb.x : nb.x * inv_diag;
+        nb.y = (bc1 || brow) ? nb.y : nb.y * inv_diag;
+    }
     // rotate the register window by one row and publish the arriving row
 #pragma unroll
     for (int d = 2 * S + 1; d > 0; --d) uw[d] = uw[d - 1];
-    uw[0] = nu;
     su[ro[0]] = nu.x; su[ro[0] + H] = nu.y;
     sb[ro[0]] = nb.x; sb[ro[0] + H] = nb.y;
     __syncthreads();
+    // the window copy of the arriving row is re-read from the ring rather than kept from the global
+    // load: the load registers then die here and the next prefetch can land in them without a
+    // dependent register move at the loop back-edge
+    uw[0] = make_double2(su[ro[0]], su[ro[0] + H]);
     double bv[S], ob[S];
 #pragma unroll
     for (int s = 1; s <= S; ++s) {
-        constexpr int dummy = 0; (void)dummy;
         const int which = (PAR + (s - 1)) & 1;        // rows i-2s have the parity of row i
         bv[s - 1] = sb[ro[s] + which * H];
         // neighbour held by the adjacent thread: even column 2t -> odd[t-1]; odd column 2t+1 -> even[t+1]
@@ -439,19 +455,28 @@ __device__ __forceinline__ void rb_stream_step(
         const int d = 2 * s;
         bool act = true;
         bool isb = which ? bc1 : bc0;
+        bool brow = false;
         if (GUARD) {
             const int r = i - d;
             const int vlo = first_is_bdry ? ifirst : ifirst + s;
             const int vhi = last_is_bdry ? ilast : ilast - s;
             act = (r >= vlo) && (r <= vhi);
-            isb = isb || (r + g.row0 == 0) || (r == glast);
+            brow = (r + g.row0 == 0) || (r == glast);
+            isb = isb || brow;
         }
         const double up = which ? uw[d + 1].y : uw[d + 1].x;
         const double dn = which ? uw[d - 1].y : uw[d - 1].x;
         const double left = which ? uw[d].x : ob[s - 1];
         const double right = which ? ob[s - 1] : uw[d].y;
-        double nv = rb_point<EXACT>(bv[s - 1], up, left, right, dn, g.off, g.diag, inv_diag);
-        nv = isb ? bv[s - 1] : nv;
+        double nv;
+        if (EXACT) {
+            nv = smooth_point(bv[s - 1], up, left, right, dn, g.off, g.diag);
+            nv = isb ? bv[s - 1] : nv;
+        } else {
+            double q = which ? q1 : q0;
+            if (GUARD) q = brow ? 0. : q;
+            nv = fma(q, (up + dn) + (left + right), bv[s - 1]);
+        }
         if (act) {
             if (which) uw[d].y = nv; else uw[d].x = nv;
             su[ro[s] + which * H] = nv;
