@@ -91,6 +91,10 @@ void mgb_gmg_config_fast(mgb_gmg_config *cfg);
 int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out);
 void mgb_gmg_destroy(mgb_gmg_t h);
 
+/* Row-slab partition used for n_ranks > 1 (pure host arithmetic, no device needed): level `level` is
+ * either sharded (rank owns rows [row0,row0+rows)) or replicated on every rank (row0 = 0, rows = width). */
+int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows);
+
 /* geometry queries (domain.hpp:82,90,94) */
 int mgb_gmg_level_width(mgb_gmg_t h, int level, size_t *width);
 /* local slab of level `level`: first global row and number of rows owned by this rank */
@@ -140,7 +144,7 @@ typedef struct mgb_gmg_stats {
     uint64_t coarse_iters_total;
     uint64_t cycles;
     double bytes_algorithmic;      /* SURVEY.md section 8d accounting, summed over the launches */
-    int reserved[8];
+    int reserved[8];               /* [0] = halo / gather exchanges posted */
 } mgb_gmg_stats;
 int mgb_gmg_get_stats(mgb_gmg_t h, mgb_gmg_stats *s);
 int mgb_gmg_reset_stats(mgb_gmg_t h);

@@ -512,7 +512,11 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     if (i0 >= g.rows) return;
     const bool top_is_domain = (g.row0 == 0), bot_is_domain = (g.row0 + g.rows == g.w);
     const int lo = top_is_domain ? 0 : -S, hi = bot_is_domain ? g.rows - 1 : g.rows - 1 + S;
-    const int ifirst = max(i0 - S, lo), ilast = min(i1 - 1 + S, hi);   // row0 + ifirst is even
+    int ifirst = max(i0 - S, lo);
+    // the unrolled loop assumes the first streamed row has an even global index; if a slab starts on
+    // an odd row, stream one more (halo) row -- it only feeds values that are never written out
+    if ((g.row0 + ifirst) & 1) ifirst -= 1;
+    const int ilast = min(i1 - 1 + S, hi);
     const bool first_is_bdry = (g.row0 + ifirst == 0), last_is_bdry = (g.row0 + ilast == g.w - 1);
     const ptrdiff_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;

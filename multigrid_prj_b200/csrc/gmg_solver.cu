@@ -7,8 +7,17 @@
 //   driver loop          main                                          src/main.cpp:73-116
 // The host only enqueues kernels on one stream and reads back one double where the reference
 // inspects a norm.  No CPU arithmetic on grid data happens here.
+//
+// Multi-GPU: one process per GPU.  The fine levels are cut into contiguous ROW SLABS (rank r owns
+// rows [row0, row0+rows) of every sharded level, slab boundaries on multiples of 2^(#sharded
+// levels - 1) so that a coarse row lives where its fine row lives); levels below a size threshold
+// are REPLICATED: their right-hand side is gathered once per cycle and every rank runs the
+// (tiny) coarse tail redundantly, which replaces a gather + a broadcast by one exchange.
+// Halo rows move by grouped ncclSend/ncclRecv on the compute stream; a fused k-sweep kernel
+// needs ONE exchange of k... 2k rows instead of one per colour pass.  Norms: ncclAllReduce of one fp64.
 #include "../../include/mgb200.h"
 #include "gmg_kernels.cuh"
+#include "nccl_dyn.h"
 
 #include <algorithm>
 #include <cmath>
@@ -28,26 +37,72 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess)                                                                \
             return fail(MGB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        int e_ = (call);                                                                      \
+        if (e_ != mgb::kNcclSuccess)                                                          \
+            return fail(MGB_ERR_NCCL, std::string(#call) + ": " + mgb::nccl().GetErrorString(e_)); \
+    } while (0)
 
 using mgb::LevelGeom;
 
+constexpr int kHalo = 12;            // halo rows kept above and below every slab (>= deepest fused kernel: 10)
+constexpr int kMinSlabRows = 64;     // a level is sharded while every rank keeps at least this many rows
+
 struct Level {
-    LevelGeom g{};
-    size_t elems = 0;                 // (rows + 2) * pitch
+    LevelGeom g{};                    // this rank's view (sharded: its slab; replicated: the whole level)
+    bool sharded = false;
+    size_t elems = 0;                 // (rows + 2*kHalo) * pitch
     double *base[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // pointers to local row 0 of: u, f (level 0 only), e, r, t (scratch for out-of-place sweeps)
     double *u = nullptr, *f = nullptr, *e = nullptr, *r = nullptr, *t = nullptr;
 };
+
+// Slab of `rank` on `level` (pure host arithmetic; also exported for the CPU-side tests).
+// Sharded levels are 0..ls; fine-row boundaries are multiples of 2^ls; the last rank owns the +1 row.
+struct Part { bool sharded; int row0, rows; };
+
+int last_sharded_level(size_t n, int levels, int n_ranks)
+{
+    if (n_ranks <= 1) return -1;
+    int ls = -1;
+    size_t w = n;
+    for (int l = 0; l < levels; ++l) {
+        if ((w - 1) / (size_t)n_ranks >= (size_t)kMinSlabRows) ls = l; else break;
+        w = (w + 1) / 2;
+    }
+    return ls;
+}
+
+Part partition(size_t n, int levels, int n_ranks, int rank, int level)
+{
+    Part p{false, 0, 0};
+    size_t w = n;
+    for (int l = 0; l < level; ++l) w = (w + 1) / 2;
+    const int ls = last_sharded_level(n, levels, n_ranks);
+    if (level > ls) { p.sharded = false; p.row0 = 0; p.rows = (int)w; return p; }
+    const size_t A = (size_t)1 << ls;                 // alignment of fine slab boundaries
+    const size_t units = (n - 1) / A;                 // (n-1) is a multiple of 2^(levels-1) >= A
+    const size_t base = units / n_ranks, rem = units % n_ranks;
+    const size_t u0 = (size_t)rank * base + std::min((size_t)rank, rem);
+    const size_t nu = base + ((size_t)rank < rem ? 1 : 0);
+    p.sharded = true;
+    p.row0 = (int)((u0 * A) >> level);
+    p.rows = (int)((nu * A) >> level) + (rank == n_ranks - 1 ? 1 : 0);
+    return p;
+}
 
 }  // namespace
 
 struct mgb_gmg {
     mgb_gmg_config cfg{};
     std::vector<Level> lv;
+    int ls = -1;                      // last sharded level (-1: single rank)
     cudaStream_t st = nullptr;
+    mgb::NcclComm comm = nullptr;
     double *d_partial = nullptr;      // per-CTA partial sums
     size_t n_partial = 0;
-    double *d_scal = nullptr;         // device scalars: [0] last sumsq
+    double *d_scal = nullptr;         // device scalars
     double *h_scal = nullptr;         // pinned mirror
     double norm_f = 0.;               // sum f^2 on the fine grid (Residual ctor, solvers.hpp:237-242)
     bool have_rhs = false;
@@ -77,19 +132,38 @@ dim3 march_grid(const LevelGeom &g)
 inline void count(mgb_gmg *h, double bytes) { h->stats.kernel_launches++; h->stats.bytes_algorithmic += bytes; }
 inline double npts(const LevelGeom &g) { return (double)g.w * (double)g.rows; }
 
-int halo_exchange(mgb_gmg *h, int level, double *v)
+// exchange `depth` halo rows of a sharded level vector with the slab neighbours
+int halo_exchange(mgb_gmg *h, int level, double *v, int depth)
 {
-    (void)level; (void)v;
-    if (h->cfg.n_ranks > 1) return fail(MGB_ERR_STATE, "halo exchange not wired");
+    Level &L = h->lv[level];
+    if (!L.sharded || h->cfg.n_ranks <= 1) return MGB_OK;
+    auto &N = mgb::nccl();
+    const int r = h->cfg.rank, n = h->cfg.n_ranks;
+    const size_t P = (size_t)L.g.pitch;
+    depth = std::min(depth, std::min(kHalo, L.g.rows));
+    const size_t cnt = (size_t)depth * P;
+    NK(N.GroupStart());
+    if (r > 0) {
+        NK(N.Send(v, cnt, mgb::kNcclFloat64, r - 1, h->comm, h->st));                                   // my top rows
+        NK(N.Recv(v - cnt, cnt, mgb::kNcclFloat64, r - 1, h->comm, h->st));                             // halo above
+    }
+    if (r < n - 1) {
+        NK(N.Send(v + (size_t)(L.g.rows - depth) * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st)); // my bottom rows
+        NK(N.Recv(v + (size_t)L.g.rows * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st));           // halo below
+    }
+    NK(N.GroupEnd());
+    h->stats.reserved[0]++;           // exchanges
     return MGB_OK;
 }
 
-// reduce d_partial[0..n) into d_scal[slot]
-int reduce_partials(mgb_gmg *h, int n, int slot)
+// reduce d_partial[0..n) into d_scal[slot]; sum over ranks when the level is sharded
+int reduce_partials(mgb_gmg *h, int n, int slot, bool sharded)
 {
     mgb::k_reduce_partials<<<1, 1024, 0, h->st>>>(h->d_partial, n, h->d_scal + slot);
     count(h, 0.);
     CK(cudaGetLastError());
+    if (sharded && h->cfg.n_ranks > 1)
+        NK(mgb::nccl().AllReduce(h->d_scal + slot, h->d_scal + slot, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
     return MGB_OK;
 }
 
@@ -104,21 +178,31 @@ int read_scalar(mgb_gmg *h, int slot, double *out)
 template <int S, bool EXACT>
 int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out)
 {
-    static bool attr_set = false;
+    static int occ = 0;
     constexpr int smem = mgb::stream_smem_bytes<S>();
-    if (!attr_set) {
+    if (!occ) {
         CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT>, mgb::kStreamNT, smem));
+        occ = std::max(1, occ);
     }
     const int OW = mgb::kStreamTW - 2 * S;
     const int nx = (g.w + OW - 1) / OW;
-    const int occ = std::max(1, std::min(16, (227 * 1024) / (smem + 1024)));
     const int slots = h->n_sm * occ;
-    int ny = std::max(1, (slots + nx / 2) / nx);
-    ny = std::min(ny, std::max(1, g.rows / (8 * S)));
-    int rc = (g.rows + ny - 1) / ny;
-    rc += rc & 1;                                  // even chunks keep (row0 + first streamed row) even
-    ny = (g.rows + rc - 1) / rc;
+    // rows per chunk: a CTA needs (rc + 2S) steps and the grid needs ceil(nx*ny/slots) waves; pick the
+    // even rc that minimises their product (small levels: many short chunks, the recomputed rows cost nothing
+    // there; large levels: one wave of long chunks, 2S/rc redundant rows)
+    int rc = g.rows + (g.rows & 1), ny = 1;
+    {
+        double best = 1e300;
+        for (int n0 = 1; n0 <= std::max(1, g.rows / 8); ++n0) {
+            int c = (g.rows + n0 - 1) / n0;
+            c += c & 1;
+            const int n = (g.rows + c - 1) / c;
+            const int waves = (nx * n + slots - 1) / slots;
+            const double t = (double)(c + 2 * S) * waves;
+            if (t < best) { best = t; rc = c; ny = n; }
+        }
+    }
     mgb::k_rb_stream<S, EXACT><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc);
     count(h, 24. * (S / 2) * npts(g));     // 24 B per point per sweep, S/2 sweeps per launch
     CK(cudaGetLastError());
@@ -138,34 +222,37 @@ int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const 
     }
 }
 
+// Smoothing.  `rhs` must carry valid halo rows to the depth the chosen kernel reads
+// (fused red-black: 2 rows per sweep of the group; everything else: none -- only `sol` is read across rows).
 int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs)
 {
     Level &L = h->lv[level];
     const LevelGeom &g = L.g;
     if (kind == MGB_SMOOTH_BICGSTAB) kind = MGB_SMOOTH_JACOBI;      // main.cpp:103-106
     dim3 grid = march_grid(g);
+    int rc;
     for (int s = 0; s < sweeps; ++s) {
         if (kind == MGB_SMOOTH_JACOBI) {
+            if ((rc = halo_exchange(h, level, *sol, 1))) return rc;
             mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, L.t);
             count(h, 24. * npts(g));
             std::swap(*sol, L.t);                                   // solvers.hpp:83 sol.swap(temp)
-            if (int rc = halo_exchange(h, level, *sol)) return rc;
         } else if (kind == MGB_SMOOTH_GS_RB && h->cfg.rb_fused) {
             // group the remaining sweeps: 5, 2 or 1 full sweeps per pass over HBM
             const int left = sweeps - s;
             const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
-            if (int rc = launch_rb_stream(h, level, grp, *sol, rhs, L.t)) return rc;
+            if ((rc = halo_exchange(h, level, *sol, 2 * grp))) return rc;
+            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, L.t))) return rc;
             std::swap(*sol, L.t);
             s += grp - 1;
-            if (int rc = halo_exchange(h, level, *sol)) return rc;
         } else if (kind == MGB_SMOOTH_GS_RB) {
             for (int colour = 0; colour < 2; ++colour) {
+                if ((rc = halo_exchange(h, level, *sol, 1))) return rc;
                 mgb::k_rbgs_colour<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, colour);
                 count(h, 12. * npts(g));
-                if (int rc = halo_exchange(h, level, *sol)) return rc;
             }
         } else if (kind == MGB_SMOOTH_GS_LEX) {
-            if (h->cfg.n_ranks > 1)
+            if (L.sharded)
                 return fail(MGB_ERR_ARG, "lexicographic GS is sequential across slabs; use one rank for parity mode");
             for (int b0 = 0; b0 < g.rows; b0 += 1024) {
                 int nb = std::min(1024, g.rows - b0);
@@ -179,57 +266,100 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
     return MGB_OK;
 }
 
-// r = rhs - A sol; leaves sum r^2 (this rank) in d_scal[slot]
-int do_residual(mgb_gmg *h, int level, const double *sol, const double *rhs, double *store, int slot)
+// r = rhs - A sol; leaves sum r^2 (all ranks) in d_scal[slot]
+int do_residual(mgb_gmg *h, int level, double *sol, const double *rhs, double *store, int slot)
 {
-    const LevelGeom &g = h->lv[level].g;
+    const Level &L = h->lv[level];
+    const LevelGeom &g = L.g;
+    if (int rc = halo_exchange(h, level, sol, 1)) return rc;
     dim3 grid = march_grid(g);
     if (store) mgb::k_residual<true><<<grid, mgb::kTPB, 0, h->st>>>(g, sol, rhs, store, h->d_partial);
     else mgb::k_residual<false><<<grid, mgb::kTPB, 0, h->st>>>(g, sol, rhs, nullptr, h->d_partial);
     count(h, (store ? 24. : 16.) * npts(g));
     CK(cudaGetLastError());
-    return reduce_partials(h, grid.x * grid.y, slot);
+    return reduce_partials(h, grid.x * grid.y, slot, L.sharded);
 }
 
 int do_sumsq(mgb_gmg *h, int level, const double *v, int slot)
 {
-    const LevelGeom &g = h->lv[level].g;
-    dim3 grid = march_grid(g);
-    mgb::k_sumsq<<<grid, mgb::kTPB, 0, h->st>>>(g, v, h->d_partial);
-    count(h, 8. * npts(g));
+    const Level &L = h->lv[level];
+    dim3 grid = march_grid(L.g);
+    mgb::k_sumsq<<<grid, mgb::kTPB, 0, h->st>>>(L.g, v, h->d_partial);
+    count(h, 8. * npts(L.g));
     CK(cudaGetLastError());
-    return reduce_partials(h, grid.x * grid.y, slot);
+    return reduce_partials(h, grid.x * grid.y, slot, L.sharded);
 }
 
+// gather the slab-distributed rows of the first replicated level's rhs onto every rank
+int allgather_rows(mgb_gmg *h, int level, double *v)
+{
+    auto &N = mgb::nccl();
+    const int n = h->cfg.n_ranks, me = h->cfg.rank;
+    const Level &C = h->lv[level];
+    const size_t P = (size_t)C.g.pitch;
+    auto vslab = [&](int rank, int &r0, int &nr) {
+        Part f = partition(h->cfg.n, h->cfg.levels, n, rank, level - 1);
+        r0 = (f.row0 + 1) / 2;
+        nr = (f.row0 + f.rows - 1) / 2 - r0 + 1;
+    };
+    int my0, myn;
+    vslab(me, my0, myn);
+    NK(N.GroupStart());
+    for (int p = 0; p < n; ++p) {
+        if (p == me) continue;
+        int p0, pn;
+        vslab(p, p0, pn);
+        NK(N.Send(v + (size_t)my0 * P, (size_t)myn * P, mgb::kNcclFloat64, p, h->comm, h->st));
+        NK(N.Recv(v + (size_t)p0 * P, (size_t)pn * P, mgb::kNcclFloat64, p, h->comm, h->st));
+    }
+    NK(N.GroupEnd());
+    h->stats.reserved[0]++;
+    return MGB_OK;
+}
+
+// restriction of r from level 0 down to every coarser level.
+// Leaves every sharded level's r with halo rows valid to depth kHalo (they are the rhs of the fused smoother).
 int do_restrict(mgb_gmg *h)
 {
     const int L = (int)h->lv.size();
+    int rc;
+    const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
+    if ((rc = halo_exchange(h, 0, h->lv[0].r, kHalo))) return rc;
     for (int l = 1; l < L; ++l) {
         Level &F = h->lv[l - 1], &C = h->lv[l];
-        dim3 grid((C.g.w + 255) / 256, C.g.rows);
-        if (h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING) {
-            if (int rc = halo_exchange(h, l - 1, F.r)) return rc;
-            mgb::k_restrict<2><<<grid, 256, 0, h->st>>>(F.g, C.g, F.r, C.r, 1.0);
-            count(h, 8. * npts(F.g) + 8. * npts(C.g));
+        LevelGeom gc = C.g;
+        double *rc_ptr = C.r;
+        if (F.sharded && !C.sharded) {
+            // this rank produces the coarse rows whose coincident fine row it owns, then all ranks gather
+            gc.row0 = (F.g.row0 + 1) / 2;
+            gc.rows = (F.g.row0 + F.g.rows - 1) / 2 - gc.row0 + 1;
+            rc_ptr = C.r + (size_t)gc.row0 * gc.pitch;
+        }
+        dim3 grid((gc.w + 255) / 256, gc.rows);
+        if (fw) {
+            mgb::k_restrict<2><<<grid, 256, 0, h->st>>>(F.g, gc, F.r, rc_ptr, 1.0);
+            count(h, 8. * npts(F.g) + 8. * npts(gc));
         } else {
             double scale = (h->cfg.restriction == MGB_RESTRICT_HALF_INJECTION && l == 1) ? 0.5 : 1.0;
-            mgb::k_restrict<0><<<grid, 256, 0, h->st>>>(F.g, C.g, F.r, C.r, scale);
-            count(h, 16. * npts(C.g));
+            mgb::k_restrict<0><<<grid, 256, 0, h->st>>>(F.g, gc, F.r, rc_ptr, scale);
+            count(h, 16. * npts(gc));
         }
+        CK(cudaGetLastError());
+        if (F.sharded && !C.sharded) { if ((rc = allgather_rows(h, l, C.r))) return rc; }
+        else if ((rc = halo_exchange(h, l, C.r, kHalo))) return rc;
     }
-    CK(cudaGetLastError());
     return MGB_OK;
 }
 
 int do_prolong(mgb_gmg *h, int lc)
 {
     Level &C = h->lv[lc], &F = h->lv[lc - 1];
-    if (int rc = halo_exchange(h, lc, C.e)) return rc;
+    if (int rc = halo_exchange(h, lc, C.e, 1)) return rc;
     dim3 grid((F.g.w + 2 * mgb::kTPB - 1) / (2 * mgb::kTPB), (F.g.rows + 3) / 4);
     mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, F.g, C.e, F.e);
     count(h, 8. * (npts(F.g) + npts(C.g)));
     CK(cudaGetLastError());
-    return halo_exchange(h, lc - 1, F.e);
+    return MGB_OK;
 }
 
 // multigrid.hpp:126-145
@@ -247,7 +377,7 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     double nb = 0., norm = 0.;
     if ((rc = read_scalar(h, 2, &nb))) return rc;
     // :130 err * COARSE_SOLVER  (err == 0 on entry, multigrid.hpp:143)
-    CK(cudaMemsetAsync(C.e - C.g.pitch, 0, C.elems * sizeof(double), h->st));
+    CK(cudaMemsetAsync(C.e - (size_t)kHalo * C.g.pitch, 0, C.elems * sizeof(double), h->st));
     int its = 0;
     if ((rc = do_residual(h, L - 1, C.e, C.r, nullptr, 3))) return rc;
     if ((rc = read_scalar(h, 3, &norm))) return rc;
@@ -270,14 +400,13 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     mgb::k_axpy_rows<<<grid, 256, 0, h->st>>>(F.g, F.u, F.e);
     count(h, 24. * npts(F.g));
     CK(cudaGetLastError());
-    if ((rc = halo_exchange(h, 0, F.u))) return rc;
     h->stats.cycles++;
     return MGB_OK;
 }
 
 int copy_2d(mgb_gmg *h, const LevelGeom &g, double *dev, const double *host_global, bool to_device)
 {
-    // host arrays are global w x w row-major; this rank moves its slab rows
+    // host arrays are global w x w row-major; this rank moves the rows it holds
     const double *hsrc = host_global + (size_t)g.row0 * g.w;
     if (to_device)
         CK(cudaMemcpy2DAsync(dev, (size_t)g.pitch * 8, hsrc, (size_t)g.w * 8, (size_t)g.w * 8, g.rows,
@@ -289,12 +418,21 @@ int copy_2d(mgb_gmg *h, const LevelGeom &g, double *dev, const double *host_glob
     return MGB_OK;
 }
 
+int after_rhs(mgb_gmg *h)
+{
+    int rc;
+    if ((rc = do_sumsq(h, 0, h->lv[0].f, 0))) return rc;
+    if ((rc = read_scalar(h, 0, &h->norm_f))) return rc;
+    h->have_rhs = true;
+    return halo_exchange(h, 0, h->lv[0].f, kHalo);      // f is static: its halo rows are exchanged once
+}
+
 }  // namespace
 
 extern "C" {
 
 const char *mgb_last_error(void) { return g_err.c_str(); }
-const char *mgb_version(void) { return "mgb200 0.1 (sm_100a)"; }
+const char *mgb_version(void) { return "mgb200 0.2 (sm_100a)"; }
 
 int mgb_device_count(void)
 {
@@ -325,6 +463,20 @@ void mgb_gmg_config_fast(mgb_gmg_config *c)
     c->rb_fast_arith = 1;
 }
 
+int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows)
+{
+    if (n < 3 || levels < 1 || levels > 30 || n_ranks < 1 || rank < 0 || rank >= n_ranks || level < 0 || level >= levels)
+        return fail(MGB_ERR_ARG, "bad partition query");
+    if ((n - 1) % ((size_t)1 << (levels - 1)) != 0) return fail(MGB_ERR_ARG, "(n-1) must be divisible by 2^(levels-1)");
+    if (n_ranks > 1 && last_sharded_level(n, levels, n_ranks) < 0)
+        return fail(MGB_ERR_ARG, "grid too small to be cut into row slabs for this many ranks");
+    Part p = partition(n, levels, n_ranks, rank, level);
+    if (sharded) *sharded = p.sharded;
+    if (row0) *row0 = (size_t)p.row0;
+    if (rows) *rows = (size_t)p.rows;
+    return MGB_OK;
+}
+
 int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
 {
     if (!cfg || !out) return fail(MGB_ERR_ARG, "null argument");
@@ -337,7 +489,10 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     // not boundary nodes and neighbour indices run out of range
     if ((N - 1) % ((size_t)1 << (L - 1)) != 0 || ((N - 1) >> (L - 1)) < 1)
         return fail(MGB_ERR_ARG, "(n-1) must be divisible by 2^(levels-1)");
-    if (cfg->n_ranks != 1 || cfg->rank != 0) return fail(MGB_ERR_ARG, "multi-rank slabs not wired in this build");
+    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail(MGB_ERR_ARG, "bad rank / n_ranks");
+    const int ls = last_sharded_level(N, L, cfg->n_ranks);
+    if (cfg->n_ranks > 1 && ls < 0)
+        return fail(MGB_ERR_ARG, "grid too small to be cut into row slabs for this many ranks");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -346,35 +501,47 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     CK(cudaSetDevice(cfg->device));
     mgb_gmg *h = new mgb_gmg();
     h->cfg = *cfg;
+    h->ls = ls;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    if (cfg->n_ranks > 1) {
+        auto &Nc = mgb::nccl();
+        if (!Nc.load()) { delete h; return fail(MGB_ERR_NCCL, Nc.error); }
+        mgb::NcclUniqueId id;
+        std::memcpy(&id, cfg->nccl_id, sizeof(id));
+        NK(Nc.CommInitRank(&h->comm, cfg->n_ranks, id, cfg->rank));
+    }
     h->lv.resize(L);
     size_t w = N;
     const double m_h = cfg->length / (double)(N - 1);                     // domain.cpp:5
+    size_t max_partial = 1;
     for (int l = 0; l < L; ++l) {
         Level &lv = h->lv[l];
         const double hl = m_h * (double)((size_t)1 << l);                 // domain.hpp:92
         const double k = hl * hl;                                         // linear_system.hpp:17
-        lv.g.w = (int)w; lv.g.rows = (int)w; lv.g.row0 = 0;
+        Part p = partition(N, L, cfg->n_ranks, cfg->rank, l);
+        lv.sharded = p.sharded;
+        lv.g.w = (int)w; lv.g.rows = p.rows; lv.g.row0 = p.row0;
         lv.g.pitch = (int)((w + 2 + 15) / 16 * 16);
         lv.g.diag = 4. * cfg->alpha / k;                                  // linear_system.hpp:28
         lv.g.off = -cfg->alpha / k;                                       // linear_system.hpp:38
-        lv.elems = (size_t)(lv.g.rows + 2) * lv.g.pitch;
-        const int nvec = 5;
-        for (int v = 0; v < nvec; ++v) {
+        lv.elems = (size_t)(lv.g.rows + 2 * kHalo) * lv.g.pitch;
+        for (int v = 0; v < 5; ++v) {
             if (l > 0 && v < 2) continue;                                 // u, f exist on level 0 only
             CK(cudaMalloc(&lv.base[v], lv.elems * sizeof(double)));
             CK(cudaMemsetAsync(lv.base[v], 0, lv.elems * sizeof(double), h->st));
         }
-        lv.u = lv.base[0] ? lv.base[0] + lv.g.pitch : nullptr;
-        lv.f = lv.base[1] ? lv.base[1] + lv.g.pitch : nullptr;
-        lv.e = lv.base[2] + lv.g.pitch;
-        lv.r = lv.base[3] + lv.g.pitch;
-        lv.t = lv.base[4] + lv.g.pitch;
+        const size_t off = (size_t)kHalo * lv.g.pitch;
+        lv.u = lv.base[0] ? lv.base[0] + off : nullptr;
+        lv.f = lv.base[1] ? lv.base[1] + off : nullptr;
+        lv.e = lv.base[2] + off;
+        lv.r = lv.base[3] + off;
+        lv.t = lv.base[4] + off;
+        dim3 g0 = march_grid(lv.g);
+        max_partial = std::max(max_partial, (size_t)g0.x * g0.y);
         w = (w + 1) / 2;                                                  // domain.cpp:10
     }
-    dim3 g0 = march_grid(h->lv[0].g);
-    h->n_partial = (size_t)g0.x * g0.y;
+    h->n_partial = max_partial;
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));
     CK(cudaMalloc(&h->d_scal, 16 * sizeof(double)));
     CK(cudaMemsetAsync(h->d_scal, 0, 16 * sizeof(double), h->st));
@@ -389,6 +556,7 @@ void mgb_gmg_destroy(mgb_gmg_t h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
+    if (h->comm) mgb::nccl().CommDestroy(h->comm);
     for (auto &lv : h->lv)
         for (double *p : lv.base) if (p) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
@@ -421,12 +589,10 @@ int mgb_gmg_set_level(mgb_gmg_t h, int level, int which, const double *host)
     CK(cudaSetDevice(h->cfg.device));
     int rc = copy_2d(h, h->lv[level].g, *p, host, true);
     if (rc) return rc;
-    if (level == 0 && which == MGB_VEC_F) {
-        if ((rc = do_sumsq(h, 0, h->lv[0].f, 0))) return rc;
-        if ((rc = read_scalar(h, 0, &h->norm_f))) return rc;
-        h->have_rhs = true;
-    }
-    return halo_exchange(h, level, *p);
+    if (level == 0 && which == MGB_VEC_F) return after_rhs(h);
+    // a level rhs set by hand gets its halo rows here (restriction does it for the cycle)
+    if (which == MGB_VEC_R) return halo_exchange(h, level, *p, kHalo);
+    return MGB_OK;
 }
 
 int mgb_gmg_get_level(mgb_gmg_t h, int level, int which, double *host)
@@ -450,11 +616,7 @@ int mgb_gmg_set_rhs_test(mgb_gmg_t h, int test)
     mgb::k_sample_rhs<<<grid, 256, 0, h->st>>>(g, h->lv[0].f, h->cfg.length, test);
     count(h, 8. * npts(g));
     CK(cudaGetLastError());
-    int rc;
-    if ((rc = do_sumsq(h, 0, h->lv[0].f, 0))) return rc;
-    if ((rc = read_scalar(h, 0, &h->norm_f))) return rc;
-    h->have_rhs = true;
-    return MGB_OK;
+    return after_rhs(h);
 }
 
 int mgb_gmg_set_u(mgb_gmg_t h, const double *u_host)
@@ -462,7 +624,7 @@ int mgb_gmg_set_u(mgb_gmg_t h, const double *u_host)
     if (!h) return fail(MGB_ERR_ARG, "null handle");
     if (u_host) return mgb_gmg_set_level(h, 0, MGB_VEC_U, u_host);
     CK(cudaSetDevice(h->cfg.device));
-    CK(cudaMemsetAsync(h->lv[0].u - h->lv[0].g.pitch, 0, h->lv[0].elems * sizeof(double), h->st));
+    CK(cudaMemsetAsync(h->lv[0].u - (size_t)kHalo * h->lv[0].g.pitch, 0, h->lv[0].elems * sizeof(double), h->st));
     return MGB_OK;
 }
 
@@ -621,8 +783,12 @@ int mgb_timer_elapsed_ms(mgb_timer_t t, double *ms)
 
 int mgb_nccl_unique_id(unsigned char id[128])
 {
-    std::memset(id, 0, 128);
-    return fail(MGB_ERR_NCCL, "NCCL not wired in this build");
+    auto &N = mgb::nccl();
+    if (!N.load()) return fail(MGB_ERR_NCCL, N.error);
+    mgb::NcclUniqueId u;
+    NK(N.GetUniqueId(&u));
+    std::memcpy(id, &u, 128);
+    return MGB_OK;
 }
 
 }  // extern "C"

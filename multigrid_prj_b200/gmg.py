@@ -48,6 +48,21 @@ class GmgConfig:
         return GmgConfig(n=n, levels=levels, **kw)
 
 
+def partition(n, levels, n_ranks, rank, level):
+    """(sharded, row0, rows) of `rank` on `level` -- host arithmetic only, no GPU needed"""
+    lib = load()
+    sh, r0, r = C.c_int(), C.c_size_t(), C.c_size_t()
+    check(lib.mgb_gmg_partition(n, levels, n_ranks, rank, level, C.byref(sh), C.byref(r0), C.byref(r)))
+    return bool(sh.value), r0.value, r.value
+
+
+def nccl_unique_id():
+    lib = load()
+    buf = (C.c_ubyte * 128)()
+    check(lib.mgb_nccl_unique_id(C.byref(buf)))
+    return bytes(buf)
+
+
 class Gmg:
     def __init__(self, cfg: GmgConfig):
         self.lib = load()
