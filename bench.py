@@ -194,6 +194,10 @@ def main():
     else:
         cfg = GmgConfig(n=n, levels=L, length=LENGTH, alpha=ALPHA, smoother=G.GS_LEX, device=local)
     cfg.rank, cfg.n_ranks = rank, world
+    if world > 1:
+        ids = [G.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        cfg.nccl_id = ids[0]
 
     def barrier():
         if dist is not None:

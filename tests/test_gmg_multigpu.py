@@ -20,6 +20,6 @@ def test_slab_results_equal_single_rank(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tools", "mg_check.py"),
-           "--n", "2049", "--levels", "11"]
+           "--size", "2049", "--depth", "11"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "MG_CHECK OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

@@ -1,7 +1,7 @@
 """Multi-rank parity check of the slab-decomposed GMG path (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/mg_check.py [--n 1025] [--levels 10]
+        tools/mg_check.py [--size 1025] [--depth 10]
 
 Every rank runs its slab; rank 0 also runs the SAME problem on one rank and the assembled slab
 results must equal it bit for bit (the kernels and their arithmetic are identical; only the
@@ -35,14 +35,12 @@ def assemble(g, n, arr_fn):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1025)
-    ap.add_argument("--levels", type=int, default=10)
+    ap.add_argument("--size", dest="n", type=int, default=1025)
+    ap.add_argument("--depth", dest="levels", type=int, default=10)
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
-    ids = [G.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     n, L = a.n, a.levels
     rng = np.random.default_rng(11)
     u0 = rng.standard_normal((n, n)); b0 = rng.standard_normal((n, n))
@@ -55,6 +53,8 @@ def main():
             print(("PASS " if cond else "FAIL ") + name, extra, flush=True)
 
     for mode in ("exact", "fast"):
+        ids = [G.nccl_unique_id() if rank == 0 else None]      # one id per communicator
+        dist.broadcast_object_list(ids, src=0)
         kw = dict(length=10.0, alpha=1.0, rb_fast_arith=int(mode == "fast"))
         cfg = GmgConfig.fast(n, L, device=local, rank=rank, n_ranks=world, nccl_id=ids[0], **kw)
         g = Gmg(cfg)
