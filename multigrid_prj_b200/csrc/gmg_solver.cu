@@ -17,6 +17,7 @@
 // needs ONE exchange of k... 2k rows instead of one per colour pass.  Norms: ncclAllReduce of one fp64.
 #include "../../include/mgb200.h"
 #include "gmg_kernels.cuh"
+#include "gmg_tail.cuh"
 #include "nccl_dyn.h"
 
 #include <algorithm>
@@ -98,6 +99,7 @@ struct mgb_gmg {
     mgb_gmg_config cfg{};
     std::vector<Level> lv;
     int ls = -1;                      // last sharded level (-1: single rank)
+    int lt = -1;                      // first level of the persistent coarse tail (-1: no tail kernel)
     cudaStream_t st = nullptr;
     mgb::NcclComm comm = nullptr;
     double *d_partial = nullptr;      // per-CTA partial sums
@@ -325,7 +327,8 @@ int do_restrict(mgb_gmg *h)
     int rc;
     const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
     if ((rc = halo_exchange(h, 0, h->lv[0].r, kHalo))) return rc;
-    for (int l = 1; l < L; ++l) {
+    const int lend = h->lt >= 0 ? h->lt : L - 1;      // the tail kernel restricts below its first level itself
+    for (int l = 1; l <= lend; ++l) {
         Level &F = h->lv[l - 1], &C = h->lv[l];
         LevelGeom gc = C.g;
         double *rc_ptr = C.r;
@@ -362,6 +365,48 @@ int do_prolong(mgb_gmg *h, int lc)
     return MGB_OK;
 }
 
+int launch_tail(mgb_gmg *h)
+{
+    const int L = (int)h->lv.size();
+    mgb::TailParams p{};
+    p.nlev = L - h->lt;
+    for (int l = h->lt; l < L; ++l) {
+        Level &lv = h->lv[l];
+        p.lv[l - h->lt] = mgb::TailLevel{lv.g, lv.e, lv.r, lv.t};
+    }
+    p.kind = h->cfg.smoother == MGB_SMOOTH_BICGSTAB ? MGB_SMOOTH_JACOBI : h->cfg.smoother;
+    p.fast = h->cfg.rb_fast_arith;
+    p.restriction = h->cfg.restriction;
+    p.first_is_level1 = (h->lt == 0);
+    p.nu = h->cfg.nu;
+    p.coarse_maxit = h->cfg.coarse_maxit;
+    p.coarse_tol = h->cfg.coarse_tol;
+    p.out = h->d_scal + 4;
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
+        attr = true;
+    }
+    mgb::k_coarse_tail<<<1, mgb::kTailThreads, mgb::kTailSmemBytes, h->st>>>(p);
+    double bytes = 0.;
+    for (int l = h->lt; l < L; ++l) bytes += 24. * h->cfg.nu * npts(h->lv[l].g);
+    count(h, bytes);
+    CK(cudaGetLastError());
+    return MGB_OK;
+}
+
+// multigrid.hpp:141-144 (err is fully rewritten next cycle, so the err = 0 store is not needed)
+int finish_cycle(mgb_gmg *h)
+{
+    Level &F = h->lv[0];
+    dim3 grid((F.g.pitch / 2 + 255) / 256, std::min(F.g.rows, 1024));
+    mgb::k_axpy_rows<<<grid, 256, 0, h->st>>>(F.g, F.u, F.e);
+    count(h, 24. * npts(F.g));
+    CK(cudaGetLastError());
+    h->stats.cycles++;
+    return MGB_OK;
+}
+
 // multigrid.hpp:126-145
 int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
 {
@@ -372,6 +417,23 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
     if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
     if ((rc = do_restrict(h))) return rc;
+    if (h->lt >= 0) {
+        // restriction below lt, coarse solve and the upward leg up to level lt: one persistent CTA
+        if ((rc = launch_tail(h))) return rc;
+        if (coarse_relres || coarse_iters) {
+            double rel = 0., its = 0.;
+            if ((rc = read_scalar(h, 4, &rel))) return rc;
+            if ((rc = read_scalar(h, 5, &its))) return rc;
+            if (coarse_relres) *coarse_relres = rel;
+            if (coarse_iters) *coarse_iters = (int)its;
+            h->stats.coarse_iters_total += (uint64_t)its;
+        }
+        for (int j = h->lt; j > 0; --j) {
+            if ((rc = do_prolong(h, j))) return rc;
+            if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
+        }
+        return finish_cycle(h);
+    }
     // :128 COARSE_RES->refresh_normalization_constant()
     if ((rc = do_sumsq(h, L - 1, C.r, 2))) return rc;
     double nb = 0., norm = 0.;
@@ -395,13 +457,7 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
         if ((rc = do_prolong(h, j))) return rc;
         if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
     }
-    // :141-144 (err is fully rewritten next cycle, so the err = 0 store is not needed)
-    dim3 grid((F.g.pitch / 2 + 255) / 256, std::min(F.g.rows, 1024));
-    mgb::k_axpy_rows<<<grid, 256, 0, h->st>>>(F.g, F.u, F.e);
-    count(h, 24. * npts(F.g));
-    CK(cudaGetLastError());
-    h->stats.cycles++;
-    return MGB_OK;
+    return finish_cycle(h);
 }
 
 int copy_2d(mgb_gmg *h, const LevelGeom &g, double *dev, const double *host_global, bool to_device)
@@ -450,7 +506,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->nu = 5; c->coarse_tol = 1.e-1; c->coarse_maxit = 2000;           // multigrid.hpp:105,123
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
-    c->tail_max_width = 0; c->use_graph = 0;
+    c->tail_max_width = 129; c->use_graph = 0;
     c->rb_fast_arith = 0; c->rb_fused = 1;
 }
 
@@ -540,6 +596,12 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         dim3 g0 = march_grid(lv.g);
         max_partial = std::max(max_partial, (size_t)g0.x * g0.y);
         w = (w + 1) / 2;                                                  // domain.cpp:10
+    }
+    // persistent coarse tail: every level from lt down (side <= tail_max_width, replicated, at most 12 levels)
+    h->lt = -1;
+    if (cfg->tail_max_width > 0) {
+        for (int l = 0; l < L; ++l)
+            if (h->lv[l].g.w <= cfg->tail_max_width && !h->lv[l].sharded && L - l <= mgb::kTailMaxLevels) { h->lt = l; break; }
     }
     h->n_partial = max_partial;
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));

@@ -33,7 +33,7 @@ class GmgConfig:
     rank: int = 0
     n_ranks: int = 1
     nccl_id: bytes = b""
-    tail_max_width: int = 0
+    tail_max_width: int = 129
     use_graph: int = 0
     rb_fast_arith: int = 0
     rb_fused: int = 1

@@ -199,6 +199,28 @@ def test_fast_path_reaches_reference_solution(mode):
     assert abs(hist.size - h_ref.size) <= 1, (hist.size, h_ref.size)
 
 
+@pytest.mark.parametrize("kind,restr", [(G.GS_LEX, G.INJECTION), (G.JACOBI, G.INJECTION), (G.GS_RB, G.FULL_WEIGHTING),
+                                        (G.GS_RB, G.HALF_INJECTION)])
+@pytest.mark.parametrize("N,L", [(257, 8), (385, 5), (65, 6)])
+def test_persistent_coarse_tail_equals_per_level_launches(kind, restr, N, L):
+    """the single-CTA coarse tail (restriction, device-side coarse-solve loop, upward leg) gives the
+    same field, bit for bit, and the same coarse-solve sweep counts as one launch per operator"""
+    b = oracle.gmg().rhs(N, W, 1)
+    res = []
+    for tail in (0, 129, 1 << 20):
+        with Gmg(GmgConfig(n=N, levels=L, smoother=kind, pre_smoother=kind, restriction=restr, tail_max_width=tail)) as g:
+            g.set_rhs(b.reshape(N, N)); g.set_u(None)
+            info = []
+            for _ in range(3):
+                g.smooth(0, kind, 2, sol=G.VEC_U, rhs=G.VEC_F)
+                info.append(g.cycle())
+            res.append((g.get_u(), info))
+    for u, info in res[1:]:
+        assert np.array_equal(u, res[0][0])
+        assert [i[1] for i in info] == [i[1] for i in res[0][1]]
+        assert np.allclose([i[0] for i in info], [i[0] for i in res[0][1]], rtol=1e-10)
+
+
 def test_device_sampled_rhs_close_to_host(orc):
     N = 129
     with Gmg(GmgConfig(n=N, levels=3)) as g:

@@ -62,12 +62,21 @@ def main():
         c.set_rhs_test(1); c.set_u(None); c.run_cycles(1)
         t2 = Timer(); c.sync()
         t2.start(c.stream())
-        for _ in range(a.reps):
-            c.cycle()
+        c.run_cycles(a.reps * 4, want_relres=False)
         t2.stop(c.stream())
-        ms = t2.elapsed_ms() / a.reps
+        ms = t2.elapsed_ms() / (a.reps * 4)
         out["coarse cycle from level 3 down"] = {"ms": ms}
         print(f"{'cycle of the (n-1)/8+1 problem (levels 3+)':42s} {ms:9.4f} ms")
+    for (cn, cl) in ((129, 7), (257, 8), (513, 9), (1025, 10)):
+        c = Gmg(GmgConfig.fast(cn, cl, rb_fast_arith=a.fast))
+        c.set_rhs_test(1); c.set_u(None); c.run_cycles(1)
+        t2 = Timer(); c.sync()
+        t2.start(c.stream())
+        c.run_cycles(a.reps * 4, want_relres=False)
+        t2.stop(c.stream())
+        ms = t2.elapsed_ms() / (a.reps * 4)
+        out[f"driver iteration of a {cn}^2 problem"] = {"ms": ms}
+        print(f"{'driver iteration of a %d^2 problem' % cn:42s} {ms:9.4f} ms")
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)
 
