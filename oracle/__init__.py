@@ -210,3 +210,212 @@ def ref_gmg():
     if _ref_gmg is None and os.path.exists(_REF_GMG_SO):
         _ref_gmg = GmgReference()
     return _ref_gmg
+
+
+# ---------------------------------------------------------------------------------------------------
+# AMG
+# ---------------------------------------------------------------------------------------------------
+_ip = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+class Csr:
+    """plain CSR triple (int64 indices) as the checkers exchange it"""
+
+    def __init__(self, n_rows, n_cols, ptr, col, val):
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int64)
+        self.val = np.ascontiguousarray(val, dtype=np.float64)
+
+    @property
+    def nnz(self):
+        return int(self.ptr[-1])
+
+    def same_as(self, o):
+        return (self.n_rows == o.n_rows and self.n_cols == o.n_cols and np.array_equal(self.ptr, o.ptr)
+                and np.array_equal(self.col, o.col) and np.array_equal(self.val, o.val))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.val, self.col, self.ptr), shape=(self.n_rows, self.n_cols))
+
+
+class AmgOracle:
+    """Restatement of AMG/ (oracle/amg_oracle.c)."""
+
+    def __init__(self, path=_ORACLE_SO):
+        if not os.path.exists(path):
+            build(ref=False)
+        L = self.lib = C.CDLL(path)
+        L.amgo_gs_sweep.argtypes = [C.c_int64, _ip, _ip, _dp, _dp, _dp]
+        L.amgo_gs_sweep_masked.argtypes = [C.c_int64, _ip, _ip, _dp, _ip, _dp, _dp]
+        L.amgo_residual.argtypes = [C.c_int64, _ip, _ip, _dp, _dp, _dp, C.c_void_p]
+        L.amgo_residual.restype = C.c_double
+        L.amgo_restrict.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, _dp]
+        L.amgo_prolong_add.argtypes = [C.c_int64, _ip, _ip, _dp, _dp, _dp]
+        L.amgo_build.argtypes = [C.c_int64, _ip, _ip, _dp, _dp, C.c_int, C.c_void_p]
+        L.amgo_build.restype = C.c_void_p
+        L.amgo_free.argtypes = [C.c_void_p]
+        L.amgo_levels.argtypes = [C.c_void_p]
+        L.amgo_level_info.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int64)] * 4
+        L.amgo_get_A.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp]
+        L.amgo_get_P.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp]
+        L.amgo_get_rhs.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.amgo_get_cf.argtypes = [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]
+        L.amgo_pass.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int]
+        L.amgo_pass.restype = C.c_double
+
+    def gs(self, A, b, x, sweeps=1):
+        for _ in range(sweeps):
+            self.lib.amgo_gs_sweep(A.n_rows, A.ptr, A.col, A.val, x, b)
+        return x
+
+    def residual(self, A, x, b):
+        r = np.zeros(A.n_rows)
+        nrm = self.lib.amgo_residual(A.n_rows, A.ptr, A.col, A.val, x, b, r.ctypes.data)
+        return nrm, r
+
+    def restrict(self, P, xf):
+        xc = np.zeros(P.n_cols)
+        self.lib.amgo_restrict(P.n_rows, P.n_cols, P.ptr, P.col, P.val, xf, xc)
+        return xc
+
+    def prolong_add(self, P, xc, xf):
+        self.lib.amgo_prolong_add(P.n_rows, P.ptr, P.col, P.val, xc, xf)
+        return xf
+
+    def build(self, A, rhs, levels, starts=None):
+        st = None
+        if starts is not None:
+            st = np.ascontiguousarray(starts, dtype=np.int64)
+        h = self.lib.amgo_build(A.n_rows, A.ptr, A.col, A.val, rhs, levels, st.ctypes.data if st is not None else None)
+        if not h:
+            raise ValueError("bad level count")
+        return AmgHierarchy(self, h)
+
+
+class AmgHierarchy:
+    def __init__(self, o, h):
+        self.o, self.h = o, h
+        self.levels = o.lib.amgo_levels(h)
+
+    def __del__(self):
+        try:
+            self.o.lib.amgo_free(self.h)
+        except Exception:
+            pass
+
+    def info(self, l):
+        v = [C.c_int64() for _ in range(4)]
+        self.o.lib.amgo_level_info(self.h, l, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)          # n, nnzA, nnzP, ncP
+
+    def A(self, l):
+        n, nnz, _, _ = self.info(l)
+        ptr, col, val = np.zeros(n + 1, np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        self.o.lib.amgo_get_A(self.h, l, ptr, col, val)
+        return Csr(n, n, ptr, col[:nnz], val[:nnz])
+
+    def P(self, l):
+        n, _, nnz, nc = self.info(l)
+        ptr, col, val = np.zeros(n + 1, np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        self.o.lib.amgo_get_P(self.h, l, ptr, col, val)
+        return Csr(n, nc, ptr, col[:nnz], val[:nnz])
+
+    def rhs(self, l):
+        b = np.zeros(self.info(l)[0])
+        self.o.lib.amgo_get_rhs(self.h, l, b)
+        return b
+
+    def cf(self, l):
+        m = np.zeros(self.info(l)[0], np.uint8)
+        self.o.lib.amgo_get_cf(self.h, l, m)
+        return m
+
+    def apply(self, x, pre=10, coarse=200, post=10):
+        """AMG::apply_AMG after initialization; returns the level-0 residual norm"""
+        return self.o.lib.amgo_pass(self.h, x, pre, coarse, post)
+
+
+class AmgReference:
+    """The reference's own AMG classes (oracle/_ref/libamgref.so); one hierarchy at a time."""
+
+    def __init__(self, path=_REF_AMG_SO):
+        L = self.lib = C.CDLL(path)
+        L.amgref_set_starts.argtypes = [_ip, C.c_int]
+        L.amgref_assemble.argtypes = [C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.amgref_get_system.argtypes = [_ip, _ip, _dp, _dp]
+        L.amgref_build.argtypes = [C.c_long, _ip, _ip, _dp, _dp, _dp, C.c_int]
+        L.amgref_build.restype = C.c_int
+        L.amgref_level_info.argtypes = [C.c_int] + [C.POINTER(C.c_long)] * 4
+        L.amgref_get_A.argtypes = [C.c_int, _ip, _ip, _dp]
+        L.amgref_get_P.argtypes = [C.c_int, _ip, _ip, _dp]
+        L.amgref_get_rhs.argtypes = [C.c_int, _dp]
+        L.amgref_pass.argtypes = [_dp]
+        L.amgref_pass.restype = C.c_double
+        L.amgref_gs.argtypes = [C.c_long, _ip, _ip, _dp, _dp, _dp, C.c_int]
+        L.amgref_set_threads.argtypes = [C.c_int]
+        L.amgref_set_threads(1)       # the reference's OpenMP loops race on std::map (AMG.hpp:314-331)
+
+    def assemble(self, msh_path):
+        n, nnz = C.c_long(), C.c_long()
+        self.lib.amgref_assemble(msh_path.encode(), C.byref(n), C.byref(nnz))
+        ptr, col, val = np.zeros(n.value + 1, np.int64), np.zeros(nnz.value, np.int64), np.zeros(nnz.value)
+        rhs = np.zeros(n.value)
+        self.lib.amgref_get_system(ptr, col, val, rhs)
+        return Csr(n.value, n.value, ptr, col, val), rhs
+
+    def build(self, A, rhs, levels, starts, x0=None):
+        st = np.ascontiguousarray(starts, dtype=np.int64)
+        self.lib.amgref_set_starts(st, st.size)
+        x0 = np.zeros(A.n_rows) if x0 is None else x0
+        return self.lib.amgref_build(A.n_rows, A.ptr, A.col, A.val, rhs, x0, levels)
+
+    def info(self, l):
+        v = [C.c_long() for _ in range(4)]
+        self.lib.amgref_level_info(l, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def A(self, l):
+        n, nnz, _, _ = self.info(l)
+        ptr, col, val = np.zeros(n + 1, np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        self.lib.amgref_get_A(l, ptr, col, val)
+        return Csr(n, n, ptr, col[:nnz], val[:nnz])
+
+    def P(self, l):
+        n, _, nnz, nc = self.info(l)
+        ptr, col, val = np.zeros(n + 1, np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        self.lib.amgref_get_P(l, ptr, col, val)
+        return Csr(n, nc, ptr, col[:nnz], val[:nnz])
+
+    def rhs(self, l):
+        b = np.zeros(self.info(l)[0])
+        self.lib.amgref_get_rhs(l, b)
+        return b
+
+    def apply(self):
+        x = np.zeros(self.info(0)[0])
+        r = self.lib.amgref_pass(x)
+        return x, r
+
+    def gs(self, A, b, x, sweeps=1):
+        self.lib.amgref_gs(A.n_rows, A.ptr, A.col, A.val, b, x, sweeps)
+        return x
+
+
+_amg = None
+_ref_amg = None
+
+
+def amg():
+    global _amg
+    if _amg is None:
+        _amg = AmgOracle()
+    return _amg
+
+
+def ref_amg():
+    global _ref_amg
+    if _ref_amg is None and os.path.exists(_REF_AMG_SO):
+        _ref_amg = AmgReference()
+    return _ref_amg
