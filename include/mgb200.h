@@ -152,6 +152,67 @@ int mgb_gmg_reset_stats(mgb_gmg_t h);
 void *mgb_gmg_stream(mgb_gmg_t h);
 int mgb_gmg_sync(mgb_gmg_t h);
 
+/* =====================================================================================================
+ * AMG on a CSR operator (reference: AMG/, citations relative to that directory)
+ * ===================================================================================================== */
+typedef struct mgb_amg_config {
+    int levels;            /* number_of_levels (src/main.cpp:126: 5)                                   */
+    double eps;            /* strength threshold EPSILON (include/AMG.hpp:21: 0.2)                     */
+    int smoother;          /* MGB_SMOOTH_GS_LEX: lexicographic GS reproduced exactly by level scheduling
+                              (include/Utilities.hpp:44-58); MGB_SMOOTH_GS_RB: multicolour GS from an
+                              on-device greedy colouring (the fast path); MGB_SMOOTH_JACOBI                */
+    int pre_sweeps;        /* src/AMG.cpp:287 (10) */
+    int coarse_sweeps;     /* src/AMG.cpp:295 (200) */
+    int post_sweeps;       /* src/AMG.cpp:302 (10) */
+    int exact_order;       /* 1: one thread per row, terms in ascending column order, unfused IEEE ops (bit-identical
+                              to the reference's loops); 0: sub-warp-per-row vector kernels with __shfl reductions */
+    int device;
+    int64_t start_index[16]; /* node the C/F splitting of level l starts from; the reference draws it from
+                              std::random_device (src/Utilities.cpp:30-40); < 0 selects n/2 */
+    int reserved[8];
+} mgb_amg_config;
+
+typedef struct mgb_amg *mgb_amg_t;
+
+void mgb_amg_config_default(mgb_amg_config *cfg);   /* the reference's constants, exact lexicographic GS */
+void mgb_amg_config_fast(mgb_amg_config *cfg);      /* multicolour GS + vector kernels */
+
+/* replaces Matrix/CSRMatrix + the AMG constructor + AMG::initialization() (include/AMG.hpp:33-41,
+ * src/AMG.cpp:76-120): takes the level-0 operator as CSR (rows sorted by column, as Matrix's std::map
+ * yields them; exact zeros are dropped as CSRMatrix::copy_from does) and the right-hand side, builds
+ * the hierarchy (strength, C/F split, direct interpolation, Galerkin operators, restricted right-hand
+ * sides) and uploads it.  x starts at zero on every level (src/main.cpp:125). */
+int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *row_ptr, const int64_t *col,
+                            const double *val, const double *rhs, mgb_amg_t *out);
+void mgb_amg_destroy(mgb_amg_t h);
+
+/* hierarchy queries (the reference prints the level sizes, src/AMG.cpp:85-86,111) */
+int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t *nnz_p, size_t *n_coarse,
+                       int *n_wavefronts, int *n_colours);
+/* which: 0 = A_level, 1 = P_level (level+1 -> level); arrays sized from mgb_amg_level_info */
+int mgb_amg_get_matrix(mgb_amg_t h, int level, int which, int64_t *row_ptr, int64_t *col, double *val);
+/* which: 0 = wavefront of each row in the level schedule of lexicographic GS, 1 = colour of each row */
+int mgb_amg_get_schedule(mgb_amg_t h, int level, int which, int *group_of_row);
+/* which: 0 = x_level, 1 = rhs_level, 2 = last residual vector of that level */
+int mgb_amg_get_vector(mgb_amg_t h, int level, int which, double *host);
+int mgb_amg_set_vector(mgb_amg_t h, int level, int which, const double *host);
+
+/* replaces AMG::apply_smoother_operator (src/AMG.cpp:236-254) */
+int mgb_amg_smooth(mgb_amg_t h, int level, int kind, int sweeps);
+/* replaces AMG::apply_restriction_operator(level) (src/AMG.cpp:50-74): x_level = P^T x_{level-1} */
+int mgb_amg_restrict(mgb_amg_t h, int level);
+/* replaces AMG::apply_prolungation_operator(level) (src/AMG.cpp:218-232): x_level += P x_{level+1} */
+int mgb_amg_prolong(mgb_amg_t h, int level);
+/* replaces AMG::compute_residual(level) (src/AMG.cpp:256-275): ||rhs - A x||_2 */
+int mgb_amg_residual(mgb_amg_t h, int level, double *norm);
+/* replaces the body of AMG::apply_AMG() after initialization (src/AMG.cpp:282-304) */
+int mgb_amg_apply(mgb_amg_t h, double *residual_norm);
+
+int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
+int mgb_amg_reset_stats(mgb_amg_t h);
+void *mgb_amg_stream(mgb_amg_t h);
+int mgb_amg_sync(mgb_amg_t h);
+
 /* CUDA-event timer on a stream of this library (stream = mgb_gmg_stream()/mgb_amg_stream()) */
 typedef struct mgb_timer *mgb_timer_t;
 int mgb_timer_create(mgb_timer_t *t);

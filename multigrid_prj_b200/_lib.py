@@ -29,6 +29,13 @@ class GmgStatsStruct(C.Structure):
                 ("bytes_algorithmic", C.c_double), ("reserved", C.c_int * 8)]
 
 
+class AmgConfigStruct(C.Structure):
+    # mirrors mgb_amg_config in include/mgb200.h
+    _fields_ = [("levels", C.c_int), ("eps", C.c_double), ("smoother", C.c_int), ("pre_sweeps", C.c_int),
+                ("coarse_sweeps", C.c_int), ("post_sweeps", C.c_int), ("exact_order", C.c_int), ("device", C.c_int),
+                ("start_index", C.c_int64 * 16), ("reserved", C.c_int * 8)]
+
+
 # every symbol include/mgb200.h declares: name -> (restype, argtypes)
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 _pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -58,6 +65,24 @@ SYMBOLS = {
     "mgb_gmg_reset_stats": (_i, [_vp]),
     "mgb_gmg_stream": (_vp, [_vp]),
     "mgb_gmg_sync": (_i, [_vp]),
+    "mgb_amg_config_default": (None, [C.POINTER(AmgConfigStruct)]),
+    "mgb_amg_config_fast": (None, [C.POINTER(AmgConfigStruct)]),
+    "mgb_amg_create_from_csr": (_i, [C.POINTER(AmgConfigStruct), C.c_size_t, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "mgb_amg_destroy": (None, [_vp]),
+    "mgb_amg_level_info": (_i, [_vp, _i] + [C.POINTER(C.c_size_t)] * 4 + [_pi, _pi]),
+    "mgb_amg_get_matrix": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "mgb_amg_get_schedule": (_i, [_vp, _i, _i, _vp]),
+    "mgb_amg_get_vector": (_i, [_vp, _i, _i, _vp]),
+    "mgb_amg_set_vector": (_i, [_vp, _i, _i, _vp]),
+    "mgb_amg_smooth": (_i, [_vp, _i, _i, _i]),
+    "mgb_amg_restrict": (_i, [_vp, _i]),
+    "mgb_amg_prolong": (_i, [_vp, _i]),
+    "mgb_amg_residual": (_i, [_vp, _i, _pd]),
+    "mgb_amg_apply": (_i, [_vp, _pd]),
+    "mgb_amg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
+    "mgb_amg_reset_stats": (_i, [_vp]),
+    "mgb_amg_stream": (_vp, [_vp]),
+    "mgb_amg_sync": (_i, [_vp]),
     "mgb_nccl_unique_id": (_i, [C.POINTER(C.c_ubyte * 128)]),
     "mgb_last_error": (C.c_char_p, []),
     "mgb_version": (C.c_char_p, []),

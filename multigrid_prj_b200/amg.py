@@ -1,0 +1,116 @@
+"""Thin Python handle over the AMG part of the C ABI (tests and bench only).
+
+Names follow the reference (AMG/include/AMG.hpp): `Amg(A, rhs, levels)` is the constructor followed
+by `initialization()`, `apply()` is the body of `apply_AMG()`, `smooth/restrict/prolong/residual` are
+`apply_smoother_operator / apply_restriction_operator / apply_prolungation_operator / compute_residual`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import AmgConfigStruct, GmgStatsStruct, check, load
+
+GS_LEX, JACOBI, GS_MULTICOLOUR = 0, 1, 3
+
+
+class Amg:
+    def __init__(self, ptr, col, val, rhs, levels=5, fast=False, starts=None, **kw):
+        self.lib = load()
+        c = AmgConfigStruct()
+        (self.lib.mgb_amg_config_fast if fast else self.lib.mgb_amg_config_default)(C.byref(c))
+        c.levels = levels
+        for k, v in kw.items():
+            setattr(c, k, v)
+        if starts is not None:
+            for i, s in enumerate(starts):
+                c.start_index[i] = int(s)
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int64)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        self.n = ptr.size - 1
+        self.levels = levels
+        self.h = C.c_void_p()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self.lib.mgb_amg_create_from_csr(C.byref(c), self.n, p(ptr), p(col), p(val), p(rhs), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.mgb_amg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self, level):
+        v = [C.c_size_t() for _ in range(4)]
+        w, k = C.c_int(), C.c_int()
+        check(self.lib.mgb_amg_level_info(self.h, level, *[C.byref(x) for x in v], C.byref(w), C.byref(k)))
+        return {"n": v[0].value, "nnz_a": v[1].value, "nnz_p": v[2].value, "n_coarse": v[3].value,
+                "wavefronts": w.value, "colours": k.value}
+
+    def matrix(self, level, which):
+        """(ptr, col, val) of A_level (which=0) or P_level (which=1)"""
+        i = self.info(level)
+        nnz = i["nnz_a"] if which == 0 else i["nnz_p"]
+        ptr, col, val = np.zeros(i["n"] + 1, np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self.lib.mgb_amg_get_matrix(self.h, level, which, p(ptr), p(col), p(val)))
+        return ptr, col[:nnz], val[:nnz]
+
+    def schedule(self, level, which):
+        """wavefront (which=0) or colour (which=1) of every row"""
+        out = np.zeros(max(self.info(level)["n"], 1), np.int32)
+        check(self.lib.mgb_amg_get_schedule(self.h, level, which, out.ctypes.data_as(C.c_void_p)))
+        return out[:self.info(level)["n"]]
+
+    def vector(self, level, which=0):
+        out = np.zeros(max(self.info(level)["n"], 1))
+        check(self.lib.mgb_amg_get_vector(self.h, level, which, out.ctypes.data_as(C.c_void_p)))
+        return out[:self.info(level)["n"]]
+
+    def set_vector(self, level, which, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        check(self.lib.mgb_amg_set_vector(self.h, level, which, a.ctypes.data_as(C.c_void_p)))
+
+    def smooth(self, level, kind, sweeps):
+        check(self.lib.mgb_amg_smooth(self.h, level, kind, sweeps))
+
+    def restrict(self, level):
+        check(self.lib.mgb_amg_restrict(self.h, level))
+
+    def prolong(self, level):
+        check(self.lib.mgb_amg_prolong(self.h, level))
+
+    def residual(self, level=0):
+        r = C.c_double()
+        check(self.lib.mgb_amg_residual(self.h, level, C.byref(r)))
+        return r.value
+
+    def apply(self, want_residual=True):
+        r = C.c_double()
+        check(self.lib.mgb_amg_apply(self.h, C.byref(r) if want_residual else None))
+        return r.value
+
+    def sync(self):
+        check(self.lib.mgb_amg_sync(self.h))
+
+    def stream(self):
+        return self.lib.mgb_amg_stream(self.h)
+
+    def stats(self):
+        s = GmgStatsStruct()
+        check(self.lib.mgb_amg_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_ if k != "reserved"}
+
+    def reset_stats(self):
+        check(self.lib.mgb_amg_reset_stats(self.h))

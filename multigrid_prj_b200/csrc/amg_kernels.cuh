@@ -1,0 +1,241 @@
+// amg_kernels.cuh -- sm_100a kernels of the AMG solve phase on device-resident CSR levels.
+//
+// Storage per level (HBM, SoA): int32 row_ptr[n+1], int32 col[nnz], fp64 val[nnz], fp64 diag[n]
+// (the reference keeps an AoS pair<size_t,double>[nnz] and finds a_ii by a linear scan on every row
+// visit, AMG/src/CSRMatrix.cpp:24-52); the transfer operator is stored twice, P (n x nc) for
+// x_f += P x_c and R = P^T (nc x n, rows sorted by fine index) so that restriction is a gather
+// SpMV without atomics.
+//
+// Two families of kernels:
+//  * exact-order kernels (one thread per row, terms added in ascending column order with unfused
+//    IEEE operations): bit-identical to the reference's serial loops -- the parity path;
+//  * vector kernels (a sub-warp of kLanes lanes per row, __shfl_xor tree reduction): the fast path,
+//    equal to the exact ones up to summation order.
+// Lexicographic Gauss-Seidel is reproduced EXACTLY by level scheduling (rows grouped into wavefronts
+// whose members do not depend on one another); the reordered fast smoother is multicolour
+// Gauss-Seidel from an on-device greedy (Jones-Plassmann) colouring.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgb {
+
+struct CsrDev {
+    int n_rows, n_cols, nnz;
+    const int *ptr, *col;
+    const double *val;
+};
+
+constexpr int kLanes = 8;        // lanes per row in the vector kernels (P1 rows hold ~7 entries)
+
+__device__ __forceinline__ double subwarp_sum(double v)
+{
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, kLanes);
+    return v;
+}
+
+// ---- Gauss-Seidel row update, reference order (AMG/include/Utilities.hpp:44-58) --------------------------
+__device__ __forceinline__ void gs_row_exact(const CsrDev &A, const double *__restrict__ diag, double *x,
+                                             const double *__restrict__ b, int i)
+{
+    double sum = 0.;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        const int j = A.col[k];
+        if (j != i) sum = __dadd_rn(sum, __dmul_rn(A.val[k], x[j]));
+    }
+    x[i] = __ddiv_rn(__dsub_rn(b[i], sum), diag[i]);
+}
+
+// rows[first..last) are mutually independent (one wavefront of the level schedule, or one colour)
+__global__ void __launch_bounds__(256)
+k_amg_gs_rows_exact(CsrDev A, const double *__restrict__ diag, double *x, const double *__restrict__ b,
+                    const int *__restrict__ rows, int first, int last)
+{
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < last) gs_row_exact(A, diag, x, b, rows[t]);
+}
+
+// whole lexicographic sweeps by ONE CTA: loops over the wavefronts with a barrier in between, so a
+// sweep costs no launch per wavefront (parity mode on small and medium levels)
+__global__ void __launch_bounds__(1024)
+k_amg_gs_lex_cta(CsrDev A, const double *__restrict__ diag, double *x, const double *__restrict__ b,
+                 const int *__restrict__ wave_ptr, const int *__restrict__ wave_rows, int n_waves, int sweeps)
+{
+    for (int s = 0; s < sweeps; ++s)
+        for (int w = 0; w < n_waves; ++w) {
+            for (int t = wave_ptr[w] + threadIdx.x; t < wave_ptr[w + 1]; t += blockDim.x)
+                gs_row_exact(A, diag, x, b, wave_rows[t]);
+            __syncthreads();
+        }
+}
+
+// multicolour GS, vector form: kLanes lanes per row of one colour
+__global__ void __launch_bounds__(256)
+k_amg_gs_color_vec(CsrDev A, const double *__restrict__ diag, double *x, const double *__restrict__ b,
+                   const int *__restrict__ rows, int first, int last)
+{
+    const int lane = threadIdx.x & (kLanes - 1);
+    const int t = first + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const bool ok = t < last;
+    const int i = ok ? rows[t] : 0;
+    double sum = 0.;
+    if (ok)
+        for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) {
+            const int j = A.col[k];
+            if (j != i) sum += A.val[k] * x[j];
+        }
+    sum = subwarp_sum(sum);
+    if (ok && lane == 0) x[i] = (b[i] - sum) / diag[i];
+}
+
+// Jacobi: xnew = (b - sum_{j != i} a_ij x_j) / a_ii for every row (vector form)
+__global__ void __launch_bounds__(256)
+k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__restrict__ x, const double *__restrict__ b,
+                 double *__restrict__ xnew)
+{
+    const int lane = threadIdx.x & (kLanes - 1);
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const bool ok = i < A.n_rows;
+    double sum = 0.;
+    if (ok)
+        for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) {
+            const int j = A.col[k];
+            if (j != i) sum += A.val[k] * x[j];
+        }
+    sum = subwarp_sum(sum);
+    if (ok && lane == 0) xnew[i] = (b[i] - sum) / diag[i];
+}
+
+// ---- residual r = b - A x and its squared norm (AMG/src/AMG.cpp:256-275) ------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+k_amg_residual(CsrDev A, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r,
+               double *__restrict__ partial)
+{
+    __shared__ double red[8];
+    double acc = 0.;
+    if (EXACT) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < A.n_rows) {
+            double Ax = 0.;
+            for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) Ax = __dadd_rn(Ax, __dmul_rn(A.val[k], x[A.col[k]]));
+            const double ri = __dsub_rn(b[i], Ax);
+            if (r) r[i] = ri;
+            acc = ri * ri;
+        }
+    } else {
+        const int lane = threadIdx.x & (kLanes - 1);
+        const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+        const bool ok = i < A.n_rows;
+        double Ax = 0.;
+        if (ok)
+            for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) Ax += A.val[k] * x[A.col[k]];
+        Ax = subwarp_sum(Ax);
+        if (ok && lane == 0) {
+            const double ri = b[i] - Ax;
+            if (r) r[i] = ri;
+            acc = ri * ri;
+        }
+    }
+    // CTA reduction (256 threads)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < 8 ? red[threadIdx.x] : 0.;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    }
+}
+
+// ---- transfers -------------------------------------------------------------------------------------------------
+// restriction x_c = P^T x_f as a gather over R = P^T (AMG/src/AMG.cpp:50-74): row m of R lists the fine
+// rows i in ascending order, which is the order in which the reference's scatter loop adds them
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+k_amg_spmv(CsrDev R, const double *__restrict__ xin, double *__restrict__ xout)
+{
+    if (EXACT) {
+        const int m = blockIdx.x * blockDim.x + threadIdx.x;
+        if (m >= R.n_rows) return;
+        double s = 0.;
+        for (int k = R.ptr[m]; k < R.ptr[m + 1]; ++k) s = __dadd_rn(s, __dmul_rn(R.val[k], xin[R.col[k]]));
+        xout[m] = s;
+    } else {
+        const int lane = threadIdx.x & (kLanes - 1);
+        const int m = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+        const bool ok = m < R.n_rows;
+        double s = 0.;
+        if (ok)
+            for (int k = R.ptr[m] + lane; k < R.ptr[m + 1]; k += kLanes) s += R.val[k] * xin[R.col[k]];
+        s = subwarp_sum(s);
+        if (ok && lane == 0) xout[m] = s;
+    }
+}
+
+// prolongation x_f += P x_c (AMG/src/AMG.cpp:218-232): the reference adds term by term INTO x_f[i]
+__global__ void __launch_bounds__(256)
+k_amg_prolong_add(CsrDev P, const double *__restrict__ xc, double *__restrict__ xf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_rows) return;
+    double v = xf[i];
+    for (int k = P.ptr[i]; k < P.ptr[i + 1]; ++k) v = __dadd_rn(v, __dmul_rn(P.val[k], xc[P.col[k]]));
+    xf[i] = v;
+}
+
+// ---- on-device greedy colouring (Jones-Plassmann rounds) ------------------------------------------------------------
+__device__ __forceinline__ unsigned hash32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// One round: an uncoloured row whose (hash, index) priority beats all its uncoloured neighbours takes the
+// smallest colour no neighbour holds.  colour[i] < 0 = uncoloured.  *remaining counts rows left.
+__global__ void __launch_bounds__(256)
+k_amg_colour_round(CsrDev A, const int *__restrict__ colour_in, int *__restrict__ colour_out, int *remaining)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_rows) return;
+    int c = colour_in[i];
+    if (c >= 0) { colour_out[i] = c; return; }
+    const unsigned pi = hash32((unsigned)i);
+    unsigned long long used = 0ull;
+    bool top = true;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        const int j = A.col[k];
+        if (j == i) continue;
+        const int cj = colour_in[j];
+        if (cj >= 0) { if (cj < 64) used |= 1ull << cj; }
+        else {
+            const unsigned pj = hash32((unsigned)j);
+            if (pj > pi || (pj == pi && j > i)) top = false;
+        }
+    }
+    if (top) c = __ffsll((long long)~used) - 1;
+    else atomicAdd(remaining, 1);
+    colour_out[i] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+k_amg_reduce(const double *__restrict__ partial, int n, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) out[0] = t;
+    }
+}
+
+}  // namespace mgb

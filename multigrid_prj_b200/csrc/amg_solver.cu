@@ -1,0 +1,620 @@
+// amg_solver.cu -- host side of the B200 AMG solve phase + its C ABI.
+//
+// Replaces (reference file:line, relative to AMG/):
+//   level-hierarchy storage   Matrix (vector<map>) / CSRMatrix (AoS)          include/CSRMatrix.hpp:19-121
+//   setup                     AMG::initialization + RestrictionOperator       src/AMG.cpp:76-120, include/AMG.hpp:105-369
+//   smoother / residual       Gauss_Seidel_iteration, AMG::compute_residual   include/Utilities.hpp:37-97, src/AMG.cpp:256-275
+//   transfers                 apply_restriction/prolungation_operator         src/AMG.cpp:50-74, 218-232
+//   cycle                     AMG::apply_AMG                                  src/AMG.cpp:277-308
+// The setup keeps the reference's semantics (strength threshold 0.2, its C/F state machine, direct
+// interpolation weights, Galerkin product evaluated in the reference's term order) but is written as
+// O(nnz) sparse loops on the host; the hierarchy is then uploaded once and the whole solve phase runs
+// on the device.  (Device-side setup is the next item of SURVEY.md section 8f.)
+#include "../../include/mgb200.h"
+#include "amg_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+int mgb_set_error(int code, const std::string &msg);   // gmg_solver.cu
+
+namespace {
+
+#define ACK(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return mgb_set_error(MGB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct HostCsr {
+    int n_rows = 0, n_cols = 0;
+    std::vector<int> ptr, col;
+    std::vector<double> val;
+    int nnz() const { return ptr.empty() ? 0 : ptr.back(); }
+    double at(int i, int j) const      // first entry of row i in column j, 0.0 when absent (CSRMatrix.cpp:24-40)
+    {
+        for (int k = ptr[i]; k < ptr[i + 1]; ++k) if (col[k] == j) return val[k];
+        return 0.0;
+    }
+};
+
+// strong couplings of a row: off-diagonal entries with |a_ij| >= eps * max_k |a_ik| (AMG.hpp:105-130)
+void strong_of_row(const HostCsr &A, int i, double eps, std::vector<int> &out)
+{
+    out.clear();
+    double big = 0.0;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
+        if (A.col[k] != i) big = std::max(big, std::fabs(A.val[k]));
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
+        if (A.col[k] != i && std::fabs(A.val[k]) >= eps * big) out.push_back(A.col[k]);
+}
+
+// C/F splitting with the reference's byte state machine (AMG.hpp:150-198): low six bits = number of
+// strong couplings still pointing at undecided nodes (+2 per neighbour turned fine), 0xC0 = fine.
+// The next seed is the largest index whose counter is still non-zero; counters only ever drop to zero,
+// so one pointer walking down from n-1 replaces the reference's full rescan.
+int split_coarse_fine(const HostCsr &A, double eps, long start, std::vector<unsigned char> &state)
+{
+    const int n = A.n_rows;
+    std::vector<int> sp(n + 1, 0), sc;
+    sc.reserve(A.nnz());
+    std::vector<int> tmp;
+    state.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+        strong_of_row(A, i, eps, tmp);
+        sc.insert(sc.end(), tmp.begin(), tmp.end());
+        sp[i + 1] = (int)sc.size();
+        state[i] = (unsigned char)tmp.size();
+    }
+    if (n == 0) return 0;
+    int seed = (int)std::min<long>(std::max<long>(start, 0), n - 1);
+    int fine = 0, walker = n - 1;
+    while (state[seed] & 0x3F) {
+        state[seed] = 0;                                            // coarse
+        for (int a = sp[seed]; a < sp[seed + 1]; ++a) {
+            const int c = sc[a];
+            if (!(state[c] & 0x3F)) continue;
+            state[c] = (unsigned char)((state[c] | 0xC0) & 0xC0);   // fine, counter cleared
+            ++fine;
+            for (int b = sp[c]; b < sp[c + 1]; ++b)
+                if (state[sc[b]] & 0x3F) state[sc[b]] = (unsigned char)(state[sc[b]] + 2);
+        }
+        while (walker >= 0 && !(state[walker] & 0x3F)) --walker;
+        if (walker >= 0) seed = walker;
+    }
+    return n - fine;
+}
+
+// direct interpolation (AMG.hpp:230-300): coarse rows are unit rows; a fine row i gets
+// w_ij = alpha a_ij / sum_k(alpha a_ik) over its strong coarse neighbours, alpha = (sum_{j!=i} a_ij) / (sum_k a_ik)
+HostCsr interpolation(const HostCsr &A, double eps, const std::vector<unsigned char> &state, int nc)
+{
+    const int n = A.n_rows;
+    std::vector<int> cidx(n, -1);
+    for (int i = 0, k = 0; i < n; ++i) if (!(state[i] & 0xC0)) cidx[i] = k++;
+    HostCsr P;
+    P.n_rows = n; P.n_cols = nc; P.ptr.assign(n + 1, 0);
+    std::vector<int> strong;
+    for (int i = 0; i < n; ++i) {
+        if (!(state[i] & 0xC0)) { P.col.push_back(cidx[i]); P.val.push_back(1.0); P.ptr[i + 1] = (int)P.col.size(); continue; }
+        double off_sum = 0.0;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) if (A.col[k] != i) off_sum += A.val[k];
+        strong_of_row(A, i, eps, strong);
+        double coarse_sum = 0.0;
+        for (int j : strong) if (!(state[j] & 0xC0)) coarse_sum += A.at(i, j);
+        const double alpha = off_sum / coarse_sum;
+        double norm = 0.0;
+        for (int j : strong) if (!(state[j] & 0xC0)) norm += alpha * A.at(i, j);
+        for (int j : strong)
+            if (!(state[j] & 0xC0)) {
+                const double w = alpha * A.at(i, j) / norm;
+                if (w != 0) { P.col.push_back(cidx[j]); P.val.push_back(w); }     // exact zeros are dropped (CSRMatrix.cpp:13-14)
+            }
+        P.ptr[i + 1] = (int)P.col.size();
+    }
+    return P;
+}
+
+HostCsr transpose(const HostCsr &M)
+{
+    HostCsr T;
+    T.n_rows = M.n_cols; T.n_cols = M.n_rows;
+    T.ptr.assign(T.n_rows + 1, 0);
+    for (int c : M.col) T.ptr[c + 1]++;
+    for (int i = 0; i < T.n_rows; ++i) T.ptr[i + 1] += T.ptr[i];
+    T.col.resize(M.col.size()); T.val.resize(M.val.size());
+    std::vector<int> fill(T.ptr.begin(), T.ptr.end() - 1);
+    for (int i = 0; i < M.n_rows; ++i)
+        for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) { int p = fill[M.col[k]]++; T.col[p] = i; T.val[p] = M.val[k]; }
+    return T;
+}
+
+// one sparse row of a product: out(c) = sum over the entries (k, v) of `row` taken in order, of v * B(k, c);
+// exact zeros dropped; columns emitted ascending
+struct RowAccumulator {
+    std::vector<int> stamp, touched;
+    std::vector<double> acc;
+    explicit RowAccumulator(int n) : stamp(n, -1), acc(n, 0.0) {}
+    void run(int tag, const int *rcol, const double *rval, int len, const HostCsr &B, HostCsr &out)
+    {
+        touched.clear();
+        for (int a = 0; a < len; ++a) {
+            const int k = rcol[a];
+            for (int b = B.ptr[k]; b < B.ptr[k + 1]; ++b) {
+                const int c = B.col[b];
+                if (stamp[c] != tag) { stamp[c] = tag; acc[c] = 0.0; touched.push_back(c); }
+                acc[c] += rval[a] * B.val[b];
+            }
+        }
+        std::sort(touched.begin(), touched.end());
+        for (int c : touched) if (acc[c] != 0) { out.col.push_back(c); out.val.push_back(acc[c]); }
+    }
+};
+
+// Galerkin operator in the reference's evaluation order (AMG.hpp:303-369):
+//   PtA(i,j) = sum_k A(j,k) P(k,i)  (k ascending; A taken as symmetric),   Ac(i,j) = sum_k PtA(i,k) P(k,j)
+HostCsr galerkin(const HostCsr &A, const HostCsr &P)
+{
+    const int n = A.n_rows, nc = P.n_cols;
+    HostCsr AP;                                  // AP(j, i) = PtA(i, j)
+    AP.n_rows = n; AP.n_cols = nc; AP.ptr.assign(n + 1, 0);
+    RowAccumulator ra(std::max(n, nc));
+    for (int j = 0; j < n; ++j) {
+        ra.run(j, &A.col[A.ptr[j]], &A.val[A.ptr[j]], A.ptr[j + 1] - A.ptr[j], P, AP);
+        AP.ptr[j + 1] = (int)AP.col.size();
+    }
+    HostCsr PtA = transpose(AP);
+    HostCsr Ac;
+    Ac.n_rows = nc; Ac.n_cols = nc; Ac.ptr.assign(nc + 1, 0);
+    RowAccumulator rb(std::max(n, nc));
+    for (int i = 0; i < nc; ++i) {
+        rb.run(i, &PtA.col[PtA.ptr[i]], &PtA.val[PtA.ptr[i]], PtA.ptr[i + 1] - PtA.ptr[i], P, Ac);
+        Ac.ptr[i + 1] = (int)Ac.col.size();
+    }
+    return Ac;
+}
+
+struct DevCsr {
+    int n_rows = 0, n_cols = 0, nnz = 0;
+    int *ptr = nullptr, *col = nullptr;
+    double *val = nullptr;
+    mgb::CsrDev view() const { return mgb::CsrDev{n_rows, n_cols, nnz, ptr, col, val}; }
+    void release() { cudaFree(ptr); cudaFree(col); cudaFree(val); ptr = col = nullptr; val = nullptr; }
+};
+
+struct Schedule {          // rows grouped into independent sets (wavefronts or colours)
+    int n_groups = 0;
+    std::vector<int> h_ptr, h_group;
+    int *d_ptr = nullptr, *d_rows = nullptr;
+    void release() { cudaFree(d_ptr); cudaFree(d_rows); d_ptr = d_rows = nullptr; }
+};
+
+struct AmgLevel {
+    HostCsr hA, hP;                       // host copies (hierarchy queries, schedules)
+    std::vector<double> h_rhs;
+    DevCsr A, P, R;
+    double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
+    Schedule lex, colour;
+};
+
+}  // namespace
+
+struct mgb_amg {
+    mgb_amg_config cfg{};
+    std::vector<AmgLevel> lv;
+    cudaStream_t st = nullptr;
+    double *d_partial = nullptr, *d_scal = nullptr, *h_scal = nullptr;
+    mgb_gmg_stats stats{};
+};
+
+namespace {
+
+int upload(const HostCsr &H, DevCsr &D, cudaStream_t st)
+{
+    D.n_rows = H.n_rows; D.n_cols = H.n_cols; D.nnz = H.nnz();
+    ACK(cudaMalloc(&D.ptr, sizeof(int) * (size_t)(H.n_rows + 1)));
+    ACK(cudaMalloc(&D.col, sizeof(int) * (size_t)std::max(D.nnz, 1)));
+    ACK(cudaMalloc(&D.val, sizeof(double) * (size_t)std::max(D.nnz, 1)));
+    ACK(cudaMemcpyAsync(D.ptr, H.ptr.data(), sizeof(int) * (size_t)(H.n_rows + 1), cudaMemcpyHostToDevice, st));
+    if (D.nnz) {
+        ACK(cudaMemcpyAsync(D.col, H.col.data(), sizeof(int) * (size_t)D.nnz, cudaMemcpyHostToDevice, st));
+        ACK(cudaMemcpyAsync(D.val, H.val.data(), sizeof(double) * (size_t)D.nnz, cudaMemcpyHostToDevice, st));
+    }
+    return MGB_OK;
+}
+
+int upload_schedule(const std::vector<int> &group_of_row, int n_groups, Schedule &S, cudaStream_t st)
+{
+    const int n = (int)group_of_row.size();
+    S.n_groups = n_groups;
+    S.h_group = group_of_row;
+    S.h_ptr.assign(n_groups + 1, 0);
+    for (int g : group_of_row) S.h_ptr[g + 1]++;
+    for (int g = 0; g < n_groups; ++g) S.h_ptr[g + 1] += S.h_ptr[g];
+    std::vector<int> rows(std::max(n, 1)), fill(S.h_ptr.begin(), S.h_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) rows[fill[group_of_row[i]]++] = i;       // ascending inside a group
+    ACK(cudaMalloc(&S.d_ptr, sizeof(int) * (size_t)(n_groups + 1)));
+    ACK(cudaMalloc(&S.d_rows, sizeof(int) * (size_t)std::max(n, 1)));
+    ACK(cudaMemcpyAsync(S.d_ptr, S.h_ptr.data(), sizeof(int) * (size_t)(n_groups + 1), cudaMemcpyHostToDevice, st));
+    ACK(cudaMemcpyAsync(S.d_rows, rows.data(), sizeof(int) * (size_t)std::max(n, 1), cudaMemcpyHostToDevice, st));
+    ACK(cudaStreamSynchronize(st));
+    return MGB_OK;
+}
+
+inline void tally(mgb_amg *h, double bytes) { h->stats.kernel_launches++; h->stats.bytes_algorithmic += bytes; }
+inline double sweep_bytes(const AmgLevel &L) { return 12. * L.A.nnz + 28. * L.A.n_rows; }
+
+// level schedule of the lexicographic sweep: wave(i) = 1 + max wave(j) over the couplings j < i
+int build_lex_schedule(mgb_amg *h, AmgLevel &L)
+{
+    const HostCsr &A = L.hA;
+    std::vector<int> wave(A.n_rows, 0);
+    int n_waves = A.n_rows ? 1 : 0;
+    for (int i = 0; i < A.n_rows; ++i) {
+        int w = 0;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) if (A.col[k] < i) w = std::max(w, wave[A.col[k]] + 1);
+        wave[i] = w;
+        n_waves = std::max(n_waves, w + 1);
+    }
+    return upload_schedule(wave, n_waves, L.lex, h->st);
+}
+
+// greedy colouring on the device (Jones-Plassmann rounds); the colour lists are then laid out on the host
+int build_colouring(mgb_amg *h, AmgLevel &L)
+{
+    const int n = L.A.n_rows;
+    int *c0 = nullptr, *c1 = nullptr, *d_left = nullptr;
+    ACK(cudaMalloc(&c0, sizeof(int) * (size_t)std::max(n, 1)));
+    ACK(cudaMalloc(&c1, sizeof(int) * (size_t)std::max(n, 1)));
+    ACK(cudaMalloc(&d_left, sizeof(int)));
+    ACK(cudaMemsetAsync(c0, 0xFF, sizeof(int) * (size_t)std::max(n, 1), h->st));
+    int left = n, rounds = 0;
+    while (left > 0 && rounds < 10000) {
+        ACK(cudaMemsetAsync(d_left, 0, sizeof(int), h->st));
+        mgb::k_amg_colour_round<<<(n + 255) / 256, 256, 0, h->st>>>(L.A.view(), c0, c1, d_left);
+        tally(h, 0.);
+        ACK(cudaMemcpyAsync(&left, d_left, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        ACK(cudaStreamSynchronize(h->st));
+        std::swap(c0, c1);
+        ++rounds;
+    }
+    std::vector<int> colour(std::max(n, 1));
+    ACK(cudaMemcpy(colour.data(), c0, sizeof(int) * (size_t)std::max(n, 1), cudaMemcpyDeviceToHost));
+    cudaFree(c0); cudaFree(c1); cudaFree(d_left);
+    colour.resize(n);
+    int nc = 0;
+    for (int c : colour) { if (c < 0) return mgb_set_error(MGB_ERR_STATE, "colouring did not finish"); nc = std::max(nc, c + 1); }
+    return upload_schedule(colour, nc, L.colour, h->st);
+}
+
+int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
+{
+    AmgLevel &L = h->lv[level];
+    const mgb::CsrDev A = L.A.view();
+    if (A.n_rows == 0 || sweeps <= 0) return MGB_OK;
+    if (kind == MGB_SMOOTH_GS_LEX) {
+        if (A.n_rows <= (1 << 18)) {
+            mgb::k_amg_gs_lex_cta<<<1, 1024, 0, h->st>>>(A, L.diag, L.x, L.b, L.lex.d_ptr, L.lex.d_rows, L.lex.n_groups, sweeps);
+            tally(h, sweep_bytes(L) * sweeps);
+        } else {
+            for (int s = 0; s < sweeps; ++s)
+                for (int w = 0; w < L.lex.n_groups; ++w) {
+                    const int a = L.lex.h_ptr[w], b = L.lex.h_ptr[w + 1];
+                    mgb::k_amg_gs_rows_exact<<<(b - a + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.lex.d_rows, a, b);
+                    tally(h, sweep_bytes(L) * (double)(b - a) / A.n_rows);
+                }
+        }
+    } else if (kind == MGB_SMOOTH_GS_RB) {            // multicolour Gauss-Seidel
+        for (int s = 0; s < sweeps; ++s)
+            for (int c = 0; c < L.colour.n_groups; ++c) {
+                const int a = L.colour.h_ptr[c], b = L.colour.h_ptr[c + 1];
+                if (h->cfg.exact_order)
+                    mgb::k_amg_gs_rows_exact<<<(b - a + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
+                else
+                    mgb::k_amg_gs_color_vec<<<((b - a) * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
+                tally(h, sweep_bytes(L) * (double)(b - a) / A.n_rows);
+            }
+    } else if (kind == MGB_SMOOTH_JACOBI) {
+        for (int s = 0; s < sweeps; ++s) {
+            mgb::k_amg_jacobi_vec<<<(A.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp);
+            tally(h, sweep_bytes(L));
+            std::swap(L.x, L.tmp);
+        }
+    } else
+        return mgb_set_error(MGB_ERR_ARG, "unknown AMG smoother");
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
+int do_residual(mgb_amg *h, int level, double *norm)
+{
+    AmgLevel &L = h->lv[level];
+    const mgb::CsrDev A = L.A.view();
+    int blocks;
+    if (h->cfg.exact_order) {
+        blocks = (A.n_rows + 255) / 256;
+        mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial);
+    } else {
+        blocks = (A.n_rows * mgb::kLanes + 255) / 256;
+        mgb::k_amg_residual<false><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial);
+    }
+    tally(h, sweep_bytes(L));
+    mgb::k_amg_reduce<<<1, 1024, 0, h->st>>>(h->d_partial, blocks, h->d_scal);
+    tally(h, 0.);
+    ACK(cudaGetLastError());
+    ACK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    *norm = std::sqrt(h->h_scal[0]);
+    return MGB_OK;
+}
+
+// x_{level} = P^T x_{level-1}  (AMG.cpp:50-74)
+int do_restrict(mgb_amg *h, int level)
+{
+    AmgLevel &F = h->lv[level - 1], &C = h->lv[level];
+    const mgb::CsrDev R = F.R.view();
+    if (R.n_rows == 0) return MGB_OK;
+    if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(R.n_rows + 255) / 256, 256, 0, h->st>>>(R, F.x, C.x);
+    else mgb::k_amg_spmv<false><<<(R.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, F.x, C.x);
+    tally(h, 12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols);
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
+// x_level += P x_{level+1}  (AMG.cpp:218-232)
+int do_prolong(mgb_amg *h, int level)
+{
+    AmgLevel &F = h->lv[level], &C = h->lv[level + 1];
+    const mgb::CsrDev P = F.P.view();
+    if (P.n_rows == 0) return MGB_OK;
+    mgb::k_amg_prolong_add<<<(P.n_rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x);
+    tally(h, 12. * P.nnz + 20. * P.n_rows + 8. * P.n_cols);
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void mgb_amg_config_default(mgb_amg_config *c)
+{
+    std::memset(c, 0, sizeof(*c));
+    c->levels = 5;                 // AMG/src/main.cpp:126
+    c->eps = 0.2;                  // AMG/include/AMG.hpp:21
+    c->smoother = MGB_SMOOTH_GS_LEX;
+    c->pre_sweeps = 10; c->coarse_sweeps = 200; c->post_sweeps = 10;      // AMG/src/AMG.cpp:287,295,302
+    c->exact_order = 1;
+    c->device = 0;
+    for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
+}
+
+void mgb_amg_config_fast(mgb_amg_config *c)
+{
+    mgb_amg_config_default(c);
+    c->smoother = MGB_SMOOTH_GS_RB;      // multicolour Gauss-Seidel
+    c->exact_order = 0;
+}
+
+int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
+                            const double *val, const double *rhs, mgb_amg_t *out)
+{
+    if (!cfg || !ptr || !col || !val || !rhs || !out) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->levels < 1 || cfg->levels > 16) return mgb_set_error(MGB_ERR_ARG, "1 <= levels <= 16");
+    if (n == 0 || n > (size_t)1 << 30 || ptr[n] > (int64_t)INT32_MAX) return mgb_set_error(MGB_ERR_ARG, "matrix too large for int32 indices");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return mgb_set_error(MGB_ERR_CUDA, "no CUDA device: libmgb200 has no CPU fallback");
+    }
+    ACK(cudaSetDevice(cfg->device));
+    mgb_amg *h = new mgb_amg();
+    h->cfg = *cfg;
+    ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    h->lv.resize(cfg->levels);
+    // level 0: CSRMatrix::copy_from drops exact zeros (CSRMatrix.cpp:13-14); rows must be column-sorted (they come from a map)
+    {
+        HostCsr &A = h->lv[0].hA;
+        A.n_rows = A.n_cols = (int)n;
+        A.ptr.assign(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) {
+            for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
+                if (col[k] < 0 || col[k] >= (int64_t)n) { delete h; return mgb_set_error(MGB_ERR_ARG, "column index out of range"); }
+                if (k > ptr[i] && col[k] <= col[k - 1]) { delete h; return mgb_set_error(MGB_ERR_ARG, "rows must be sorted by column without duplicates"); }
+                if (val[k] != 0) { A.col.push_back((int)col[k]); A.val.push_back(val[k]); }
+            }
+            A.ptr[i + 1] = (int)A.col.size();
+        }
+        h->lv[0].h_rhs.assign(rhs, rhs + n);
+    }
+    // AMG::initialization (AMG.cpp:76-120)
+    for (int l = 1; l < cfg->levels; ++l) {
+        AmgLevel &F = h->lv[l - 1], &C = h->lv[l];
+        std::vector<unsigned char> state;
+        const long start = cfg->start_index[l - 1] >= 0 ? (long)cfg->start_index[l - 1] : F.hA.n_rows / 2;
+        const int nc = split_coarse_fine(F.hA, cfg->eps, start, state);
+        F.hP = interpolation(F.hA, cfg->eps, state, nc);
+        C.h_rhs.assign(nc, 0.0);                                                      // b_c = P^T b  (AMG.cpp:100-109)
+        for (int i = 0; i < F.hP.n_rows; ++i)
+            for (int k = F.hP.ptr[i]; k < F.hP.ptr[i + 1]; ++k) C.h_rhs[F.hP.col[k]] += F.hP.val[k] * F.h_rhs[i];
+        C.hA = galerkin(F.hA, F.hP);
+    }
+    // upload
+    size_t max_blocks = 1;
+    for (int l = 0; l < cfg->levels; ++l) {
+        AmgLevel &L = h->lv[l];
+        const int nl = L.hA.n_rows;
+        int rc;
+        if ((rc = upload(L.hA, L.A, h->st))) return rc;
+        std::vector<double> dg(std::max(nl, 1), 0.0);
+        for (int i = 0; i < nl; ++i) dg[i] = L.hA.at(i, i);
+        const size_t bytes = sizeof(double) * (size_t)std::max(nl, 1);
+        ACK(cudaMalloc(&L.diag, bytes)); ACK(cudaMalloc(&L.x, bytes)); ACK(cudaMalloc(&L.b, bytes)); ACK(cudaMalloc(&L.tmp, bytes));
+        ACK(cudaMemcpyAsync(L.diag, dg.data(), bytes, cudaMemcpyHostToDevice, h->st));
+        ACK(cudaMemsetAsync(L.x, 0, bytes, h->st));
+        if (nl) ACK(cudaMemcpyAsync(L.b, L.h_rhs.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, h->st));
+        ACK(cudaStreamSynchronize(h->st));
+        if (l + 1 < cfg->levels) {
+            if ((rc = upload(L.hP, L.P, h->st))) return rc;
+            HostCsr R = transpose(L.hP);
+            if ((rc = upload(R, L.R, h->st))) return rc;
+            ACK(cudaStreamSynchronize(h->st));
+        }
+        if ((rc = build_lex_schedule(h, L))) return rc;
+        if ((rc = build_colouring(h, L))) return rc;
+        max_blocks = std::max(max_blocks, (size_t)(nl * mgb::kLanes + 255) / 256 + 1);
+    }
+    ACK(cudaMalloc(&h->d_partial, sizeof(double) * max_blocks));
+    ACK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
+    ACK(cudaMallocHost(&h->h_scal, sizeof(double) * 4));
+    *out = h;
+    return MGB_OK;
+}
+
+void mgb_amg_destroy(mgb_amg_t h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    for (auto &L : h->lv) {
+        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release();
+        cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
+    }
+    cudaFree(h->d_partial); cudaFree(h->d_scal);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t *nnz_p, size_t *n_coarse,
+                       int *n_waves, int *n_colours)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "bad level");
+    const AmgLevel &L = h->lv[level];
+    if (n) *n = (size_t)L.hA.n_rows;
+    if (nnz_a) *nnz_a = (size_t)L.hA.nnz();
+    if (nnz_p) *nnz_p = (size_t)L.hP.nnz();
+    if (n_coarse) *n_coarse = (size_t)L.hP.n_cols;
+    if (n_waves) *n_waves = L.lex.n_groups;
+    if (n_colours) *n_colours = L.colour.n_groups;
+    return MGB_OK;
+}
+
+static int copy_csr(const HostCsr &M, int64_t *ptr, int64_t *col, double *val)
+{
+    for (int i = 0; i <= M.n_rows; ++i) ptr[i] = M.ptr[i];
+    for (int k = 0; k < M.nnz(); ++k) { col[k] = M.col[k]; val[k] = M.val[k]; }
+    return MGB_OK;
+}
+int mgb_amg_get_matrix(mgb_amg_t h, int level, int which, int64_t *ptr, int64_t *col, double *val)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !ptr || !col || !val) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
+    return copy_csr(which == 0 ? h->lv[level].hA : h->lv[level].hP, ptr, col, val);
+}
+
+int mgb_amg_get_schedule(mgb_amg_t h, int level, int which, int *group_of_row)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !group_of_row) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
+    const Schedule &S = which == 0 ? h->lv[level].lex : h->lv[level].colour;
+    std::copy(S.h_group.begin(), S.h_group.end(), group_of_row);
+    return MGB_OK;
+}
+
+int mgb_amg_get_vector(mgb_amg_t h, int level, int which, double *host)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !host) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
+    AmgLevel &L = h->lv[level];
+    ACK(cudaSetDevice(h->cfg.device));
+    const double *src = which == 0 ? L.x : (which == 1 ? L.b : L.tmp);
+    if (L.A.n_rows) ACK(cudaMemcpyAsync(host, src, sizeof(double) * (size_t)L.A.n_rows, cudaMemcpyDeviceToHost, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    return MGB_OK;
+}
+
+int mgb_amg_set_vector(mgb_amg_t h, int level, int which, const double *host)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !host || which < 0 || which > 1) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
+    AmgLevel &L = h->lv[level];
+    ACK(cudaSetDevice(h->cfg.device));
+    if (L.A.n_rows) ACK(cudaMemcpyAsync(which == 0 ? L.x : L.b, host, sizeof(double) * (size_t)L.A.n_rows, cudaMemcpyHostToDevice, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    return MGB_OK;
+}
+
+int mgb_amg_smooth(mgb_amg_t h, int level, int kind, int sweeps)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "Invalid level");   // AMG.cpp:237-240
+    if (sweeps <= 0) return mgb_set_error(MGB_ERR_ARG, "Invalid number of iterations");                         // AMG.cpp:241-244
+    ACK(cudaSetDevice(h->cfg.device));
+    return do_smooth(h, level, kind, sweeps);
+}
+
+int mgb_amg_restrict(mgb_amg_t h, int level)
+{
+    if (!h || level < 1 || level >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "Level does not exist");   // AMG.cpp:51-57
+    ACK(cudaSetDevice(h->cfg.device));
+    return do_restrict(h, level);
+}
+
+int mgb_amg_prolong(mgb_amg_t h, int level)
+{
+    if (!h || level < 0 || level + 1 >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "Level does not exist");
+    ACK(cudaSetDevice(h->cfg.device));
+    return do_prolong(h, level);
+}
+
+int mgb_amg_residual(mgb_amg_t h, int level, double *norm)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !norm) return mgb_set_error(MGB_ERR_ARG, "bad level");
+    ACK(cudaSetDevice(h->cfg.device));
+    return do_residual(h, level, norm);
+}
+
+// AMG::apply_AMG after initialization (AMG.cpp:282-304)
+int mgb_amg_apply(mgb_amg_t h, double *residual_norm)
+{
+    if (!h) return mgb_set_error(MGB_ERR_ARG, "null handle");
+    ACK(cudaSetDevice(h->cfg.device));
+    const int L = (int)h->lv.size();
+    int rc, i;
+    for (i = 0; i < L - 1; ++i) {
+        if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.pre_sweeps))) return rc;
+        if ((rc = do_restrict(h, i + 1))) return rc;
+    }
+    if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.coarse_sweeps))) return rc;
+    for (i--; i >= 0; --i) {
+        if ((rc = do_prolong(h, i))) return rc;
+        if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.post_sweeps))) return rc;
+    }
+    h->stats.cycles++;
+    if (residual_norm) return do_residual(h, 0, residual_norm);
+    return MGB_OK;
+}
+
+int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s)
+{
+    if (!h || !s) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    *s = h->stats;
+    return MGB_OK;
+}
+int mgb_amg_reset_stats(mgb_amg_t h)
+{
+    if (!h) return mgb_set_error(MGB_ERR_ARG, "null handle");
+    h->stats = mgb_gmg_stats{};
+    return MGB_OK;
+}
+void *mgb_amg_stream(mgb_amg_t h) { return h ? (void *)h->st : nullptr; }
+int mgb_amg_sync(mgb_amg_t h)
+{
+    if (!h) return mgb_set_error(MGB_ERR_ARG, "null handle");
+    ACK(cudaSetDevice(h->cfg.device));
+    ACK(cudaStreamSynchronize(h->st));
+    return MGB_OK;
+}
+
+}  // extern "C"

@@ -95,6 +95,9 @@ Part partition(size_t n, int levels, int n_ranks, int rank, int level)
 
 }  // namespace
 
+// shared with amg_solver.cu: records the thread's last error text and returns the code
+int mgb_set_error(int code, const std::string &msg) { return fail(code, msg); }
+
 struct mgb_gmg {
     mgb_gmg_config cfg{};
     std::vector<Level> lv;
