@@ -124,6 +124,10 @@ int mgb_gmg_restrict(mgb_gmg_t h);
 /* replaces InterpolationClass::interpolate (multigrid.cpp:3-27): E(level_coarse) -> E(level_coarse-1) */
 int mgb_gmg_prolong(mgb_gmg_t h, int level_coarse);
 
+/* the reference builds one SawtoothMGIteration object per smoother (main.cpp:54-56) over the same grids; the
+ * handle keeps one hierarchy and switches the cycle's parameters instead */
+int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double coarse_tol, int coarse_maxit);
+
 /* replaces SawtoothMGIteration::apply_iteration_to_vec (multigrid.hpp:126-145) applied to u.
  * coarse_relres = the value the reference prints per cycle; coarse_iters = coarse-solve sweeps. */
 int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters);

@@ -58,6 +58,7 @@ SYMBOLS = {
     "mgb_gmg_sumsq": (_i, [_vp, _i, _i, _pd]),
     "mgb_gmg_restrict": (_i, [_vp]),
     "mgb_gmg_prolong": (_i, [_vp, _i]),
+    "mgb_gmg_set_cycle": (_i, [_vp, _i, _i, _i, _d, _i]),
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
     "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),
     "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),

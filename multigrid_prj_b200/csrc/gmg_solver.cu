@@ -742,6 +742,17 @@ int mgb_gmg_prolong(mgb_gmg_t h, int level_coarse)
     return do_prolong(h, level_coarse);
 }
 
+int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double coarse_tol, int coarse_maxit)
+{
+    if (!h || smoother < 0 || smoother > 3 || restriction < 0 || restriction > 2 || nu < 0 || coarse_maxit < 0)
+        return fail(MGB_ERR_ARG, "bad cycle parameter");
+    if (smoother == MGB_SMOOTH_GS_LEX && h->cfg.n_ranks > 1)
+        return fail(MGB_ERR_ARG, "lexicographic GS is sequential across slabs; use one rank for parity mode");
+    h->cfg.smoother = smoother; h->cfg.restriction = restriction; h->cfg.nu = nu;
+    h->cfg.coarse_tol = coarse_tol; h->cfg.coarse_maxit = coarse_maxit;
+    return MGB_OK;
+}
+
 int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters)
 {
     if (!h) return fail(MGB_ERR_ARG, "null handle");

@@ -1,0 +1,513 @@
+// mgb200_gmg_facade.hpp -- the reference's GeometricMultigrid class API as thin handles over libmgb200.
+//
+// Same names, constructor signatures and operator* chaining as the reference
+// (GeometricMultigrid/include/{domain,linear_system,solvers,multigrid}.hpp), so that its driver
+// (src/main.cpp) compiles unchanged; every operator body is a call into the C ABI of include/mgb200.h.
+// There is no CPU arithmetic on grid data here and no fallback: without a B200 the first operator throws.
+//
+// Memory model.  The reference keeps every level in ONE fine-sized host vector and lets the caller own
+// it.  Here the device holds compact per-level arrays; a host vector is bound to a device slot the
+// first time an operator sees it (host -> device copy, strided gather for coarse levels), stays
+// device-resident across operator calls (no PCIe traffic inside `u * GS * GS * MG`), and is copied
+// back when (a) Utils::saveVectorOnFile is about to write it, (b) MultiGrid::sync_to_host is called,
+// (c) another host vector claims its slot, or (d) a facade operator object is destroyed.
+// Set MGB_FACADE_EAGER=1 to copy back after every operator (slow, but valid for callers that read the
+// vector between operator calls).  MGB_GMG_MODE=fast maps Gauss_Seidel_iteration to red-black GS and the
+// cycle's restriction to full weighting (the B200 fast path); the default reproduces the reference.
+#ifndef MGB200_GMG_FACADE_HPP
+#define MGB200_GMG_FACADE_HPP
+
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "mgb200.h"
+
+#ifndef TOL
+#define TOL 1e-11      // solvers.hpp:5
+#endif
+
+namespace MultiGrid {
+
+namespace detail {
+
+inline void ok(int rc)
+{
+    if (rc != MGB_OK) throw std::runtime_error(std::string("libmgb200: ") + mgb_last_error());
+}
+inline bool fast_mode()
+{
+    const char *m = std::getenv("MGB_GMG_MODE");
+    return m && std::strcmp(m, "fast") == 0;
+}
+inline bool eager()
+{
+    const char *m = std::getenv("MGB_FACADE_EAGER");
+    return m && m[0] == '1';
+}
+
+struct Slot {
+    const void *owner = nullptr;      // identity of the host object bound to this device vector
+    double *host = nullptr;           // its storage (fine-sized, strided for level > 0)
+    bool dirty = false;               // device copy is newer than the host copy
+};
+
+// one device hierarchy per (N, length, alpha); levels = deepest level any PoissonMatrix of that grid asked for
+struct Context {
+    size_t N = 0;
+    double length = 0, alpha = 0;
+    int want_levels = 1, levels = 0;
+    mgb_gmg_t h = nullptr;
+    Slot U, F, E[32], R[32];
+    std::vector<double> scratch;
+
+    ~Context() { if (h) mgb_gmg_destroy(h); }
+
+    Slot &slot(int which, int level) { return which == MGB_VEC_U ? U : which == MGB_VEC_F ? F : which == MGB_VEC_E ? E[level] : R[level]; }
+    size_t width(int level) const { size_t w = N; for (int l = 0; l < level; ++l) w = (w + 1) / 2; return w; }
+
+    void ensure()
+    {
+        if (h && levels >= want_levels) return;
+        flush_all();
+        if (h) { mgb_gmg_destroy(h); h = nullptr; U = F = Slot(); for (auto &s : E) s = Slot(); for (auto &s : R) s = Slot(); }
+        mgb_gmg_config c;
+        if (fast_mode()) mgb_gmg_config_fast(&c); else mgb_gmg_config_default(&c);
+        c.n = N; c.length = length; c.alpha = alpha; c.levels = want_levels;
+        if (const char *d = std::getenv("MGB_DEVICE")) c.device = std::atoi(d);
+        ok(mgb_gmg_create(&c, &h));
+        levels = want_levels;
+    }
+    void download(int which, int level)
+    {
+        Slot &s = slot(which, level);
+        if (!s.dirty || !s.host) return;
+        const size_t w = width(level), st = (size_t)1 << level;
+        if (level == 0) ok(mgb_gmg_get_level(h, 0, which, s.host));
+        else {
+            scratch.resize(w * w);
+            ok(mgb_gmg_get_level(h, level, which, scratch.data()));
+            for (size_t i = 0; i < w; ++i)
+                for (size_t j = 0; j < w; ++j) s.host[st * i * N + st * j] = scratch[i * w + j];   // domain.hpp:78-80
+        }
+        s.dirty = false;
+    }
+    void upload(int which, int level, const double *host)
+    {
+        const size_t w = width(level), st = (size_t)1 << level;
+        if (level == 0) ok(mgb_gmg_set_level(h, 0, which, host));
+        else {
+            scratch.resize(w * w);
+            for (size_t i = 0; i < w; ++i)
+                for (size_t j = 0; j < w; ++j) scratch[i * w + j] = host[st * i * N + st * j];
+            ok(mgb_gmg_set_level(h, level, which, scratch.data()));
+        }
+    }
+    // make `owner` the device-resident content of (which, level); uploads unless it already is
+    void bind(int which, int level, const void *owner, double *host)
+    {
+        ensure();
+        Slot &s = slot(which, level);
+        if (s.owner == owner) return;
+        download(which, level);
+        upload(which, level, host);
+        s.owner = owner; s.host = host; s.dirty = false;
+    }
+    void touched(int which, int level)
+    {
+        slot(which, level).dirty = true;
+        if (eager()) download(which, level);
+    }
+    void flush_owner(const void *owner)
+    {
+        if (!h) return;
+        if (U.owner == owner) download(MGB_VEC_U, 0);
+        for (int l = levels - 1; l >= 0; --l) {            // coarse first: finer levels hold the newer values
+            if (E[l].owner == owner) download(MGB_VEC_E, l);
+            if (R[l].owner == owner) download(MGB_VEC_R, l);
+        }
+    }
+    void flush_all()
+    {
+        if (!h) return;
+        download(MGB_VEC_U, 0);
+        for (int l = levels - 1; l >= 0; --l) { download(MGB_VEC_E, l); download(MGB_VEC_R, l); }
+    }
+};
+
+inline std::map<std::tuple<size_t, double, double>, std::unique_ptr<Context>> &registry()
+{
+    static std::map<std::tuple<size_t, double, double>, std::unique_ptr<Context>> r;
+    return r;
+}
+inline Context &context(size_t N, double length, double alpha, int level)
+{
+    auto &p = registry()[std::make_tuple(N, length, alpha)];
+    if (!p) { p = std::make_unique<Context>(); p->N = N; p->length = length; p->alpha = alpha; }
+    if (level + 1 > p->want_levels) p->want_levels = level + 1;
+    return *p;
+}
+inline void flush_everything() { for (auto &kv : registry()) kv.second->flush_all(); }
+
+// host storage of a right-hand side object: std::vector<double> or DataVector<double>
+template <class V> struct HostData { static double *get(V &v) { return v.data(); } };
+
+}  // namespace detail
+
+// bring the device-resident copy of a host vector (if any) back to the host
+inline void sync_to_host(const void *host_vector)
+{
+    for (auto &kv : detail::registry()) kv.second->flush_owner(host_vector);
+}
+inline void sync_all_to_host() { detail::flush_everything(); }
+
+// ---- geometry (domain.hpp:9-96, domain.cpp:4-38): pure host arithmetic ------------------------------------------
+class Domain {
+public:
+    virtual ~Domain() = default;
+    virtual std::tuple<double, double> coord(const size_t i, const size_t j) const = 0;
+    virtual std::tuple<size_t, size_t> meshIdx(size_t l) const = 0;
+    virtual std::tuple<double, double> operator[](const size_t i) const = 0;
+    virtual bool isOnBoundary(const size_t l) const = 0;
+    virtual std::array<size_t, 5> inRowConnections_a(const size_t l) = 0;
+    virtual size_t mask(const size_t l) const = 0;
+    virtual size_t getWidth() const = 0;
+    virtual size_t numBoundaryNodes() const = 0;
+    virtual size_t numConnections() const = 0;
+    virtual size_t N() const = 0;
+    virtual double h() const = 0;
+    virtual size_t getStep() const = 0;
+    // facade additions
+    virtual size_t fineSize() const = 0;
+    virtual double length() const = 0;
+    virtual size_t level() const = 0;
+};
+
+class SquareDomain : public Domain {
+    size_t m_size, step, m_level, width;
+    double m_length, m_h;
+
+public:
+    SquareDomain(const size_t size, const double length, const size_t level)
+        : m_size(size), step(1), m_level(level), width(size), m_length(length), m_h(length / (size - 1))
+    {
+        for (size_t i = 0; i < level; i++) { width = (width + 1) / 2; step *= 2; }
+    }
+    SquareDomain(const SquareDomain &dom, const size_t level) : SquareDomain(dom.m_size, dom.m_length, level) {}
+    std::tuple<size_t, size_t> meshIdx(size_t l) const override { return {l / m_size, l % m_size}; }
+    std::tuple<double, double> coord(const size_t i, const size_t j) const override { return {j * m_h, m_length - i * m_h}; }
+    std::tuple<double, double> operator[](const size_t l) const override { auto [i, j] = meshIdx(mask(l)); return coord(i, j); }
+    bool isOnBoundary(const size_t l) const override
+    {
+        auto [i, j] = meshIdx(l);
+        return i == 0 || j == 0 || i == m_size - 1 || j == m_size - 1;
+    }
+    std::array<size_t, 5> inRowConnections_a(const size_t l) override { return {l - width, l - 1, l, l + 1, l + width}; }
+    size_t mask(const size_t l) const override { return step * (l / width) * m_size + step * (l % width); }
+    size_t getWidth() const override { return width; }
+    size_t numBoundaryNodes() const override { return width * 4 - 4; }
+    size_t numConnections() const override { return 4 * (width * width - numBoundaryNodes()); }
+    size_t N() const override { return width * width; }
+    double h() const override { return m_h * step; }
+    size_t getStep() const override { return step; }
+    size_t fineSize() const override { return m_size; }
+    double length() const override { return m_length; }
+    size_t level() const override { return m_level; }
+};
+
+// ---- operator construction (linear_system.hpp:12-109) ----------------------------------------------------------
+template <typename T>
+class PoissonMatrix {
+    Domain &m_domain;
+    size_t m_size;
+    T m_alpha;
+    double k;
+
+public:
+    PoissonMatrix(Domain &domain, const T const_alfa)
+        : m_domain(domain), m_size(domain.N()), m_alpha(const_alfa), k(domain.h() * domain.h())
+    {
+        detail::context(domain.fineSize(), domain.length(), (double)const_alfa, (int)domain.level());
+    }
+    T coeffRef(const size_t i, const size_t j)            // matrix-free entry, for callers that print the operator
+    {
+        if (m_domain.isOnBoundary(m_domain.mask(i))) return (j == i) ? 1. : 0.;
+        if (j == i) return 4. * m_alpha / k;
+        auto [ki, li] = m_domain.meshIdx(m_domain.mask(i));
+        auto [kj, lj] = m_domain.meshIdx(m_domain.mask(j));
+        const size_t s = m_domain.getStep();
+        const size_t dk = ki > kj ? ki - kj : kj - ki, dl = li > lj ? li - lj : lj - li;
+        return (dk == s || dl == s) ? -m_alpha / k : 0.;
+    }
+    std::array<size_t, 5> nonZerosInRow_a(const size_t row) { return m_domain.inRowConnections_a(row); }
+    std::vector<size_t> nonZerosInRow(const size_t row)
+    {
+        if (m_domain.isOnBoundary(m_domain.mask(row))) return {row};
+        auto a = m_domain.inRowConnections_a(row);
+        return std::vector<size_t>(a.begin(), a.end());
+    }
+    size_t nonZeros() { return m_size + m_domain.numConnections(); }
+    size_t mask(const size_t l) { return m_domain.mask(l); }
+    size_t getWidth() { return m_domain.getWidth(); }
+    bool isOnBoundary(const size_t l) { return m_domain.isOnBoundary(l); }
+    size_t rows() { return m_size; }
+    size_t cols() { return m_size; }
+    // facade
+    int level() const { return (int)m_domain.level(); }
+    detail::Context &ctx() const { return detail::context(m_domain.fineSize(), m_domain.length(), (double)m_alpha, (int)m_domain.level()); }
+};
+
+template <typename T>
+class DataVector {
+    Domain &m_domain;
+    std::vector<T> m_vec;
+
+public:
+    DataVector(Domain &domain, const std::function<T(double, double)> &f, const std::function<T(double, double)> &g)
+        : m_domain(domain)
+    {
+        m_vec.reserve(domain.N());
+        for (size_t i = 0; i < domain.N(); i++) {
+            auto [x, y] = domain[i];
+            m_vec.push_back((domain.isOnBoundary(i) ? g : f)(x, y));       // linear_system.hpp:86-91
+        }
+    }
+    const T &operator[](const size_t i) { return m_vec[i]; }
+    size_t size() { return m_vec.size(); }
+    T *data() { return m_vec.data(); }
+};
+
+namespace detail {
+// which device vector a right-hand side object maps to: the fine forcing vector or a level's residual
+template <class V> struct RhsRole { static constexpr int which = MGB_VEC_R; };
+template <class T> struct RhsRole<DataVector<T>> { static constexpr int which = MGB_VEC_F; };
+}  // namespace detail
+
+// ---- smoothers (solvers.hpp:9-216) ---------------------------------------------------------------------------------
+template <class Vector>
+class SmootherClass {
+public:
+    virtual ~SmootherClass() { detail::flush_everything(); }
+    virtual void apply_iteration_to_vec(std::vector<double> &sol) = 0;
+    virtual int kind() const = 0;
+    inline friend std::vector<double> &operator*(std::vector<double> &x_k, SmootherClass &B)
+    {
+        B.apply_iteration_to_vec(x_k);
+        return x_k;
+    }
+};
+
+namespace detail {
+template <class Vector>
+void smooth(PoissonMatrix<double> &A, Vector &b, std::vector<double> &sol, int kind)
+{
+    Context &c = A.ctx();
+    const int l = A.level();
+    const int rhs = (RhsRole<Vector>::which == MGB_VEC_F && l == 0) ? MGB_VEC_F : MGB_VEC_R;
+    const int sl = rhs == MGB_VEC_F ? MGB_VEC_U : MGB_VEC_E;
+    c.bind(rhs, l, &b, HostData<Vector>::get(b));
+    c.bind(sl, l, &sol, sol.data());
+    if (kind == MGB_SMOOTH_GS_LEX && fast_mode()) kind = MGB_SMOOTH_GS_RB;
+    ok(mgb_gmg_smooth(c.h, l, kind, 1, sl, rhs));
+    c.touched(sl, l);
+}
+}  // namespace detail
+
+template <class Vector>
+class Gauss_Seidel_iteration : public SmootherClass<Vector> {
+    PoissonMatrix<double> &m_A;
+    Vector &b;
+
+public:
+    Gauss_Seidel_iteration(PoissonMatrix<double> &A, Vector &f) : m_A(A), b(f) {}
+    void apply_iteration_to_vec(std::vector<double> &sol) override { detail::smooth(m_A, b, sol, MGB_SMOOTH_GS_LEX); }
+    int kind() const override { return MGB_SMOOTH_GS_LEX; }
+};
+
+template <class Vector>
+class Jacobi_iteration : public SmootherClass<Vector> {
+    PoissonMatrix<double> &m_A;
+    Vector &b;
+
+public:
+    Jacobi_iteration(PoissonMatrix<double> &A, Vector &f) : m_A(A), b(f) {}
+    void apply_iteration_to_vec(std::vector<double> &sol) override { detail::smooth(m_A, b, sol, MGB_SMOOTH_JACOBI); }
+    int kind() const override { return MGB_SMOOTH_JACOBI; }
+};
+
+// The reference constructs BiCGSTAB objects but its driver never runs them (main.cpp:103-106 routes
+// `-smt 2` to the Jacobi cycle); the library routes this id to Jacobi in the same way.
+template <class Vector>
+class BiCGSTAB : public SmootherClass<Vector> {
+    PoissonMatrix<double> &m_A;
+    Vector &b;
+
+public:
+    BiCGSTAB(PoissonMatrix<double> &A, Vector &f, double = TOL) : m_A(A), b(f) {}
+    void apply_iteration_to_vec(std::vector<double> &sol) override { detail::smooth(m_A, b, sol, MGB_SMOOTH_BICGSTAB); }
+    int kind() const override { return MGB_SMOOTH_BICGSTAB; }
+};
+
+namespace detail {
+template <class S> struct SmootherKind;
+template <class V> struct SmootherKind<Gauss_Seidel_iteration<V>> { static constexpr int value = MGB_SMOOTH_GS_LEX; };
+template <class V> struct SmootherKind<Jacobi_iteration<V>> { static constexpr int value = MGB_SMOOTH_JACOBI; };
+template <class V> struct SmootherKind<BiCGSTAB<V>> { static constexpr int value = MGB_SMOOTH_BICGSTAB; };
+}  // namespace detail
+
+// ---- residual (solvers.hpp:219-308) ------------------------------------------------------------------------------------
+template <class Vector>
+class Residual {
+    PoissonMatrix<double> &m_A;
+    Vector &b;
+    std::vector<double> *m_res;
+    bool saveVector;
+    double norm_of_b, norm;
+
+public:
+    Residual(PoissonMatrix<double> &A, Vector &f) : m_A(A), b(f), m_res(nullptr), saveVector(false), norm_of_b(0.), norm(0.)
+    {
+        for (size_t i = 0; i < b.size(); i++) { double v = b[i]; norm_of_b += v * v; }          // solvers.hpp:230-235
+    }
+    Residual(PoissonMatrix<double> &A, Vector &f, std::vector<double> &res)
+        : m_A(A), b(f), m_res(&res), saveVector(true), norm_of_b(0.), norm(0.)
+    {
+        for (size_t i = 0; i < A.rows(); i++) { double v = b[A.mask(i)]; norm_of_b += v * v; }  // solvers.hpp:237-242
+    }
+    ~Residual() { detail::flush_everything(); }
+    void refresh_normalization_constant()                                                        // solvers.hpp:244-254
+    {
+        detail::Context &c = m_A.ctx();
+        const int l = m_A.level();
+        const int rhs = (detail::RhsRole<Vector>::which == MGB_VEC_F && l == 0) ? MGB_VEC_F : MGB_VEC_R;
+        c.bind(rhs, l, &b, detail::HostData<Vector>::get(b));
+        detail::ok(mgb_gmg_sumsq(c.h, l, rhs, &norm_of_b));
+    }
+    void apply_iteration_to_vec(std::vector<double> &sol)                                        // solvers.hpp:257-296
+    {
+        detail::Context &c = m_A.ctx();
+        const int l = m_A.level();
+        const int rhs = (detail::RhsRole<Vector>::which == MGB_VEC_F && l == 0) ? MGB_VEC_F : MGB_VEC_R;
+        const int sl = rhs == MGB_VEC_F ? MGB_VEC_U : MGB_VEC_E;
+        c.bind(rhs, l, &b, detail::HostData<Vector>::get(b));
+        c.bind(sl, l, &sol, sol.data());
+        const bool store = saveVector && rhs == MGB_VEC_F;       // the stored residual becomes the level's R vector
+        detail::ok(mgb_gmg_residual(c.h, l, sl, rhs, store ? 1 : 0, &norm));
+        if (store) {
+            detail::Slot &s = c.slot(MGB_VEC_R, l);
+            if (s.owner != m_res) { s.owner = m_res; s.host = m_res->data(); }
+            c.touched(MGB_VEC_R, l);
+        }
+    }
+    friend std::vector<double> &operator*(std::vector<double> &x_k, Residual &B)
+    {
+        B.apply_iteration_to_vec(x_k);
+        return x_k;
+    }
+    double Norm() { return std::sqrt(norm / norm_of_b); }                                        // solvers.hpp:305-307
+};
+
+// ---- iterate-until-tolerance loop (solvers.hpp:310-353) ------------------------------------------------------------------
+template <class Vector>
+class Solver {
+    SmootherClass<Vector> &m_it;
+    Residual<Vector> &m_res;
+    size_t m_maxit;
+    double m_tol;
+    int flag = 0;
+    int m_step;
+
+public:
+    Solver(SmootherClass<Vector> &it, Residual<Vector> &res, size_t maxit, double tol, int step)
+        : m_it(it), m_res(res), m_maxit(maxit), m_tol(tol), m_step(step) {}
+    void Solve(std::vector<double> &x_k)
+    {
+        size_t counter = m_maxit;
+        x_k * m_res;
+        while (m_res.Norm() > m_tol) {
+            if (counter > 0) {
+                for (int i = 0; i < m_step; i++) { x_k * m_it; counter -= 1; }
+                x_k * m_res;
+            } else { flag = 1; return; }
+        }
+        flag = 0;
+    }
+    int Status() { return flag; }
+    friend std::vector<double> &operator*(std::vector<double> &x_k, Solver &B)
+    {
+        B.Solve(x_k);
+        return x_k;
+    }
+};
+
+// ---- bilinear prolongation (multigrid.hpp:9-23, multigrid.cpp:3-27) --------------------------------------------------------
+class InterpolationClass {
+    PoissonMatrix<double> &m_A_inf, &m_A_sup;
+
+public:
+    InterpolationClass(PoissonMatrix<double> &A_inf, PoissonMatrix<double> &A_sup) : m_A_inf(A_inf), m_A_sup(A_sup) {}
+    ~InterpolationClass() { detail::flush_everything(); }
+    void interpolate(std::vector<double> &vec)
+    {
+        detail::Context &c = m_A_inf.ctx();
+        const int lc = m_A_inf.level();
+        c.bind(MGB_VEC_E, lc, &vec, vec.data());
+        detail::ok(mgb_gmg_prolong(c.h, lc));
+        detail::Slot &s = c.slot(MGB_VEC_E, lc - 1);
+        if (s.owner != &vec) { c.download(MGB_VEC_E, lc - 1); s.owner = &vec; s.host = vec.data(); }
+        c.touched(MGB_VEC_E, lc - 1);
+    }
+    friend std::vector<double> &operator*(std::vector<double> &x_k, InterpolationClass &B)
+    {
+        B.interpolate(x_k);
+        return x_k;
+    }
+};
+
+// ---- the cycle (multigrid.hpp:88-158) ------------------------------------------------------------------------------------------
+template <class Vector, class Smoother>
+class SawtoothMGIteration {
+    std::vector<PoissonMatrix<double>> &A_level;
+    Vector &b;
+
+public:
+    SawtoothMGIteration(std::vector<PoissonMatrix<double>> &matrices, Vector &knownVec) : A_level(matrices), b(knownVec)
+    {
+        // res, err, the per-level smoothers, interpolators and the coarse solver of the reference's constructor
+        // (multigrid.hpp:108-124) all live inside the device hierarchy
+        A_level.front().ctx();
+    }
+    ~SawtoothMGIteration() { detail::flush_everything(); }
+    void apply_iteration_to_vec(std::vector<double> &sol)
+    {
+        detail::Context &c = A_level.front().ctx();
+        c.want_levels = std::max(c.want_levels, (int)A_level.size());
+        c.bind(MGB_VEC_F, 0, &b, detail::HostData<Vector>::get(b));
+        c.bind(MGB_VEC_U, 0, &sol, sol.data());
+        int kind = detail::SmootherKind<Smoother>::value;
+        int restriction = MGB_RESTRICT_INJECTION;
+        if (detail::fast_mode()) { kind = MGB_SMOOTH_GS_RB; restriction = MGB_RESTRICT_FULL_WEIGHTING; }
+        detail::ok(mgb_gmg_set_cycle(c.h, kind, restriction, 5, 1.e-1, 2000));        // multigrid.hpp:105,123
+        double coarse = 0.;
+        detail::ok(mgb_gmg_cycle(c.h, &coarse, nullptr));
+        std::cout << "Achieved residual on coarse grid: " << coarse << std::endl;      // multigrid.hpp:131
+        c.touched(MGB_VEC_U, 0);
+    }
+    friend std::vector<double> &operator*(std::vector<double> &x_k, SawtoothMGIteration &B)
+    {
+        B.apply_iteration_to_vec(x_k);
+        return x_k;
+    }
+};
+
+}  // namespace MultiGrid
+#endif

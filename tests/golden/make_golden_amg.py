@@ -24,6 +24,9 @@ def pack(prefix, m, out):
 
 
 def main():
+    import shutil
+    os.makedirs(os.path.join(HERE, "mesh"), exist_ok=True)
+    shutil.copyfile("/root/reference/AMG/mesh/mesh1.msh", os.path.join(HERE, "mesh", "mesh1.msh"))   # data fixture of config C2
     import oracle
     oracle.build(ref=True)
     r = oracle.ref_amg()
