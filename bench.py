@@ -251,34 +251,61 @@ def main():
     kname = {G.GS_RB: (f"k_rb_stream<{2 * group}> ({group} fused red-black sweeps per launch = {group} x 24 B/pt "
                        f"algorithmic; the launch itself moves ~24 B/pt through HBM)") if cfg.rb_fused else "k_rbgs_colour (one colour pass, 12 B/pt)",
              G.JACOBI: "k_jacobi (24 B/pt)"}[kind]
+    moved = 24.0 * n * rows0                          # what one launch actually moves: read u, read rhs, write u
+    traffic = 1.098564e9 + 0.506433e9 if (kind == G.GS_RB and cfg.rb_fused and n == 8193 and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kname, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "profiles/r01_ncu_rb_stream10_full.txt (ncu --set full, dram__bytes_read.sum + "
+                                                       "dram__bytes_write.sum of one launch at 8193^2)" if traffic else None,
+                "hbm_bytes_moved_per_launch": moved, "hbm_frac_actual": moved / (kms * 1e-3 / launches) / 1e9 / peak,
+                "note": "achieved counts SURVEY 8d algorithmic bytes (24 B/pt per sweep x sweeps per launch, no credit for "
+                        "fusion); the launch is temporally blocked and moves ~24 B/pt once, so frac > 1 measures what fusion "
+                        "saved and hbm_frac_actual is the fraction of HBM bandwidth the launch really uses",
+                "kernel": kname, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kms / launches,
                 "step_algorithmic_gbs": stats["bytes_algorithmic"] / (ms * 1e-3) / 1e9,
                 "step_frac": stats["bytes_algorithmic"] / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    # every rank owns the pinned host copy of ITS slab of f and u; the ABI takes the address of the global
+    # array, so the slab buffer is passed with the offset of its first row subtracted (only slab rows are touched)
     e2e = None
     if not args.no_e2e:
+        import ctypes as C
         import torch
         r0, rows = g.rows(0)
-        f_host = torch.empty((n, n), dtype=torch.float64).pin_memory() if world == 1 else None
-        if f_host is not None:
-            fh = f_host.numpy()
+        f_host = torch.empty((rows, n), dtype=torch.float64).pin_memory()
+        u_host = torch.zeros((rows, n), dtype=torch.float64).pin_memory()
+        fh, uh = f_host.numpy(), u_host.numpy()
+        gl = np.zeros((n, n)) if world == 1 else None
+        if world == 1:
             fh[:] = g.get_level(0, G.VEC_F)
-            u_host = torch.zeros((n, n), dtype=torch.float64).pin_memory()
-            uh = u_host.numpy()
-            g.sync(); barrier()
-            t0 = time.perf_counter()
-            g.set_rhs(fh)
-            g.set_u(uh)
-            hist = g.solve(tol=0.0, maxiter=args.steps, check_every=1)
-            g.get_u(uh)
-            dt = time.perf_counter() - t0
-            e2e = {"value": dof * args.steps / dt, "unit": UNIT,
-                   "h2d_bytes_per_step": 2 * dof * 8 / args.steps, "d2h_bytes_per_step": dof * 8 / args.steps + 8,
-                   "what": f"mgb_gmg_set_rhs + set_u (pinned host -> HBM), {args.steps} steps each reading its residual "
-                           f"norm back, mgb_gmg_get_u (HBM -> pinned host); wall clock", "final_relres": float(hist[-1])}
+        else:                                   # multi-rank: refill the slab from the device-resident f
+            from multigrid_prj_b200._lib import check
+            check(g.lib.mgb_gmg_get_level(g.h, 0, G.VEC_F, C.c_void_p(fh.ctypes.data - r0 * n * 8)))
+        del gl
+        fptr = C.c_void_p(fh.ctypes.data - r0 * n * 8)
+        uptr = C.c_void_p(uh.ctypes.data - r0 * n * 8)
+        from multigrid_prj_b200._lib import check
+        hist = np.zeros(args.steps + 1)
+        nh = C.c_int()
+        g.sync(); barrier()
+        t0 = time.perf_counter()
+        check(g.lib.mgb_gmg_set_rhs(g.h, fptr))
+        check(g.lib.mgb_gmg_set_u(g.h, uptr))
+        check(g.lib.mgb_gmg_solve(g.h, 0.0, args.steps, 1, hist.ctypes.data_as(C.c_void_p), C.byref(nh)))
+        check(g.lib.mgb_gmg_get_u(g.h, uptr))
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        slab_bytes = float(rows) * n * 8
+        e2e = {"value": dof * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": 2 * slab_bytes / args.steps, "d2h_bytes_per_step": slab_bytes / args.steps + 8,
+               "what": f"per rank: mgb_gmg_set_rhs + mgb_gmg_set_u (pinned host slab -> HBM), mgb_gmg_solve with "
+                       f"{args.steps} steps each reading its residual norm back, mgb_gmg_get_u (HBM -> pinned host); "
+                       f"wall clock, max over ranks; bytes are per rank", "final_relres": float(hist[nh.value - 1])}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------------
     cpu = None
