@@ -54,9 +54,10 @@ struct Level {
     LevelGeom g{};                    // this rank's view (sharded: its slab; replicated: the whole level)
     bool sharded = false;
     size_t elems = 0;                 // (rows + 2*kHalo) * pitch
-    double *base[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // pointers to local row 0 of: u, f (level 0 only), e, r, t (scratch for out-of-place sweeps)
-    double *u = nullptr, *f = nullptr, *e = nullptr, *r = nullptr, *t = nullptr;
+    double *base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // pointers to local row 0 of: u, f (level 0 only), e, r, t (ping-pong partner of e in out-of-place sweeps),
+    // tu (ping-pong partner of u, level 0 only: two independent pairs keep the buffer rotation at period 2)
+    double *u = nullptr, *f = nullptr, *e = nullptr, *r = nullptr, *t = nullptr, *tu = nullptr;
 };
 
 // Slab of `rank` on `level` (pure host arithmetic; also exported for the CPU-side tests).
@@ -113,6 +114,9 @@ struct mgb_gmg {
     bool have_rhs = false;
     int n_sm = 148;
     mgb_gmg_stats stats{};
+    // CUDA graphs of `period` driver iterations, keyed by the buffer-pointer state they were captured in
+    struct IterGraph { std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; };
+    std::vector<IterGraph> graphs;
 
     double **vec(int level, int which)
     {
@@ -180,8 +184,9 @@ int read_scalar(mgb_gmg *h, int slot, double *out)
     return MGB_OK;
 }
 
+// resident CTAs per SM of one instantiation of the streaming kernel (also raises its dynamic-smem limit)
 template <int S, bool EXACT>
-int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out)
+int stream_occupancy(int *out)
 {
     static int occ = 0;
     constexpr int smem = mgb::stream_smem_bytes<S>();
@@ -190,6 +195,26 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT>, mgb::kStreamNT, smem));
         occ = std::max(1, occ);
     }
+    *out = occ;
+    return MGB_OK;
+}
+
+int prepare_kernels()
+{
+    int o, rc;
+    if ((rc = stream_occupancy<2, true>(&o)) || (rc = stream_occupancy<2, false>(&o)) || (rc = stream_occupancy<4, true>(&o)) ||
+        (rc = stream_occupancy<4, false>(&o)) || (rc = stream_occupancy<10, true>(&o)) || (rc = stream_occupancy<10, false>(&o)))
+        return rc;
+    CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
+    return MGB_OK;
+}
+
+template <int S, bool EXACT>
+int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out)
+{
+    int occ = 1;
+    constexpr int smem = mgb::stream_smem_bytes<S>();
+    if (int rc = stream_occupancy<S, EXACT>(&occ)) return rc;
     const int OW = mgb::kStreamTW - 2 * S;
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
@@ -236,19 +261,20 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
     if (kind == MGB_SMOOTH_BICGSTAB) kind = MGB_SMOOTH_JACOBI;      // main.cpp:103-106
     dim3 grid = march_grid(g);
     int rc;
+    double *&scratch = (sol == &L.u) ? L.tu : L.t;                  // ping-pong partner of this vector
     for (int s = 0; s < sweeps; ++s) {
         if (kind == MGB_SMOOTH_JACOBI) {
             if ((rc = halo_exchange(h, level, *sol, 1))) return rc;
-            mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, L.t);
+            mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, scratch);
             count(h, 24. * npts(g));
-            std::swap(*sol, L.t);                                   // solvers.hpp:83 sol.swap(temp)
+            std::swap(*sol, scratch);                               // solvers.hpp:83 sol.swap(temp)
         } else if (kind == MGB_SMOOTH_GS_RB && h->cfg.rb_fused) {
             // group the remaining sweeps: 5, 2 or 1 full sweeps per pass over HBM
             const int left = sweeps - s;
             const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
             if ((rc = halo_exchange(h, level, *sol, 2 * grp))) return rc;
-            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, L.t))) return rc;
-            std::swap(*sol, L.t);
+            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch))) return rc;
+            std::swap(*sol, scratch);
             s += grp - 1;
         } else if (kind == MGB_SMOOTH_GS_RB) {
             for (int colour = 0; colour < 2; ++colour) {
@@ -385,11 +411,6 @@ int launch_tail(mgb_gmg *h)
     p.coarse_maxit = h->cfg.coarse_maxit;
     p.coarse_tol = h->cfg.coarse_tol;
     p.out = h->d_scal + 4;
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
-        attr = true;
-    }
     mgb::k_coarse_tail<<<1, mgb::kTailThreads, mgb::kTailSmemBytes, h->st>>>(p);
     double bytes = 0.;
     for (int l = h->lt; l < L; ++l) bytes += 24. * h->cfg.nu * npts(h->lv[l].g);
@@ -477,6 +498,75 @@ int copy_2d(mgb_gmg *h, const LevelGeom &g, double *dev, const double *host_glob
     return MGB_OK;
 }
 
+// one iteration of the driver loop (main.cpp:84-86): pre-sweeps, cycle, residual norm into d_scal[1]
+int one_iteration(mgb_gmg *h)
+{
+    Level &F = h->lv[0];
+    int rc;
+    if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
+    if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
+    return do_residual(h, 0, F.u, F.f, nullptr, 1);
+}
+
+std::vector<const double *> pointer_state(mgb_gmg *h)
+{
+    std::vector<const double *> k;
+    for (auto &lv : h->lv) { k.push_back(lv.u); k.push_back(lv.tu); k.push_back(lv.e); k.push_back(lv.t); k.push_back(lv.r); }
+    k.push_back((const double *)(uintptr_t)((h->cfg.smoother << 8) | (h->cfg.pre_smoother << 4) | h->cfg.restriction));
+    k.push_back((const double *)(uintptr_t)((h->cfg.nu << 8) | h->cfg.n_pre));
+    return k;
+}
+
+// Runs `cycles` iterations, as whole CUDA-graph launches where possible.  Out-of-place kernels swap buffer
+// roles, so a graph covers the smallest number of iterations after which every pointer is back in place.
+int run_iterations(mgb_gmg *h, int cycles)
+{
+    int rc;
+    const bool graph_ok = h->cfg.use_graph && h->lt >= 0;       // the cycle must be free of host synchronisation
+    while (cycles > 0) {
+        if (graph_ok) {
+            auto key = pointer_state(h);
+            mgb_gmg::IterGraph *g = nullptr;
+            for (auto &c : h->graphs) if (c.key == key) g = &c;
+            if (!g && cycles < 4) { if ((rc = one_iteration(h))) return rc; --cycles; continue; }   // not worth a capture
+            if (!g) {
+                const mgb_gmg_stats before = h->stats;
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+                int period = 0;
+                rc = MGB_OK;
+                do { rc = one_iteration(h); ++period; } while (!rc && period < 12 && pointer_state(h) != key);
+                cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+                // capturing executes nothing: restore the counters and (after an odd number of swaps) the pointers
+                mgb_gmg::IterGraph ng{key, nullptr, period, h->stats.kernel_launches - before.kernel_launches,
+                                      h->stats.bytes_algorithmic - before.bytes_algorithmic,
+                                      h->stats.reserved[0] - before.reserved[0]};
+                h->stats = before;
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+                if (pointer_state(h) != key) { cudaGraphDestroy(graph); return fail(MGB_ERR_STATE, "buffer rotation has no short period"); }
+                CK(cudaGraphInstantiate(&ng.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                h->graphs.push_back(ng);
+                g = &h->graphs.back();
+            }
+            if (cycles >= g->period) {
+                CK(cudaGraphLaunch(g->exec, h->st));
+                h->stats.graph_launches++;
+                h->stats.kernel_launches += g->launches;
+                h->stats.bytes_algorithmic += g->bytes;
+                h->stats.reserved[0] += g->exchanges;
+                h->stats.cycles += g->period;
+                cycles -= g->period;
+                continue;
+            }
+        }
+        if ((rc = one_iteration(h))) return rc;
+        --cycles;
+    }
+    return MGB_OK;
+}
+
 int after_rhs(mgb_gmg *h)
 {
     int rc;
@@ -509,7 +599,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->nu = 5; c->coarse_tol = 1.e-1; c->coarse_maxit = 2000;           // multigrid.hpp:105,123
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
-    c->tail_max_width = 129; c->use_graph = 0;
+    c->tail_max_width = 129; c->use_graph = 1;
     c->rb_fast_arith = 0; c->rb_fused = 1;
 }
 
@@ -558,6 +648,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         return fail(MGB_ERR_CUDA, "no CUDA device: libmgb200 has no CPU fallback");
     }
     CK(cudaSetDevice(cfg->device));
+    if (int rc = prepare_kernels()) return rc;
     mgb_gmg *h = new mgb_gmg();
     h->cfg = *cfg;
     h->ls = ls;
@@ -585,8 +676,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         lv.g.diag = 4. * cfg->alpha / k;                                  // linear_system.hpp:28
         lv.g.off = -cfg->alpha / k;                                       // linear_system.hpp:38
         lv.elems = (size_t)(lv.g.rows + 2 * kHalo) * lv.g.pitch;
-        for (int v = 0; v < 5; ++v) {
-            if (l > 0 && v < 2) continue;                                 // u, f exist on level 0 only
+        for (int v = 0; v < 6; ++v) {
+            if (l > 0 && (v < 2 || v == 5)) continue;                     // u, f, tu exist on level 0 only
             CK(cudaMalloc(&lv.base[v], lv.elems * sizeof(double)));
             CK(cudaMemsetAsync(lv.base[v], 0, lv.elems * sizeof(double), h->st));
         }
@@ -596,6 +687,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         lv.e = lv.base[2] + off;
         lv.r = lv.base[3] + off;
         lv.t = lv.base[4] + off;
+        lv.tu = lv.base[5] ? lv.base[5] + off : nullptr;
         dim3 g0 = march_grid(lv.g);
         max_partial = std::max(max_partial, (size_t)g0.x * g0.y);
         w = (w + 1) / 2;                                                  // domain.cpp:10
@@ -621,6 +713,7 @@ void mgb_gmg_destroy(mgb_gmg_t h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->comm) mgb::nccl().CommDestroy(h->comm);
     for (auto &lv : h->lv)
         for (double *p : lv.base) if (p) cudaFree(p);
@@ -795,11 +888,7 @@ int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres)
     CK(cudaSetDevice(h->cfg.device));
     Level &F = h->lv[0];
     int rc;
-    for (int i = 0; i < cycles; ++i) {
-        if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
-        if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
-        if ((rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;
-    }
+    if ((rc = run_iterations(h, cycles))) return rc;
     if (final_relres) {
         double ss = 0.;
         if (cycles == 0 && (rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;

@@ -34,7 +34,7 @@ class GmgConfig:
     n_ranks: int = 1
     nccl_id: bytes = b""
     tail_max_width: int = 129
-    use_graph: int = 0
+    use_graph: int = 1
     rb_fast_arith: int = 0
     rb_fused: int = 1
 
