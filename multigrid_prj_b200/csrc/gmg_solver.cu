@@ -47,8 +47,9 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 using mgb::LevelGeom;
 
-constexpr int kHalo = 12;            // halo rows kept above and below every slab (>= deepest fused kernel: 10)
-constexpr int kMinSlabRows = 64;     // a level is sharded while every rank keeps at least this many rows
+constexpr int kHalo = 44;            // halo rows kept above and below every slab (deepest need: see plan_depths)
+constexpr int kMinSlabRows = 256;    // a level is sharded while every rank keeps at least this many rows;
+                                     // smaller levels are replicated (cheaper than a latency-bound exchange per operator)
 
 struct Level {
     LevelGeom g{};                    // this rank's view (sharded: its slab; replicated: the whole level)
@@ -104,6 +105,7 @@ struct mgb_gmg {
     std::vector<Level> lv;
     int ls = -1;                      // last sharded level (-1: single rank)
     int lt = -1;                      // first level of the persistent coarse tail (-1: no tail kernel)
+    int u_halo_valid = 0;             // halo rows of u known to be current (communication-avoiding path)
     cudaStream_t st = nullptr;
     mgb::NcclComm comm = nullptr;
     double *d_partial = nullptr;      // per-CTA partial sums
@@ -140,6 +142,17 @@ dim3 march_grid(const LevelGeom &g)
 
 inline void count(mgb_gmg *h, double bytes) { h->stats.kernel_launches++; h->stats.bytes_algorithmic += bytes; }
 inline double npts(const LevelGeom &g) { return (double)g.w * (double)g.rows; }
+
+// A slab seen with `ext` extra rows on each interior side: kernels take this geometry and pointers moved by
+// `off` elements, and thereby also (re)compute rows of the halo -- redundant work that replaces an exchange.
+struct View { LevelGeom g; ptrdiff_t off; };
+View extended(const Level &L, int ext)
+{
+    const int et = (L.g.row0 == 0) ? 0 : ext, eb = (L.g.row0 + L.g.rows == L.g.w) ? 0 : ext;
+    LevelGeom g = L.g;
+    g.row0 -= et; g.rows += et + eb;
+    return View{g, -(ptrdiff_t)et * (ptrdiff_t)g.pitch};
+}
 
 // exchange `depth` halo rows of a sharded level vector with the slab neighbours
 int halo_exchange(mgb_gmg *h, int level, double *v, int depth)
@@ -240,9 +253,12 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
 }
 
 // `sweeps` (1, 2 or 5) full red-black sweeps in one pass: in -> out
-int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out)
+// `ext` > 0: also produce `ext` rows of the halo on each interior side (the input must be valid ext + 2*sweeps deep)
+int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out, int ext = 0)
 {
-    const LevelGeom &g = h->lv[level].g;
+    const View v = extended(h->lv[level], ext);
+    const LevelGeom &g = v.g;
+    in += v.off; rhs += v.off; out += v.off;
     const bool ex = !h->cfg.rb_fast_arith;
     switch (sweeps) {
     case 1: return ex ? launch_rb_stream_t<2, true>(h, g, in, rhs, out) : launch_rb_stream_t<2, false>(h, g, in, rhs, out);
@@ -257,6 +273,7 @@ int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const 
 int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs)
 {
     Level &L = h->lv[level];
+    if (sol == &L.u) h->u_halo_valid = 0;
     const LevelGeom &g = L.g;
     if (kind == MGB_SMOOTH_BICGSTAB) kind = MGB_SMOOTH_JACOBI;      // main.cpp:103-106
     dim3 grid = march_grid(g);
@@ -423,12 +440,176 @@ int launch_tail(mgb_gmg *h)
 int finish_cycle(mgb_gmg *h)
 {
     Level &F = h->lv[0];
+    h->u_halo_valid = 0;
     dim3 grid((F.g.pitch / 2 + 255) / 256, std::min(F.g.rows, 1024));
     mgb::k_axpy_rows<<<grid, 256, 0, h->st>>>(F.g, F.u, F.e);
     count(h, 24. * npts(F.g));
     CK(cudaGetLastError());
     h->stats.cycles++;
     return MGB_OK;
+}
+
+// ---- communication-avoiding schedule for the fused red-black path on slabs --------------------------------
+// Every fused kernel recomputes halo rows from a deeper input halo instead of receiving them, so one driver
+// iteration needs 3 point-to-point exchange groups (u; the fine residual; all restricted residuals + the
+// gather of the first replicated level) and 1 all-reduce, instead of one exchange per operator.
+struct Depths {
+    std::vector<int> din, dout, ext_r;     // per level: input halo the post-smoother reads, halo rows it must
+};                                         // produce for the prolongation above it, halo rows of r made by restriction
+
+Depths plan_depths(mgb_gmg *h)
+{
+    const int L = (int)h->lv.size();
+    Depths d;
+    d.din.assign(L, 0); d.dout.assign(L, 0); d.ext_r.assign(L, 0);
+    for (int l = 0; l <= h->ls; ++l) {
+        d.din[l] = d.dout[l] + 2 * h->cfg.nu;
+        if (l + 1 <= h->ls) d.dout[l + 1] = (d.din[l] + 1) / 2 + 1;
+    }
+    if (h->ls + 1 < L) d.ext_r[h->ls] = 1;              // rows of the first replicated level need fine rows +-1
+    for (int l = h->ls; l > 0; --l) d.ext_r[l - 1] = 2 * d.ext_r[l] + 1;
+    return d;
+}
+
+bool ca_applicable(mgb_gmg *h)
+{
+    if (h->cfg.n_ranks <= 1 || !h->cfg.rb_fused || h->cfg.smoother != MGB_SMOOTH_GS_RB || h->cfg.pre_smoother != MGB_SMOOTH_GS_RB)
+        return false;
+    if (h->cfg.restriction != MGB_RESTRICT_FULL_WEIGHTING && h->cfg.restriction != MGB_RESTRICT_HALF_INJECTION &&
+        h->cfg.restriction != MGB_RESTRICT_INJECTION) return false;
+    if (h->lt < 0 || h->lt <= h->ls) return false;       // the replicated part must end in the tail kernel
+    const Depths d = plan_depths(h);
+    int need = std::max(d.ext_r[0], 2 * h->cfg.n_pre + 1);
+    for (int l = 0; l <= h->ls; ++l) need = std::max(need, d.din[l]);
+    return need + 2 <= kHalo && need <= h->lv[h->ls].g.rows / 2;
+}
+
+// fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
+int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out)
+{
+    int left = sweeps, rc;
+    while (left > 0) {
+        const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
+        left -= grp;
+        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, ext_out + 2 * left))) return rc;
+        std::swap(*sol, scratch);
+    }
+    return MGB_OK;
+}
+
+int one_iteration_ca(mgb_gmg *h)
+{
+    const int L = (int)h->lv.size(), ls = h->ls;
+    Level &F = h->lv[0];
+    const Depths d = plan_depths(h);
+    auto &N = mgb::nccl();
+    int rc;
+    // (1) u: one exchange serves the pre-sweeps (2 rows per sweep) and the residual after them (+1)
+    const int ext_u = 2 * h->cfg.n_pre + 1;
+    if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
+    h->u_halo_valid = 0;
+    if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 1))) return rc;
+    // (2) fine residual on the owned rows, then ONE deep exchange of it
+    {
+        dim3 grid = march_grid(F.g);
+        mgb::k_residual<true><<<grid, mgb::kTPB, 0, h->st>>>(F.g, F.u, F.f, F.r, h->d_partial);
+        count(h, 24. * npts(F.g));
+        CK(cudaGetLastError());
+    }
+    if ((rc = halo_exchange(h, 0, F.r, std::max(d.din[0], d.ext_r[0])))) return rc;
+    // (3) restriction down the sharded levels, halo rows recomputed; then the first replicated level's slab
+    const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
+    for (int l = 1; l <= std::min(ls + 1, h->lt); ++l) {
+        Level &Fl = h->lv[l - 1], &C = h->lv[l];
+        LevelGeom gc;
+        double *out;
+        if (C.sharded) { const View v = extended(C, d.ext_r[l]); gc = v.g; out = C.r + v.off; }
+        else {
+            gc = C.g;
+            gc.row0 = (Fl.g.row0 + 1) / 2;
+            gc.rows = (Fl.g.row0 + Fl.g.rows - 1) / 2 - gc.row0 + 1;
+            out = C.r + (size_t)gc.row0 * gc.pitch;
+        }
+        dim3 grid((gc.w + 255) / 256, gc.rows);
+        if (fw) mgb::k_restrict<2><<<grid, 256, 0, h->st>>>(Fl.g, gc, Fl.r, out, 1.0);
+        else {
+            const double scale = (h->cfg.restriction == MGB_RESTRICT_HALF_INJECTION && l == 1) ? 0.5 : 1.0;
+            mgb::k_restrict<0><<<grid, 256, 0, h->st>>>(Fl.g, gc, Fl.r, out, scale);
+        }
+        count(h, fw ? 8. * npts(Fl.g) + 8. * npts(gc) : 16. * npts(gc));
+        CK(cudaGetLastError());
+    }
+    // one NCCL group: halo rows of every restricted residual (the smoothers' rhs) + gather of the replicated slab rows
+    {
+        const int r = h->cfg.rank, n = h->cfg.n_ranks;
+        NK(N.GroupStart());
+        for (int l = 1; l <= ls; ++l) {
+            Level &Lv = h->lv[l];
+            const size_t P = (size_t)Lv.g.pitch, cnt = (size_t)d.din[l] * P;
+            if (r > 0) {
+                NK(N.Send(Lv.r, cnt, mgb::kNcclFloat64, r - 1, h->comm, h->st));
+                NK(N.Recv(Lv.r - cnt, cnt, mgb::kNcclFloat64, r - 1, h->comm, h->st));
+            }
+            if (r < n - 1) {
+                NK(N.Send(Lv.r + (size_t)(Lv.g.rows - d.din[l]) * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st));
+                NK(N.Recv(Lv.r + (size_t)Lv.g.rows * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st));
+            }
+        }
+        if (ls + 1 < L) {
+            Level &C = h->lv[ls + 1];
+            const size_t P = (size_t)C.g.pitch;
+            auto vslab = [&](int rank, int &r0, int &nr) {
+                Part f = partition(h->cfg.n, h->cfg.levels, n, rank, ls);
+                r0 = (f.row0 + 1) / 2;
+                nr = (f.row0 + f.rows - 1) / 2 - r0 + 1;
+            };
+            int my0, myn;
+            vslab(r, my0, myn);
+            for (int p = 0; p < n; ++p) {
+                if (p == r) continue;
+                int p0, pn;
+                vslab(p, p0, pn);
+                NK(N.Send(C.r + (size_t)my0 * P, (size_t)myn * P, mgb::kNcclFloat64, p, h->comm, h->st));
+                NK(N.Recv(C.r + (size_t)p0 * P, (size_t)pn * P, mgb::kNcclFloat64, p, h->comm, h->st));
+            }
+        }
+        NK(N.GroupEnd());
+        h->stats.reserved[0]++;
+    }
+    // (4) replicated levels down to the tail, the tail itself, and back up to the first replicated level
+    for (int l = ls + 2; l <= h->lt; ++l) {
+        Level &Fl = h->lv[l - 1], &C = h->lv[l];
+        dim3 grid((C.g.w + 255) / 256, C.g.rows);
+        if (fw) mgb::k_restrict<2><<<grid, 256, 0, h->st>>>(Fl.g, C.g, Fl.r, C.r, 1.0);
+        else mgb::k_restrict<0><<<grid, 256, 0, h->st>>>(Fl.g, C.g, Fl.r, C.r, 1.0);
+        count(h, fw ? 8. * npts(Fl.g) + 8. * npts(C.g) : 16. * npts(C.g));
+        CK(cudaGetLastError());
+    }
+    if ((rc = launch_tail(h))) return rc;
+    for (int j = h->lt; j > ls + 1; --j) {
+        if ((rc = do_prolong(h, j))) return rc;
+        if ((rc = do_smooth(h, j - 1, MGB_SMOOTH_GS_RB, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
+    }
+    // (5) upward through the sharded levels without any exchange
+    for (int j = ls + 1; j > 0; --j) {
+        Level &C = h->lv[j], &Fl = h->lv[j - 1];
+        const View vf = extended(Fl, d.din[j - 1]);
+        dim3 grid((vf.g.w + 2 * mgb::kTPB - 1) / (2 * mgb::kTPB), (vf.g.rows + 3) / 4);
+        mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, vf.g, C.e, Fl.e + vf.off);
+        count(h, 8. * (npts(vf.g) + npts(C.g)));
+        CK(cudaGetLastError());
+        if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1]))) return rc;
+    }
+    if ((rc = finish_cycle(h))) return rc;
+    // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
+    // enough to serve the next iteration's pre-sweeps as well (u does not change in between).
+    if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
+    h->u_halo_valid = ext_u;
+    dim3 grid = march_grid(F.g);
+    mgb::k_residual<false><<<grid, mgb::kTPB, 0, h->st>>>(F.g, F.u, F.f, nullptr, h->d_partial);
+    count(h, 16. * npts(F.g));
+    CK(cudaGetLastError());
+    return reduce_partials(h, grid.x * grid.y, 1, true);
 }
 
 // multigrid.hpp:126-145
@@ -501,6 +682,7 @@ int copy_2d(mgb_gmg *h, const LevelGeom &g, double *dev, const double *host_glob
 // one iteration of the driver loop (main.cpp:84-86): pre-sweeps, cycle, residual norm into d_scal[1]
 int one_iteration(mgb_gmg *h)
 {
+    if (ca_applicable(h)) return one_iteration_ca(h);
     Level &F = h->lv[0];
     int rc;
     if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
@@ -747,6 +929,7 @@ int mgb_gmg_set_level(mgb_gmg_t h, int level, int which, const double *host)
     CK(cudaSetDevice(h->cfg.device));
     int rc = copy_2d(h, h->lv[level].g, *p, host, true);
     if (rc) return rc;
+    if (which == MGB_VEC_U) h->u_halo_valid = 0;
     if (level == 0 && which == MGB_VEC_F) return after_rhs(h);
     // a level rhs set by hand gets its halo rows here (restriction does it for the cycle)
     if (which == MGB_VEC_R) return halo_exchange(h, level, *p, kHalo);
@@ -783,6 +966,7 @@ int mgb_gmg_set_u(mgb_gmg_t h, const double *u_host)
     if (u_host) return mgb_gmg_set_level(h, 0, MGB_VEC_U, u_host);
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemsetAsync(h->lv[0].u - (size_t)kHalo * h->lv[0].g.pitch, 0, h->lv[0].elems * sizeof(double), h->st));
+    h->u_halo_valid = 0;
     return MGB_OK;
 }
 
@@ -868,9 +1052,7 @@ int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double 
     if ((rc = read_scalar(h, 1, &ss))) return rc;
     hist[n++] = std::sqrt(ss / h->norm_f);
     for (int i = 0; i < maxiter; ++i) {                                   // main.cpp:84-90
-        if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
-        if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
-        if ((rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;
+        if ((rc = one_iteration(h))) return rc;
         if ((i + 1) % check_every == 0 || i + 1 == maxiter) {
             if ((rc = read_scalar(h, 1, &ss))) return rc;
             hist[n++] = std::sqrt(ss / h->norm_f);
