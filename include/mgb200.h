@@ -76,7 +76,11 @@ typedef struct mgb_gmg_config {
                              1 = u = b/diag + (sum of neighbours)/4 with FMA (a few ulp away) */
     int rb_fused;         /* 1 = streaming temporally-blocked red-black kernel (all sweeps of a group in one
                              pass over HBM); 0 = one launch per colour */
-    int reserved[6];
+    int fuse_correction;  /* red-black fused path only: the last post-smoothing launch on the fine level also applies
+                             u += err (multigrid.hpp:141-144) and leaves sum (res - A err)^2 = ||f - A u_new||^2, the norm
+                             main.cpp:86 asks for next, from data already on chip (no axpy pass, no residual pass).
+                             The norm then carries the rounding of res - A err instead of f - A u (same value to ~1e-13 ||f||). */
+    int reserved[5];
 } mgb_gmg_config;
 
 typedef struct mgb_gmg *mgb_gmg_t;

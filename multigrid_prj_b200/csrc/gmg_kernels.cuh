@@ -418,7 +418,7 @@ __device__ __forceinline__ double rb_point(double b, double up, double left, dou
 // read their neighbours, so nothing crosses into the domain.
 template <int S, bool EXACT, int PAR, bool GUARD>
 __device__ __forceinline__ void rb_stream_step(
-    const LevelGeom &g, double2 (&uw)[2 * S + 2], int (&ro)[S + 1], double2 nu, double2 nb, double *su,
+    const LevelGeom &g, double2 (&uw)[2 * S + 3], int (&ro)[S + 1], double2 nu, double2 nb, double *su,
     double *sb, int i, bool bc0, bool bc1, int ifirst, int ilast, bool first_is_bdry,
     bool last_is_bdry, int glast, double inv_diag)
 {
@@ -433,7 +433,7 @@ __device__ __forceinline__ void rb_stream_step(
     }
     // rotate the register window by one row and publish the arriving row
 #pragma unroll
-    for (int d = 2 * S + 1; d > 0; --d) uw[d] = uw[d - 1];
+    for (int d = 2 * S + 2; d > 0; --d) uw[d] = uw[d - 1];
     su[ro[0]] = nu.x; su[ro[0] + H] = nu.y;
     sb[ro[0]] = nb.x; sb[ro[0] + H] = nb.y;
     __syncthreads();
@@ -490,17 +490,26 @@ __device__ __forceinline__ void rb_stream_step(
     }
 }
 
-template <int S, bool EXACT>
+// MODE 0: uout = S/2 sweeps applied to uin.
+// MODE 1 (last post-smoothing launch on the fine level): the smoothed error is not written out; instead
+//   ucorr += e            (the correction u += err of multigrid.hpp:141-144, in place on the owned rows), and
+//   partial[cta] = sum (rhs - A e)^2   over the CTA's output rows.
+// Since rhs = f - A u_old, rhs - A e = f - A (u_old + e): this is the residual of the NEW iterate (main.cpp:86),
+// obtained from data already on chip -- no separate axpy pass and no separate residual pass over HBM.
+// It needs the final values of one more row on each side, so the stream starts/ends one row further out.
+template <int S, bool EXACT, int MODE>
 __global__ void __launch_bounds__(kStreamNT)
 k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
-            double *__restrict__ uout, int rows_per_chunk)
+            double *__restrict__ uout, int rows_per_chunk, double *ucorr, double *__restrict__ partial)
 {
-    constexpr int TW = kStreamTW, NT = kStreamNT, PF = kStreamPF;
+    constexpr int TW = kStreamTW, PF = kStreamPF, H = TW / 2;
     constexpr int WR = 2 * S + 3;
+    constexpr int X = (MODE == 1) ? 1 : 0;
     static_assert(PF == 4, "the main loop is unrolled by 4 rows");
     extern __shared__ double smem[];
     double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
     double *sb = smem + WR * TW;
+    __shared__ double red[kStreamNT / 32];
 
     const int t = threadIdx.x;
     const int OW = TW - 2 * S;
@@ -511,12 +520,12 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const int i1 = min(i0 + rows_per_chunk, g.rows);
     if (i0 >= g.rows) return;
     const bool top_is_domain = (g.row0 == 0), bot_is_domain = (g.row0 + g.rows == g.w);
-    const int lo = top_is_domain ? 0 : -S, hi = bot_is_domain ? g.rows - 1 : g.rows - 1 + S;
-    int ifirst = max(i0 - S, lo);
+    const int lo = top_is_domain ? 0 : -S - X, hi = bot_is_domain ? g.rows - 1 : g.rows - 1 + S + X;
+    int ifirst = max(i0 - S - X, lo);
     // the unrolled loop assumes the first streamed row has an even global index; if a slab starts on
     // an odd row, stream one more (halo) row -- it only feeds values that are never written out
     if ((g.row0 + ifirst) & 1) ifirst -= 1;
-    const int ilast = min(i1 - 1 + S, hi);
+    const int ilast = min(i1 - 1 + S + X, hi);
     const bool first_is_bdry = (g.row0 + ifirst == 0), last_is_bdry = (g.row0 + ilast == g.w - 1);
     const ptrdiff_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;
@@ -527,9 +536,9 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const int glast = g.w - 1 - g.row0;              // local index of the global last row
     const int i_lo = ifirst + (first_is_bdry ? 2 * S + 1 : 3 * S), i_hi = ilast + 1;   // steady steps
 
-    double2 uw[2 * S + 2];
+    double2 uw[2 * S + 3];
 #pragma unroll
-    for (int d = 0; d < 2 * S + 2; ++d) uw[d] = make_double2(0., 0.);
+    for (int d = 0; d < 2 * S + 3; ++d) uw[d] = make_double2(0., 0.);
     double2 pu[PF], pb[PF];
 #pragma unroll
     for (int p = 0; p < PF; ++p) {
@@ -537,10 +546,20 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
         pu[p] = ld2(uin + (ptrdiff_t)r * P + jl);
         pb[p] = ld2(b + (ptrdiff_t)r * P + jl);
     }
-    const int ksteps = (i1 - 1 + 2 * S) - ifirst + 1;
+    const int ksteps = (i1 - 1 + 2 * S + X) - ifirst + 1;
     int ro[S + 1];                                   // ring offsets of rows i-2s (s = 0: arriving row)
 #pragma unroll
     for (int s = 0; s <= S; ++s) ro[s] = ((WR - 2 * s) % WR) * TW + t;
+    int roq = ((WR - (2 * S + 1)) % WR) * TW + t;    // ring offset of row i-2S-1 (MODE 1: the residual row)
+    double2 pc[2];                                   // MODE 1: rows of ucorr, requested two steps ahead
+    double acc = 0.;
+    if (MODE == 1) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            int r = min(max(ifirst + p - 2 * S, i0), i1 - 1);
+            pc[p] = ld2(ucorr + (ptrdiff_t)r * P + jl);
+        }
+    }
 #define MGB_STREAM_STEP(p)                                                                                  \
     {                                                                                                       \
         const int i = ifirst + k0 + (p);             /* row arriving at this step */                         \
@@ -558,9 +577,43 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
             rb_stream_step<S, EXACT, ((p) & 1), true>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst,       \
                                                       ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         const int r = i - 2 * S;                     /* final after this step */                             \
-        if (r >= i0 && r < i1 && own) {                                                                     \
-            double *dstp = uout + (ptrdiff_t)r * P + j0;                                                    \
-            if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                             \
+        if (MODE == 0) {                                                                                    \
+            if (r >= i0 && r < i1 && own) {                                                                 \
+                double *dstp = uout + (ptrdiff_t)r * P + j0;                                                \
+                if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                         \
+            }                                                                                               \
+        } else {                                                                                            \
+            const double2 uc = pc[(p) & 1];                                                                 \
+            {                                                                                               \
+                int r2 = min(max(r + 2, i0), i1 - 1);                                                       \
+                pc[(p) & 1] = ld2(ucorr + (ptrdiff_t)r2 * P + jl);                                          \
+            }                                                                                               \
+            if (r >= i0 && r < i1 && own) {                                                                 \
+                double *dstp = ucorr + (ptrdiff_t)r * P + j0;                                               \
+                const double2 un = make_double2(__dadd_rn(uc.x, uw[2 * S].x), __dadd_rn(uc.y, uw[2 * S].y)); \
+                if (j0 + 1 < g.w) st2(dstp, un); else dstp[0] = un.x;                                       \
+            }                                                                                               \
+            const int q = r - 1;                     /* rows q-1, q, q+1 are final: residual of row q */     \
+            if (q >= i0 && q < i1 && own) {                                                                 \
+                const double2 c = uw[2 * S + 1], up = uw[2 * S + 2], dn = uw[2 * S];                        \
+                const double lf = su[roq + H - 1], rt = su[roq + 1];                                        \
+                const double b0 = sb[roq], b1 = sb[roq + H];                                                \
+                const bool brow = (q + g.row0 == 0) || (q == glast);                                        \
+                double r0v, r1v;                                                                            \
+                if (EXACT) {                                                                                \
+                    r0v = (bc0 || brow) ? __dsub_rn(b0, c.x) : resid_point(b0, up.x, lf, c.x, c.y, dn.x, g.off, g.diag); \
+                    r1v = (bc1 || brow) ? __dsub_rn(b1, c.y) : resid_point(b1, up.y, c.x, c.y, rt, dn.y, g.off, g.diag); \
+                } else {                                                                                    \
+                    /* the ring holds b/diag (b itself on Dirichlet points): r = diag*(b/diag - e + sum/4) */ \
+                    const double q0 = (bc0 || brow) ? 0. : 0.25, q1 = (bc1 || brow) ? 0. : 0.25;            \
+                    const double w0 = (bc0 || brow) ? 1. : g.diag, w1 = (bc1 || brow) ? 1. : g.diag;        \
+                    r0v = w0 * fma(q0, (up.x + dn.x) + (lf + c.y), b0 - c.x);                               \
+                    r1v = w1 * fma(q1, (up.y + dn.y) + (c.x + rt), b1 - c.y);                               \
+                }                                                                                           \
+                acc += r0v * r0v;                                                                           \
+                if (j0 + 1 < g.w) acc += r1v * r1v;                                                         \
+            }                                                                                               \
+            roq += TW; if (roq >= WR * TW) roq -= WR * TW;                                                  \
         }                                                                                                   \
     }
     for (int k0 = 0; k0 < ksteps; k0 += PF) {
@@ -570,6 +623,10 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
         MGB_STREAM_STEP(3)
     }
 #undef MGB_STREAM_STEP
+    if (MODE == 1) {
+        const double tsum = block_sum(acc, red);
+        if (t == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = tsum;
+    }
 }
 
 }  // namespace mgb

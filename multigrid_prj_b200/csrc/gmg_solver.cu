@@ -106,6 +106,8 @@ struct mgb_gmg {
     int ls = -1;                      // last sharded level (-1: single rank)
     int lt = -1;                      // first level of the persistent coarse tail (-1: no tail kernel)
     int u_halo_valid = 0;             // halo rows of u known to be current (communication-avoiding path)
+    int norm_partials = 0;            // > 0: the last fine post-smoothing launch left that many partial sums of the
+                                      // new iterate's squared residual in d_partial (fused correction + norm)
     cudaStream_t st = nullptr;
     mgb::NcclComm comm = nullptr;
     double *d_partial = nullptr;      // per-CTA partial sums
@@ -198,14 +200,14 @@ int read_scalar(mgb_gmg *h, int slot, double *out)
 }
 
 // resident CTAs per SM of one instantiation of the streaming kernel (also raises its dynamic-smem limit)
-template <int S, bool EXACT>
+template <int S, bool EXACT, int MODE>
 int stream_occupancy(int *out)
 {
     static int occ = 0;
     constexpr int smem = mgb::stream_smem_bytes<S>();
     if (!occ) {
-        CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT>, mgb::kStreamNT, smem));
+        CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT, MODE>, mgb::kStreamNT, smem));
         occ = std::max(1, occ);
     }
     *out = occ;
@@ -215,19 +217,21 @@ int stream_occupancy(int *out)
 int prepare_kernels()
 {
     int o, rc;
-    if ((rc = stream_occupancy<2, true>(&o)) || (rc = stream_occupancy<2, false>(&o)) || (rc = stream_occupancy<4, true>(&o)) ||
-        (rc = stream_occupancy<4, false>(&o)) || (rc = stream_occupancy<10, true>(&o)) || (rc = stream_occupancy<10, false>(&o)))
+    if ((rc = stream_occupancy<2, true, 0>(&o)) || (rc = stream_occupancy<2, false, 0>(&o)) || (rc = stream_occupancy<4, true, 0>(&o)) ||
+        (rc = stream_occupancy<4, false, 0>(&o)) || (rc = stream_occupancy<10, true, 0>(&o)) || (rc = stream_occupancy<10, false, 0>(&o)) ||
+        (rc = stream_occupancy<2, true, 1>(&o)) || (rc = stream_occupancy<2, false, 1>(&o)) || (rc = stream_occupancy<4, true, 1>(&o)) ||
+        (rc = stream_occupancy<4, false, 1>(&o)) || (rc = stream_occupancy<10, true, 1>(&o)) || (rc = stream_occupancy<10, false, 1>(&o)))
         return rc;
     CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
     return MGB_OK;
 }
 
-template <int S, bool EXACT>
-int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out)
+template <int S, bool EXACT, int MODE>
+int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr)
 {
     int occ = 1;
     constexpr int smem = mgb::stream_smem_bytes<S>();
-    if (int rc = stream_occupancy<S, EXACT>(&occ)) return rc;
+    if (int rc = stream_occupancy<S, EXACT, MODE>(&occ)) return rc;
     const int OW = mgb::kStreamTW - 2 * S;
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
@@ -246,31 +250,44 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
             if (t < best) { best = t; rc = c; ny = n; }
         }
     }
-    mgb::k_rb_stream<S, EXACT><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc);
-    count(h, 24. * (S / 2) * npts(g));     // 24 B per point per sweep, S/2 sweeps per launch
+    if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
+    mgb::k_rb_stream<S, EXACT, MODE><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, h->d_partial);
+    // 24 B per point per sweep, S/2 sweeps per launch (+ correction 24 + norm-only residual 16 when fused)
+    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : 0.)) * npts(g));
+    if (MODE == 1) h->norm_partials = nx * ny;
     CK(cudaGetLastError());
     return MGB_OK;
 }
 
 // `sweeps` (1, 2 or 5) full red-black sweeps in one pass: in -> out
 // `ext` > 0: also produce `ext` rows of the halo on each interior side (the input must be valid ext + 2*sweeps deep)
-int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out, int ext = 0)
+// `ucorr` != nullptr: fused correction + residual norm (kernel MODE 1; owned rows only, ext must be 0)
+int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out, int ext = 0,
+                     double *ucorr = nullptr)
 {
     const View v = extended(h->lv[level], ext);
     const LevelGeom &g = v.g;
     in += v.off; rhs += v.off; out += v.off;
     const bool ex = !h->cfg.rb_fast_arith;
+    if (ucorr) {
+        switch (sweeps) {
+        case 1: return ex ? launch_rb_stream_t<2, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<2, false, 1>(h, g, in, rhs, out, ucorr);
+        case 2: return ex ? launch_rb_stream_t<4, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<4, false, 1>(h, g, in, rhs, out, ucorr);
+        case 5: return ex ? launch_rb_stream_t<10, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<10, false, 1>(h, g, in, rhs, out, ucorr);
+        default: return fail(MGB_ERR_ARG, "unsupported sweep group");
+        }
+    }
     switch (sweeps) {
-    case 1: return ex ? launch_rb_stream_t<2, true>(h, g, in, rhs, out) : launch_rb_stream_t<2, false>(h, g, in, rhs, out);
-    case 2: return ex ? launch_rb_stream_t<4, true>(h, g, in, rhs, out) : launch_rb_stream_t<4, false>(h, g, in, rhs, out);
-    case 5: return ex ? launch_rb_stream_t<10, true>(h, g, in, rhs, out) : launch_rb_stream_t<10, false>(h, g, in, rhs, out);
+    case 1: return ex ? launch_rb_stream_t<2, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<2, false, 0>(h, g, in, rhs, out, nullptr);
+    case 2: return ex ? launch_rb_stream_t<4, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<4, false, 0>(h, g, in, rhs, out, nullptr);
+    case 5: return ex ? launch_rb_stream_t<10, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<10, false, 0>(h, g, in, rhs, out, nullptr);
     default: return fail(MGB_ERR_ARG, "unsupported sweep group");
     }
 }
 
 // Smoothing.  `rhs` must carry valid halo rows to the depth the chosen kernel reads
 // (fused red-black: 2 rows per sweep of the group; everything else: none -- only `sol` is read across rows).
-int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs)
+int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs, double *ucorr = nullptr)
 {
     Level &L = h->lv[level];
     if (sol == &L.u) h->u_halo_valid = 0;
@@ -289,8 +306,9 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
             // group the remaining sweeps: 5, 2 or 1 full sweeps per pass over HBM
             const int left = sweeps - s;
             const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
-            if ((rc = halo_exchange(h, level, *sol, 2 * grp))) return rc;
-            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch))) return rc;
+            double *uc = (left == grp) ? ucorr : nullptr;           // the last group applies the fused correction
+            if ((rc = halo_exchange(h, level, *sol, 2 * grp + (uc ? 1 : 0)))) return rc;
+            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, 0, uc))) return rc;
             std::swap(*sol, scratch);
             s += grp - 1;
         } else if (kind == MGB_SMOOTH_GS_RB) {
@@ -457,13 +475,20 @@ struct Depths {
     std::vector<int> din, dout, ext_r;     // per level: input halo the post-smoother reads, halo rows it must
 };                                         // produce for the prolongation above it, halo rows of r made by restriction
 
+// the correction u += e and the new iterate's residual norm ride on the last fine post-smoothing launch
+bool fuse_corr(mgb_gmg *h)
+{
+    return h->cfg.fuse_correction && h->cfg.smoother == MGB_SMOOTH_GS_RB && h->cfg.rb_fused && h->cfg.nu > 0 &&
+           h->lv.size() > 1 && h->lt != 0;
+}
+
 Depths plan_depths(mgb_gmg *h)
 {
     const int L = (int)h->lv.size();
     Depths d;
     d.din.assign(L, 0); d.dout.assign(L, 0); d.ext_r.assign(L, 0);
     for (int l = 0; l <= h->ls; ++l) {
-        d.din[l] = d.dout[l] + 2 * h->cfg.nu;
+        d.din[l] = d.dout[l] + 2 * h->cfg.nu + ((l == 0 && fuse_corr(h)) ? 1 : 0);
         if (l + 1 <= h->ls) d.dout[l + 1] = (d.din[l] + 1) / 2 + 1;
     }
     if (h->ls + 1 < L) d.ext_r[h->ls] = 1;              // rows of the first replicated level need fine rows +-1
@@ -485,13 +510,15 @@ bool ca_applicable(mgb_gmg *h)
 }
 
 // fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
-int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out)
+int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out,
+              double *ucorr = nullptr)
 {
     int left = sweeps, rc;
+    const int x = ucorr ? 1 : 0;            // the fused correction reads one more final row on each side
     while (left > 0) {
         const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
         left -= grp;
-        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, ext_out + 2 * left))) return rc;
+        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, left ? ext_out + x + 2 * left : ext_out, left ? nullptr : ucorr))) return rc;
         std::swap(*sol, scratch);
     }
     return MGB_OK;
@@ -504,6 +531,7 @@ int one_iteration_ca(mgb_gmg *h)
     const Depths d = plan_depths(h);
     auto &N = mgb::nccl();
     int rc;
+    h->norm_partials = 0;
     // (1) u: one exchange serves the pre-sweeps (2 rows per sweep) and the residual after them (+1)
     const int ext_u = 2 * h->cfg.n_pre + 1;
     if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
@@ -598,7 +626,17 @@ int one_iteration_ca(mgb_gmg *h)
         mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, vf.g, C.e, Fl.e + vf.off);
         count(h, 8. * (npts(vf.g) + npts(C.g)));
         CK(cudaGetLastError());
-        if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1]))) return rc;
+        double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+        if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc))) return rc;
+    }
+    if (fuse_corr(h)) {
+        h->u_halo_valid = 0;
+        h->stats.cycles++;
+        if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;          // for the next iteration's pre-sweeps
+        h->u_halo_valid = ext_u;
+        const int np = h->norm_partials;
+        h->norm_partials = 0;
+        return reduce_partials(h, np, 1, true);
     }
     if ((rc = finish_cycle(h))) return rc;
     // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
@@ -619,6 +657,7 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     Level &F = h->lv[0], &C = h->lv[L - 1];
     const int kind = h->cfg.smoother;
     int rc;
+    h->norm_partials = 0;
     // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
     if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
     if ((rc = do_restrict(h))) return rc;
@@ -635,8 +674,10 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
         }
         for (int j = h->lt; j > 0; --j) {
             if ((rc = do_prolong(h, j))) return rc;
-            if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
+            double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+            if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
         }
+        if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
         return finish_cycle(h);
     }
     // :128 COARSE_RES->refresh_normalization_constant()
@@ -660,8 +701,10 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     // :134-139
     for (int j = L - 1; j > 0; --j) {
         if ((rc = do_prolong(h, j))) return rc;
-        if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
+        double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+        if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
     }
+    if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
     return finish_cycle(h);
 }
 
@@ -687,6 +730,11 @@ int one_iteration(mgb_gmg *h)
     int rc;
     if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
     if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
+    if (h->norm_partials > 0) {          // the fused last launch already left the new iterate's residual partial sums
+        const int np = h->norm_partials;
+        h->norm_partials = 0;
+        return reduce_partials(h, np, 1, h->lv[0].sharded);
+    }
     return do_residual(h, 0, F.u, F.f, nullptr, 1);
 }
 
@@ -782,7 +830,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
     c->tail_max_width = 129; c->use_graph = 1;
-    c->rb_fast_arith = 0; c->rb_fused = 1;
+    c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0;
 }
 
 void mgb_gmg_config_fast(mgb_gmg_config *c)
@@ -792,6 +840,7 @@ void mgb_gmg_config_fast(mgb_gmg_config *c)
     c->pre_smoother = MGB_SMOOTH_GS_RB;
     c->restriction = MGB_RESTRICT_FULL_WEIGHTING;
     c->rb_fast_arith = 1;
+    c->fuse_correction = 1;
 }
 
 int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows)
@@ -880,7 +929,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         for (int l = 0; l < L; ++l)
             if (h->lv[l].g.w <= cfg->tail_max_width && !h->lv[l].sharded && L - l <= mgb::kTailMaxLevels) { h->lt = l; break; }
     }
-    h->n_partial = max_partial;
+    h->n_partial = std::max<size_t>(max_partial, 1 << 16);
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));
     CK(cudaMalloc(&h->d_scal, 16 * sizeof(double)));
     CK(cudaMemsetAsync(h->d_scal, 0, 16 * sizeof(double), h->st));

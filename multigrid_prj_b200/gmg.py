@@ -37,6 +37,7 @@ class GmgConfig:
     use_graph: int = 1
     rb_fast_arith: int = 0
     rb_fused: int = 1
+    fuse_correction: int = 0
 
     @staticmethod
     def fast(n, levels, **kw):
@@ -45,6 +46,7 @@ class GmgConfig:
         kw.setdefault("pre_smoother", GS_RB)
         kw.setdefault("restriction", FULL_WEIGHTING)
         kw.setdefault("rb_fast_arith", 1)
+        kw.setdefault("fuse_correction", 1)
         return GmgConfig(n=n, levels=levels, **kw)
 
 
@@ -70,7 +72,7 @@ class Gmg:
         self.lib.mgb_gmg_config_default(C.byref(c))
         for k in ("n", "levels", "length", "alpha", "smoother", "pre_smoother", "n_pre", "nu",
                   "restriction", "coarse_tol", "coarse_maxit", "device", "rank", "n_ranks",
-                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused"):
+                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction"):
             setattr(c, k, getattr(cfg, k))
         if cfg.nccl_id:
             C.memmove(c.nccl_id, cfg.nccl_id, min(128, len(cfg.nccl_id)))

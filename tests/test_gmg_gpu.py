@@ -221,6 +221,23 @@ def test_persistent_coarse_tail_equals_per_level_launches(kind, restr, N, L):
         assert np.allclose([i[0] for i in info], [i[0] for i in res[0][1]], rtol=1e-10)
 
 
+@pytest.mark.parametrize("N,L", [(257, 8), (1025, 10), (2049, 5), (513, 2)])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_fused_correction_and_norm_equal_separate_passes(N, L, fast):
+    """the last fine post-smoothing launch applies u += err and leaves ||rhs - A err||^2 = ||f - A u_new||^2:
+    same u bit for bit, same norm up to rounding, as the separate axpy + residual passes"""
+    out = []
+    for fuse in (0, 1):
+        for graph in (0, 1):
+            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_correction=fuse, use_graph=graph)) as g:
+                g.set_rhs_test(1); g.set_u(None)
+                rel = [g.run_cycles(1), g.run_cycles(4), g.run_cycles(3)]
+                out.append((g.get_u(), rel))
+    for u, rel in out[1:]:
+        assert np.array_equal(u, out[0][0])
+        assert np.allclose(rel, out[0][1], rtol=1e-6, atol=1e-14)
+
+
 def test_device_sampled_rhs_close_to_host(orc):
     N = 129
     with Gmg(GmgConfig(n=N, levels=3)) as g:
