@@ -512,8 +512,11 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     __shared__ double red[kStreamNT / 32];
 
     const int t = threadIdx.x;
-    const int OW = TW - 2 * S;
-    const int jbase = blockIdx.x * OW - S;           // global column of tile column 0 (even)
+    // halo columns per side: S for the S half-sweeps; MODE 1 reads FINAL values of the lateral neighbours, i.e. one
+    // more valid column, and a column pair is the unit of ownership
+    constexpr int HC = S + 2 * X;
+    const int OW = TW - 2 * HC;
+    const int jbase = blockIdx.x * OW - HC;          // global column of tile column 0 (even)
     const int j0 = jbase + 2 * t;                    // this thread's even column
     const int jl = min(max(j0, 0), g.pitch - 2);     // clamped for loads
     const int i0 = blockIdx.y * rows_per_chunk;      // rows_per_chunk is even (host)
@@ -529,7 +532,7 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     const bool first_is_bdry = (g.row0 + ifirst == 0), last_is_bdry = (g.row0 + ilast == g.w - 1);
     const ptrdiff_t P = g.pitch;
     const double inv_diag = 1.0 / g.diag;
-    const bool own = (2 * t >= S) && (2 * t < TW - S) && (j0 < g.w) && (j0 >= 0);
+    const bool own = (2 * t >= HC) && (2 * t < TW - HC) && (j0 < g.w) && (j0 >= 0);
     // Dirichlet-column flags of the pair; columns outside the domain are frozen the same way
     const bool bc0 = (j0 <= 0) || (j0 >= g.w - 1);
     const bool bc1 = (j0 + 1 <= 0) || (j0 + 1 >= g.w - 1);

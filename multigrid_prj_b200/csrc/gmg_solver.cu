@@ -232,7 +232,7 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
     int occ = 1;
     constexpr int smem = mgb::stream_smem_bytes<S>();
     if (int rc = stream_occupancy<S, EXACT, MODE>(&occ)) return rc;
-    const int OW = mgb::kStreamTW - 2 * S;
+    const int OW = mgb::kStreamTW - 2 * (S + 2 * MODE);       // owned columns per CTA (kernel: HC)
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
     // rows per chunk: a CTA needs (rc + 2S) steps and the grid needs ceil(nx*ny/slots) waves; pick the
