@@ -416,7 +416,7 @@ __device__ __forceinline__ double rb_point(double b, double up, double left, dou
 // at the tile edge / outside the domain compute harmless garbage there: tile-edge columns are
 // halo (invalid after s half-sweeps by construction) and the Dirichlet columns j=0, j=w-1 never
 // read their neighbours, so nothing crosses into the domain.
-template <int S, bool EXACT, int PAR, bool GUARD>
+template <int S, bool EXACT, int PAR, bool GUARD, int BATCH>
 __device__ __forceinline__ void rb_stream_step(
     const LevelGeom &g, double2 (&uw)[2 * S + 3], int (&ro)[S + 1], double2 nu, double2 nb, double *su,
     double *sb, int i, bool bc0, bool bc1, int ifirst, int ilast, bool first_is_bdry,
@@ -441,45 +441,54 @@ __device__ __forceinline__ void rb_stream_step(
     // load: the load registers then die here and the next prefetch can land in them without a
     // dependent register move at the loop back-edge
     uw[0] = make_double2(su[ro[0]], su[ro[0] + H]);
-    double bv[S], ob[S];
+    // the S half-sweep updates of a step are mutually independent: operands of a whole batch are read first
+    // (shared-memory latency paid once per batch), then computed, then published
 #pragma unroll
-    for (int s = 1; s <= S; ++s) {
-        const int which = (PAR + (s - 1)) & 1;        // rows i-2s have the parity of row i
-        bv[s - 1] = sb[ro[s] + which * H];
-        // neighbour held by the adjacent thread: even column 2t -> odd[t-1]; odd column 2t+1 -> even[t+1]
-        ob[s - 1] = su[ro[s] + (which ? 1 : (H - 1))];
-    }
+    for (int s0 = 1; s0 <= S; s0 += BATCH) {
+        double bv[BATCH], ob[BATCH];
 #pragma unroll
-    for (int s = 1; s <= S; ++s) {
-        const int which = (PAR + (s - 1)) & 1;
-        const int d = 2 * s;
-        bool act = true;
-        bool isb = which ? bc1 : bc0;
-        bool brow = false;
-        if (GUARD) {
-            const int r = i - d;
-            const int vlo = first_is_bdry ? ifirst : ifirst + s;
-            const int vhi = last_is_bdry ? ilast : ilast - s;
-            act = (r >= vlo) && (r <= vhi);
-            brow = (r + g.row0 == 0) || (r == glast);
-            isb = isb || brow;
+        for (int k = 0; k < BATCH; ++k) {
+            const int s = s0 + k;
+            if (s > S) break;
+            const int which = (PAR + (s - 1)) & 1;        // rows i-2s have the parity of row i
+            bv[k] = sb[ro[s] + which * H];
+            // neighbour held by the adjacent thread: even column 2t -> odd[t-1]; odd column 2t+1 -> even[t+1]
+            ob[k] = su[ro[s] + (which ? 1 : (H - 1))];
         }
-        const double up = which ? uw[d + 1].y : uw[d + 1].x;
-        const double dn = which ? uw[d - 1].y : uw[d - 1].x;
-        const double left = which ? uw[d].x : ob[s - 1];
-        const double right = which ? ob[s - 1] : uw[d].y;
-        double nv;
-        if (EXACT) {
-            nv = smooth_point(bv[s - 1], up, left, right, dn, g.off, g.diag);
-            nv = isb ? bv[s - 1] : nv;
-        } else {
-            double q = which ? q1 : q0;
-            if (GUARD) q = brow ? 0. : q;
-            nv = fma(q, (up + dn) + (left + right), bv[s - 1]);
-        }
-        if (act) {
-            if (which) uw[d].y = nv; else uw[d].x = nv;
-            su[ro[s] + which * H] = nv;
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int s = s0 + k;
+            if (s > S) break;
+            const int which = (PAR + (s - 1)) & 1;
+            const int d = 2 * s;
+            bool act = true;
+            bool isb = which ? bc1 : bc0;
+            bool brow = false;
+            if (GUARD) {
+                const int r = i - d;
+                const int vlo = first_is_bdry ? ifirst : ifirst + s;
+                const int vhi = last_is_bdry ? ilast : ilast - s;
+                act = (r >= vlo) && (r <= vhi);
+                brow = (r + g.row0 == 0) || (r == glast);
+                isb = isb || brow;
+            }
+            const double up = which ? uw[d + 1].y : uw[d + 1].x;
+            const double dn = which ? uw[d - 1].y : uw[d - 1].x;
+            const double left = which ? uw[d].x : ob[k];
+            const double right = which ? ob[k] : uw[d].y;
+            double nv;
+            if (EXACT) {
+                nv = smooth_point(bv[k], up, left, right, dn, g.off, g.diag);
+                nv = isb ? bv[k] : nv;
+            } else {
+                double q = which ? q1 : q0;
+                if (GUARD) q = brow ? 0. : q;
+                nv = fma(q, (up + dn) + (left + right), bv[k]);
+            }
+            if (act) {
+                if (which) uw[d].y = nv; else uw[d].x = nv;
+                su[ro[s] + which * H] = nv;
+            }
         }
     }
     // advance every carried ring offset by one row
@@ -505,6 +514,7 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     constexpr int TW = kStreamTW, PF = kStreamPF, H = TW / 2;
     constexpr int WR = 2 * S + 3;
     constexpr int X = (MODE == 1) ? 1 : 0;
+    constexpr int BATCH = (MODE == 1 && S > 5) ? 5 : S;     // MODE 1 is register-bound: operands in two batches
     static_assert(PF == 4, "the main loop is unrolled by 4 rows");
     extern __shared__ double smem[];
     double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
@@ -554,11 +564,11 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
 #pragma unroll
     for (int s = 0; s <= S; ++s) ro[s] = ((WR - 2 * s) % WR) * TW + t;
     int roq = ((WR - (2 * S + 1)) % WR) * TW + t;    // ring offset of row i-2S-1 (MODE 1: the residual row)
-    double2 pc[2];                                   // MODE 1: rows of ucorr, requested two steps ahead
+    double2 pc[PF];                                  // MODE 1: rows of ucorr, requested PF steps ahead
     double acc = 0.;
     if (MODE == 1) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < PF; ++p) {
             int r = min(max(ifirst + p - 2 * S, i0), i1 - 1);
             pc[p] = ld2(ucorr + (ptrdiff_t)r * P + jl);
         }
@@ -574,10 +584,10 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
         }                                                                                                   \
         const bool steady = (i >= i_lo) && (i <= i_hi);                                                     \
         if (steady)                                                                                         \
-            rb_stream_step<S, EXACT, ((p) & 1), false>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst,      \
+            rb_stream_step<S, EXACT, ((p) & 1), false, BATCH>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst, \
                                                        ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         else                                                                                                \
-            rb_stream_step<S, EXACT, ((p) & 1), true>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst,       \
+            rb_stream_step<S, EXACT, ((p) & 1), true, BATCH>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst, \
                                                       ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         const int r = i - 2 * S;                     /* final after this step */                             \
         if (MODE == 0) {                                                                                    \
@@ -586,10 +596,10 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
                 if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                         \
             }                                                                                               \
         } else {                                                                                            \
-            const double2 uc = pc[(p) & 1];                                                                 \
+            const double2 uc = pc[p];                                                                       \
             {                                                                                               \
-                int r2 = min(max(r + 2, i0), i1 - 1);                                                       \
-                pc[(p) & 1] = ld2(ucorr + (ptrdiff_t)r2 * P + jl);                                          \
+                int r2 = min(max(r + PF, i0), i1 - 1);                                                      \
+                pc[p] = ld2(ucorr + (ptrdiff_t)r2 * P + jl);                                                \
             }                                                                                               \
             if (r >= i0 && r < i1 && own) {                                                                 \
                 double *dstp = ucorr + (ptrdiff_t)r * P + j0;                                               \
@@ -597,24 +607,24 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
                 if (j0 + 1 < g.w) st2(dstp, un); else dstp[0] = un.x;                                       \
             }                                                                                               \
             const int q = r - 1;                     /* rows q-1, q, q+1 are final: residual of row q */     \
-            if (q >= i0 && q < i1 && own) {                                                                 \
+            /* The black point of the pair was the last one updated and nothing around it changed since, so its   \
+               residual is a rounding error of its own update (~1e-16 of the terms) and Dirichlet points have     \
+               residual 0 exactly: only the RED interior point of the pair contributes to the sum. */              \
+            const bool brow = (q + g.row0 == 0) || (q == glast);                                            \
+            if (q >= i0 && q < i1 && own && !brow) {                                                        \
                 const double2 c = uw[2 * S + 1], up = uw[2 * S + 2], dn = uw[2 * S];                        \
-                const double lf = su[roq + H - 1], rt = su[roq + 1];                                        \
-                const double b0 = sb[roq], b1 = sb[roq + H];                                                \
-                const bool brow = (q + g.row0 == 0) || (q == glast);                                        \
-                double r0v, r1v;                                                                            \
-                if (EXACT) {                                                                                \
-                    r0v = (bc0 || brow) ? __dsub_rn(b0, c.x) : resid_point(b0, up.x, lf, c.x, c.y, dn.x, g.off, g.diag); \
-                    r1v = (bc1 || brow) ? __dsub_rn(b1, c.y) : resid_point(b1, up.y, c.x, c.y, rt, dn.y, g.off, g.diag); \
+                constexpr int RED = ((p) & 1) ^ 1;   /* row q has the other parity than row i: red = column of that parity */ \
+                double rv;                                                                                  \
+                if (RED == 0) {                                                                             \
+                    const double lf = su[roq + H - 1], b0 = sb[roq];                                        \
+                    if (EXACT) rv = bc0 ? 0. : resid_point(b0, up.x, lf, c.x, c.y, dn.x, g.off, g.diag);     \
+                    else rv = bc0 ? 0. : g.diag * fma(0.25, (up.x + dn.x) + (lf + c.y), b0 - c.x);           \
                 } else {                                                                                    \
-                    /* the ring holds b/diag (b itself on Dirichlet points): r = diag*(b/diag - e + sum/4) */ \
-                    const double q0 = (bc0 || brow) ? 0. : 0.25, q1 = (bc1 || brow) ? 0. : 0.25;            \
-                    const double w0 = (bc0 || brow) ? 1. : g.diag, w1 = (bc1 || brow) ? 1. : g.diag;        \
-                    r0v = w0 * fma(q0, (up.x + dn.x) + (lf + c.y), b0 - c.x);                               \
-                    r1v = w1 * fma(q1, (up.y + dn.y) + (c.x + rt), b1 - c.y);                               \
+                    const double rt = su[roq + 1], b1 = sb[roq + H];                                        \
+                    if (EXACT) rv = bc1 ? 0. : resid_point(b1, up.y, c.x, c.y, rt, dn.y, g.off, g.diag);     \
+                    else rv = bc1 ? 0. : g.diag * fma(0.25, (up.y + dn.y) + (c.x + rt), b1 - c.y);           \
                 }                                                                                           \
-                acc += r0v * r0v;                                                                           \
-                if (j0 + 1 < g.w) acc += r1v * r1v;                                                         \
+                acc += rv * rv;                                                                             \
             }                                                                                               \
             roq += TW; if (roq >= WR * TW) roq -= WR * TW;                                                  \
         }                                                                                                   \
