@@ -107,6 +107,64 @@ k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__rest
     if (ok && lane == 0) xnew[i] = (b[i] - sum) / diag[i];
 }
 
+// ---- fast path: sliced-ELLPACK copy of the level operator ---------------------------------------------------------------
+// The vector-CSR kernels above are latency-bound on P1 operators (~7 entries per row: row_ptr -> col/val -> x is
+// a chain of three dependent loads with one row in flight per sub-warp).  The fast kernels therefore read a second
+// copy of A in SELL-32 form: rows are sorted by colour (every colour starts on a slice boundary, so a colour is a
+// contiguous range of slices), a slice stores the OFF-DIAGONAL entries of 32 rows column-major, padded to the
+// longest row of the slice.  One thread owns one row: its loads of col/val are coalesced across the warp and
+// mutually independent (all entries of the row in flight at once), and there is no row_ptr load on the path.
+struct SellDev {
+    int n_slots;                 // rows including padding (multiple of 32)
+    const int *slice_ptr;        // [n_slots/32 + 1] offsets into col/val
+    const int *col;              // column of each stored entry (padding: 0)
+    const double *val;           // value (padding: 0.0)
+    const int *row_of_slot;      // original row of a slot, -1 for padding slots
+    const double *diag_s, *b_s;  // diagonal and right-hand side in slot order
+};
+
+// MODE 0: r = b - A x (+ sum r^2 per CTA); MODE 1: Jacobi into `out`; MODE 2: Gauss-Seidel on the slots
+// [first, last) of one colour, in place on x
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *out, double *__restrict__ partial,
+           int first, int last)
+{
+    __shared__ double red[8];
+    const int p = first + blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.;
+    if (p < last) {
+        const int i = A.row_of_slot[p];
+        if (i >= 0) {
+            const int s = p >> 5;
+            const int base = A.slice_ptr[s] + (p & 31);
+            const int len = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
+            double sum = 0.;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) sum += A.val[base + 32 * k] * x[A.col[base + 32 * k]];
+            const double d = A.diag_s[p], bi = b_s[p];
+            if (MODE == 0) {
+                const double ri = bi - (sum + d * x[i]);
+                if (out) out[i] = ri;
+                acc = ri * ri;
+            } else
+                out[i] = (bi - sum) / d;
+        }
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double t = threadIdx.x < 8 ? red[threadIdx.x] : 0.;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) partial[blockIdx.x] = t;
+        }
+    }
+}
+
 // ---- residual r = b - A x and its squared norm (AMG/src/AMG.cpp:256-275) ------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(256)

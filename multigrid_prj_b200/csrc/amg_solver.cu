@@ -193,12 +193,23 @@ struct Schedule {          // rows grouped into independent sets (wavefronts or 
     void release() { cudaFree(d_ptr); cudaFree(d_rows); d_ptr = d_rows = nullptr; }
 };
 
+struct SellCopy {              // colour-sorted SELL-32 copy of A for the fast kernels (amg_kernels.cuh)
+    int n_slots = 0;
+    std::vector<int> colour_slot_ptr;      // first slot of each colour (+ end)
+    int *slice_ptr = nullptr, *col = nullptr, *row_of_slot = nullptr;
+    double *val = nullptr, *diag_s = nullptr, *b_s = nullptr;
+    size_t stored = 0;                     // entries incl. padding
+    mgb::SellDev view() const { return mgb::SellDev{n_slots, slice_ptr, col, val, row_of_slot, diag_s, b_s}; }
+    void release() { cudaFree(slice_ptr); cudaFree(col); cudaFree(row_of_slot); cudaFree(val); cudaFree(diag_s); cudaFree(b_s); }
+};
+
 struct AmgLevel {
     HostCsr hA, hP;                       // host copies (hierarchy queries, schedules)
     std::vector<double> h_rhs;
     DevCsr A, P, R;
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
     Schedule lex, colour;
+    SellCopy sell;
 };
 
 }  // namespace
@@ -291,6 +302,68 @@ int build_colouring(mgb_amg *h, AmgLevel &L)
     return upload_schedule(colour, nc, L.colour, h->st);
 }
 
+// colour-sorted SELL-32 copy (off-diagonal entries) + slot-ordered diagonal and rhs
+int build_sell(mgb_amg *h, AmgLevel &L)
+{
+    const HostCsr &A = L.hA;
+    const int n = A.n_rows, ncol = L.colour.n_groups;
+    SellCopy &S = L.sell;
+    std::vector<int> row_of_slot;
+    S.colour_slot_ptr.assign(ncol + 1, 0);
+    {
+        std::vector<std::vector<int>> by_colour(std::max(ncol, 1));
+        for (int i = 0; i < n; ++i) by_colour[L.colour.h_group[i]].push_back(i);
+        for (int c = 0; c < ncol; ++c) {
+            S.colour_slot_ptr[c] = (int)row_of_slot.size();
+            row_of_slot.insert(row_of_slot.end(), by_colour[c].begin(), by_colour[c].end());
+            while (row_of_slot.size() % 32) row_of_slot.push_back(-1);        // every colour starts on a slice boundary
+        }
+        S.colour_slot_ptr[ncol] = (int)row_of_slot.size();
+    }
+    S.n_slots = (int)row_of_slot.size();
+    const int n_slices = S.n_slots / 32;
+    std::vector<int> slice_ptr(n_slices + 1, 0);
+    for (int s = 0; s < n_slices; ++s) {
+        int longest = 0;
+        for (int q = 0; q < 32; ++q) {
+            const int i = row_of_slot[32 * s + q];
+            if (i < 0) continue;
+            int len = 0;
+            for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) len += (A.col[k] != i);
+            longest = std::max(longest, len);
+        }
+        slice_ptr[s + 1] = slice_ptr[s] + 32 * longest;
+    }
+    S.stored = (size_t)slice_ptr[n_slices];
+    std::vector<int> col(std::max<size_t>(S.stored, 1), 0);
+    std::vector<double> val(std::max<size_t>(S.stored, 1), 0.0), diag_s(std::max(S.n_slots, 1), 1.0), b_s(std::max(S.n_slots, 1), 0.0);
+    for (int p = 0; p < S.n_slots; ++p) {
+        const int i = row_of_slot[p];
+        if (i < 0) continue;
+        int k2 = 0;
+        const int base = slice_ptr[p >> 5] + (p & 31);
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+            if (A.col[k] == i) continue;
+            col[base + 32 * k2] = A.col[k]; val[base + 32 * k2] = A.val[k]; ++k2;
+        }
+        diag_s[p] = A.at(i, i);
+        b_s[p] = L.h_rhs[i];
+    }
+    ACK(cudaMalloc(&S.slice_ptr, sizeof(int) * (size_t)(n_slices + 1)));
+    ACK(cudaMalloc(&S.col, sizeof(int) * col.size()));
+    ACK(cudaMalloc(&S.val, sizeof(double) * val.size()));
+    ACK(cudaMalloc(&S.row_of_slot, sizeof(int) * (size_t)std::max(S.n_slots, 1)));
+    ACK(cudaMalloc(&S.diag_s, sizeof(double) * diag_s.size()));
+    ACK(cudaMalloc(&S.b_s, sizeof(double) * b_s.size()));
+    ACK(cudaMemcpy(S.slice_ptr, slice_ptr.data(), sizeof(int) * (size_t)(n_slices + 1), cudaMemcpyHostToDevice));
+    ACK(cudaMemcpy(S.col, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice));
+    ACK(cudaMemcpy(S.val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
+    if (S.n_slots) ACK(cudaMemcpy(S.row_of_slot, row_of_slot.data(), sizeof(int) * (size_t)S.n_slots, cudaMemcpyHostToDevice));
+    ACK(cudaMemcpy(S.diag_s, diag_s.data(), sizeof(double) * diag_s.size(), cudaMemcpyHostToDevice));
+    ACK(cudaMemcpy(S.b_s, b_s.data(), sizeof(double) * b_s.size(), cudaMemcpyHostToDevice));
+    return MGB_OK;
+}
+
 int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
 {
     AmgLevel &L = h->lv[level];
@@ -314,13 +387,19 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
                 const int a = L.colour.h_ptr[c], b = L.colour.h_ptr[c + 1];
                 if (h->cfg.exact_order)
                     mgb::k_amg_gs_rows_exact<<<(b - a + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
-                else
-                    mgb::k_amg_gs_color_vec<<<((b - a) * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
+                else {
+                    const int p0 = L.sell.colour_slot_ptr[c], p1 = L.sell.colour_slot_ptr[c + 1];
+                    if (p1 > p0)
+                        mgb::k_amg_sell<2><<<(p1 - p0 + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.x, nullptr, p0, p1);
+                }
                 tally(h, sweep_bytes(L) * (double)(b - a) / A.n_rows);
             }
     } else if (kind == MGB_SMOOTH_JACOBI) {
         for (int s = 0; s < sweeps; ++s) {
-            mgb::k_amg_jacobi_vec<<<(A.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp);
+            if (h->cfg.exact_order)
+                mgb::k_amg_jacobi_vec<<<(A.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp);
+            else
+                mgb::k_amg_sell<1><<<(L.sell.n_slots + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, nullptr, 0, L.sell.n_slots);
             tally(h, sweep_bytes(L));
             std::swap(L.x, L.tmp);
         }
@@ -339,8 +418,8 @@ int do_residual(mgb_amg *h, int level, double *norm)
         blocks = (A.n_rows + 255) / 256;
         mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial);
     } else {
-        blocks = (A.n_rows * mgb::kLanes + 255) / 256;
-        mgb::k_amg_residual<false><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial);
+        blocks = (L.sell.n_slots + 255) / 256;
+        mgb::k_amg_sell<0><<<blocks, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, h->d_partial, 0, L.sell.n_slots);
     }
     tally(h, sweep_bytes(L));
     mgb::k_amg_reduce<<<1, 1024, 0, h->st>>>(h->d_partial, blocks, h->d_scal);
@@ -467,6 +546,7 @@ int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *
         }
         if ((rc = build_lex_schedule(h, L))) return rc;
         if ((rc = build_colouring(h, L))) return rc;
+        if ((rc = build_sell(h, L))) return rc;
         max_blocks = std::max(max_blocks, (size_t)(nl * mgb::kLanes + 255) / 256 + 1);
     }
     ACK(cudaMalloc(&h->d_partial, sizeof(double) * max_blocks));
@@ -482,7 +562,7 @@ void mgb_amg_destroy(mgb_amg_t h)
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &L : h->lv) {
-        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release();
+        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
     }
     cudaFree(h->d_partial); cudaFree(h->d_scal);
@@ -543,6 +623,14 @@ int mgb_amg_set_vector(mgb_amg_t h, int level, int which, const double *host)
     ACK(cudaSetDevice(h->cfg.device));
     if (L.A.n_rows) ACK(cudaMemcpyAsync(which == 0 ? L.x : L.b, host, sizeof(double) * (size_t)L.A.n_rows, cudaMemcpyHostToDevice, h->st));
     ACK(cudaStreamSynchronize(h->st));
+    if (which == 1 && L.sell.n_slots) {           // keep the slot-ordered copy of the right-hand side in step
+        std::vector<int> ros(L.sell.n_slots);
+        ACK(cudaMemcpy(ros.data(), L.sell.row_of_slot, sizeof(int) * (size_t)L.sell.n_slots, cudaMemcpyDeviceToHost));
+        std::vector<double> bs(L.sell.n_slots, 0.0);
+        for (int p = 0; p < L.sell.n_slots; ++p) if (ros[p] >= 0) bs[p] = host[ros[p]];
+        ACK(cudaMemcpy(L.sell.b_s, bs.data(), sizeof(double) * bs.size(), cudaMemcpyHostToDevice));
+        L.h_rhs.assign(host, host + L.A.n_rows);
+    }
     return MGB_OK;
 }
 
