@@ -80,7 +80,9 @@ typedef struct mgb_gmg_config {
                              u += err (multigrid.hpp:141-144) and leaves sum (res - A err)^2 = ||f - A u_new||^2, the norm
                              main.cpp:86 asks for next, from data already on chip (no axpy pass, no residual pass).
                              The norm then carries the rounding of res - A err instead of f - A u (same value to ~1e-13 ||f||). */
-    int reserved[5];
+    int fuse_residual;    /* red-black fused path only: the last driver pre-sweep launch also writes res = f - A u
+                             (multigrid.hpp:127) for the rows it produces (no separate residual pass) */
+    int reserved[4];
 } mgb_gmg_config;
 
 typedef struct mgb_gmg *mgb_gmg_t;

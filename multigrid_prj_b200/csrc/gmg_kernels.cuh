@@ -506,6 +506,8 @@ __device__ __forceinline__ void rb_stream_step(
 // Since rhs = f - A u_old, rhs - A e = f - A (u_old + e): this is the residual of the NEW iterate (main.cpp:86),
 // obtained from data already on chip -- no separate axpy pass and no separate residual pass over HBM.
 // It needs the final values of one more row on each side, so the stream starts/ends one row further out.
+// MODE 2 (the driver's pre-sweeps): uout = the smoothed u AND ucorr(:= the residual array) = rhs - A uout on the
+//   output rows, i.e. the fine residual of multigrid.hpp:127 without a separate pass that re-reads u and f.
 template <int S, bool EXACT, int MODE>
 __global__ void __launch_bounds__(kStreamNT)
 k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
@@ -513,7 +515,7 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
 {
     constexpr int TW = kStreamTW, PF = kStreamPF, H = TW / 2;
     constexpr int WR = 2 * S + 3;
-    constexpr int X = (MODE == 1) ? 1 : 0;
+    constexpr int X = (MODE != 0) ? 1 : 0;
     constexpr int BATCH = (MODE == 1 && S > 5) ? 5 : S;     // MODE 1 is register-bound: operands in two batches
     static_assert(PF == 4, "the main loop is unrolled by 4 rows");
     extern __shared__ double smem[];
@@ -590,12 +592,36 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
             rb_stream_step<S, EXACT, ((p) & 1), true, BATCH>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst, \
                                                       ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         const int r = i - 2 * S;                     /* final after this step */                             \
-        if (MODE == 0) {                                                                                    \
+        if (MODE == 0 || MODE == 2) {                                                                       \
             if (r >= i0 && r < i1 && own) {                                                                 \
                 double *dstp = uout + (ptrdiff_t)r * P + j0;                                                \
                 if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                         \
             }                                                                                               \
-        } else {                                                                                            \
+        }                                                                                                   \
+        if (MODE == 2) {                                                                                    \
+            const int q = r - 1;                     /* rows q-1, q, q+1 are final: residual of row q */     \
+            if (q >= i0 && q < i1 && own) {                                                                 \
+                const double2 c = uw[2 * S + 1], up = uw[2 * S + 2], dn = uw[2 * S];                        \
+                const double lf = su[roq + H - 1], rt = su[roq + 1];                                        \
+                const double b0 = sb[roq], b1 = sb[roq + H];                                                \
+                const bool brow = (q + g.row0 == 0) || (q == glast);                                        \
+                double2 rv;                                                                                 \
+                if (EXACT) {                                                                                \
+                    rv.x = (bc0 || brow) ? __dsub_rn(b0, c.x) : resid_point(b0, up.x, lf, c.x, c.y, dn.x, g.off, g.diag); \
+                    rv.y = (bc1 || brow) ? __dsub_rn(b1, c.y) : resid_point(b1, up.y, c.x, c.y, rt, dn.y, g.off, g.diag); \
+                } else {                                                                                    \
+                    /* the ring holds b/diag (b itself on Dirichlet points): r = diag*(b/diag - u + sum/4) */ \
+                    const double q0 = (bc0 || brow) ? 0. : 0.25, q1 = (bc1 || brow) ? 0. : 0.25;            \
+                    const double w0 = (bc0 || brow) ? 1. : g.diag, w1 = (bc1 || brow) ? 1. : g.diag;        \
+                    rv.x = w0 * fma(q0, (up.x + dn.x) + (lf + c.y), b0 - c.x);                              \
+                    rv.y = w1 * fma(q1, (up.y + dn.y) + (c.x + rt), b1 - c.y);                              \
+                }                                                                                           \
+                double *dstp = ucorr + (ptrdiff_t)q * P + j0;                                               \
+                if (j0 + 1 < g.w) st2(dstp, rv); else dstp[0] = rv.x;                                       \
+            }                                                                                               \
+            roq += TW; if (roq >= WR * TW) roq -= WR * TW;                                                  \
+        }                                                                                                   \
+        if (MODE == 1) {                                                                                            \
             const double2 uc = pc[p];                                                                       \
             {                                                                                               \
                 int r2 = min(max(r + PF, i0), i1 - 1);                                                      \

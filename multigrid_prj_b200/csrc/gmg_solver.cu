@@ -106,6 +106,7 @@ struct mgb_gmg {
     int ls = -1;                      // last sharded level (-1: single rank)
     int lt = -1;                      // first level of the persistent coarse tail (-1: no tail kernel)
     int u_halo_valid = 0;             // halo rows of u known to be current (communication-avoiding path)
+    bool r0_ready = false;            // the fused pre-sweep launch already wrote the fine residual into r (level 0)
     int norm_partials = 0;            // > 0: the last fine post-smoothing launch left that many partial sums of the
                                       // new iterate's squared residual in d_partial (fused correction + norm)
     cudaStream_t st = nullptr;
@@ -220,7 +221,9 @@ int prepare_kernels()
     if ((rc = stream_occupancy<2, true, 0>(&o)) || (rc = stream_occupancy<2, false, 0>(&o)) || (rc = stream_occupancy<4, true, 0>(&o)) ||
         (rc = stream_occupancy<4, false, 0>(&o)) || (rc = stream_occupancy<10, true, 0>(&o)) || (rc = stream_occupancy<10, false, 0>(&o)) ||
         (rc = stream_occupancy<2, true, 1>(&o)) || (rc = stream_occupancy<2, false, 1>(&o)) || (rc = stream_occupancy<4, true, 1>(&o)) ||
-        (rc = stream_occupancy<4, false, 1>(&o)) || (rc = stream_occupancy<10, true, 1>(&o)) || (rc = stream_occupancy<10, false, 1>(&o)))
+        (rc = stream_occupancy<4, false, 1>(&o)) || (rc = stream_occupancy<10, true, 1>(&o)) || (rc = stream_occupancy<10, false, 1>(&o)) ||
+        (rc = stream_occupancy<2, true, 2>(&o)) || (rc = stream_occupancy<2, false, 2>(&o)) || (rc = stream_occupancy<4, true, 2>(&o)) ||
+        (rc = stream_occupancy<4, false, 2>(&o)) || (rc = stream_occupancy<10, true, 2>(&o)) || (rc = stream_occupancy<10, false, 2>(&o)))
         return rc;
     CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
     return MGB_OK;
@@ -232,7 +235,7 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
     int occ = 1;
     constexpr int smem = mgb::stream_smem_bytes<S>();
     if (int rc = stream_occupancy<S, EXACT, MODE>(&occ)) return rc;
-    const int OW = mgb::kStreamTW - 2 * (S + 2 * MODE);       // owned columns per CTA (kernel: HC)
+    const int OW = mgb::kStreamTW - 2 * (S + 2 * (MODE != 0));    // owned columns per CTA (kernel: HC)
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
     // rows per chunk: a CTA needs (rc + 2S) steps and the grid needs ceil(nx*ny/slots) waves; pick the
@@ -253,7 +256,7 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
     if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
     mgb::k_rb_stream<S, EXACT, MODE><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, h->d_partial);
     // 24 B per point per sweep, S/2 sweeps per launch (+ correction 24 + norm-only residual 16 when fused)
-    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : 0.)) * npts(g));
+    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE == 2 ? 24. : 0.))) * npts(g));
     if (MODE == 1) h->norm_partials = nx * ny;
     CK(cudaGetLastError());
     return MGB_OK;
@@ -263,12 +266,20 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
 // `ext` > 0: also produce `ext` rows of the halo on each interior side (the input must be valid ext + 2*sweeps deep)
 // `ucorr` != nullptr: fused correction + residual norm (kernel MODE 1; owned rows only, ext must be 0)
 int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out, int ext = 0,
-                     double *ucorr = nullptr)
+                     double *ucorr = nullptr, double *resid = nullptr)
 {
     const View v = extended(h->lv[level], ext);
     const LevelGeom &g = v.g;
     in += v.off; rhs += v.off; out += v.off;
     const bool ex = !h->cfg.rb_fast_arith;
+    if (resid) {          // kernel MODE 2: also writes the residual of the smoothed iterate (owned rows; ext must be 0)
+        switch (sweeps) {
+        case 1: return ex ? launch_rb_stream_t<2, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<2, false, 2>(h, g, in, rhs, out, resid);
+        case 2: return ex ? launch_rb_stream_t<4, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<4, false, 2>(h, g, in, rhs, out, resid);
+        case 5: return ex ? launch_rb_stream_t<10, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<10, false, 2>(h, g, in, rhs, out, resid);
+        default: return fail(MGB_ERR_ARG, "unsupported sweep group");
+        }
+    }
     if (ucorr) {
         switch (sweeps) {
         case 1: return ex ? launch_rb_stream_t<2, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<2, false, 1>(h, g, in, rhs, out, ucorr);
@@ -287,10 +298,11 @@ int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const 
 
 // Smoothing.  `rhs` must carry valid halo rows to the depth the chosen kernel reads
 // (fused red-black: 2 rows per sweep of the group; everything else: none -- only `sol` is read across rows).
-int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs, double *ucorr = nullptr)
+int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs, double *ucorr = nullptr,
+              double *resid = nullptr)
 {
     Level &L = h->lv[level];
-    if (sol == &L.u) h->u_halo_valid = 0;
+    if (sol == &L.u) { h->u_halo_valid = 0; h->r0_ready = false; }
     const LevelGeom &g = L.g;
     if (kind == MGB_SMOOTH_BICGSTAB) kind = MGB_SMOOTH_JACOBI;      // main.cpp:103-106
     dim3 grid = march_grid(g);
@@ -307,8 +319,9 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
             const int left = sweeps - s;
             const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
             double *uc = (left == grp) ? ucorr : nullptr;           // the last group applies the fused correction
-            if ((rc = halo_exchange(h, level, *sol, 2 * grp + (uc ? 1 : 0)))) return rc;
-            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, 0, uc))) return rc;
+            double *rs = (left == grp) ? resid : nullptr;           // ... or also writes the residual of its output
+            if ((rc = halo_exchange(h, level, *sol, 2 * grp + ((uc || rs) ? 1 : 0)))) return rc;
+            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, 0, uc, rs))) return rc;
             std::swap(*sol, scratch);
             s += grp - 1;
         } else if (kind == MGB_SMOOTH_GS_RB) {
@@ -475,6 +488,12 @@ struct Depths {
     std::vector<int> din, dout, ext_r;     // per level: input halo the post-smoother reads, halo rows it must
 };                                         // produce for the prolongation above it, halo rows of r made by restriction
 
+// the fine residual of multigrid.hpp:127 rides on the last pre-sweep launch of the driver
+bool fuse_resid(mgb_gmg *h)
+{
+    return h->cfg.fuse_residual && h->cfg.pre_smoother == MGB_SMOOTH_GS_RB && h->cfg.rb_fused && h->cfg.n_pre > 0;
+}
+
 // the correction u += e and the new iterate's residual norm ride on the last fine post-smoothing launch
 bool fuse_corr(mgb_gmg *h)
 {
@@ -511,14 +530,15 @@ bool ca_applicable(mgb_gmg *h)
 
 // fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
 int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out,
-              double *ucorr = nullptr)
+              double *ucorr = nullptr, double *resid = nullptr)
 {
     int left = sweeps, rc;
-    const int x = ucorr ? 1 : 0;            // the fused correction reads one more final row on each side
+    const int x = (ucorr || resid) ? 1 : 0;     // the fused tail reads one more final row on each side
     while (left > 0) {
         const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
         left -= grp;
-        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, left ? ext_out + x + 2 * left : ext_out, left ? nullptr : ucorr))) return rc;
+        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, left ? ext_out + x + 2 * left : ext_out,
+                                   left ? nullptr : ucorr, left ? nullptr : resid))) return rc;
         std::swap(*sol, scratch);
     }
     return MGB_OK;
@@ -536,9 +556,13 @@ int one_iteration_ca(mgb_gmg *h)
     const int ext_u = 2 * h->cfg.n_pre + 1;
     if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
     h->u_halo_valid = 0;
-    if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 1))) return rc;
+    if (fuse_resid(h)) {
+        if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 0, nullptr, F.r))) return rc;
+    } else {
+        if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 1))) return rc;
+    }
     // (2) fine residual on the owned rows, then ONE deep exchange of it
-    {
+    if (!fuse_resid(h)) {
         dim3 grid = march_grid(F.g);
         mgb::k_residual<true><<<grid, mgb::kTPB, 0, h->st>>>(F.g, F.u, F.f, F.r, h->d_partial);
         count(h, 24. * npts(F.g));
@@ -659,7 +683,8 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     int rc;
     h->norm_partials = 0;
     // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
-    if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
+    if (h->r0_ready) h->r0_ready = false;
+    else if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
     if ((rc = do_restrict(h))) return rc;
     if (h->lt >= 0) {
         // restriction below lt, coarse solve and the upward leg up to level lt: one persistent CTA
@@ -728,7 +753,10 @@ int one_iteration(mgb_gmg *h)
     if (ca_applicable(h)) return one_iteration_ca(h);
     Level &F = h->lv[0];
     int rc;
-    if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
+    if (fuse_resid(h)) {
+        if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f, nullptr, F.r))) return rc;
+        h->r0_ready = true;
+    } else if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
     if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
     if (h->norm_partials > 0) {          // the fused last launch already left the new iterate's residual partial sums
         const int np = h->norm_partials;
@@ -830,7 +858,8 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
     c->tail_max_width = 129; c->use_graph = 1;
-    c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0;
+    c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0; c->fuse_residual = 0;
+    c->tail_max_width = 65;
 }
 
 void mgb_gmg_config_fast(mgb_gmg_config *c)
@@ -841,6 +870,7 @@ void mgb_gmg_config_fast(mgb_gmg_config *c)
     c->restriction = MGB_RESTRICT_FULL_WEIGHTING;
     c->rb_fast_arith = 1;
     c->fuse_correction = 1;
+    c->fuse_residual = 1;
 }
 
 int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows)

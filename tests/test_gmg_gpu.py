@@ -229,13 +229,31 @@ def test_fused_correction_and_norm_equal_separate_passes(N, L, fast):
     out = []
     for fuse in (0, 1):
         for graph in (0, 1):
-            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_correction=fuse, use_graph=graph)) as g:
+            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_correction=fuse, fuse_residual=0, use_graph=graph)) as g:
                 g.set_rhs_test(1); g.set_u(None)
                 rel = [g.run_cycles(1), g.run_cycles(4), g.run_cycles(3)]
                 out.append((g.get_u(), rel))
     for u, rel in out[1:]:
         assert np.array_equal(u, out[0][0])
         assert np.allclose(rel, out[0][1], rtol=1e-6, atol=1e-14)
+
+
+@pytest.mark.parametrize("N,L", [(257, 8), (1025, 10), (513, 2)])
+def test_fused_residual_in_pre_sweeps_equals_separate_pass(N, L):
+    """exact arithmetic: the residual written by the last pre-sweep launch is the one the separate pass computes,
+    bit for bit, so whole iterations agree bit for bit; fast arithmetic: agreement to rounding"""
+    res = {}
+    for fast in (0, 1):
+        for fuse in (0, 1):
+            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_residual=fuse, fuse_correction=0)) as g:
+                g.set_rhs_test(1); g.set_u(None)
+                rel = g.run_cycles(3)
+                res[(fast, fuse)] = (g.get_u(), rel, g.get_level(0, G.VEC_R))
+    assert np.array_equal(res[(0, 0)][0], res[(0, 1)][0]) and np.array_equal(res[(0, 0)][2], res[(0, 1)][2])
+    assert res[(0, 0)][1] == res[(0, 1)][1]
+    scale = np.abs(res[(1, 0)][0]).max()
+    assert np.abs(res[(1, 0)][0] - res[(1, 1)][0]).max() <= 1e-12 * scale
+    assert abs(res[(1, 0)][1] - res[(1, 1)][1]) <= 1e-6 * res[(1, 0)][1]
 
 
 def test_device_sampled_rhs_close_to_host(orc):
