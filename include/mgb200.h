@@ -82,7 +82,10 @@ typedef struct mgb_gmg_config {
                              The norm then carries the rounding of res - A err instead of f - A u (same value to ~1e-13 ||f||). */
     int fuse_residual;    /* red-black fused path only: the last driver pre-sweep launch also writes res = f - A u
                              (multigrid.hpp:127) for the rows it produces (no separate residual pass) */
-    int reserved[4];
+    int fuse_prolong;     /* red-black fused path only: the first post-smoothing launch of a level interpolates its input
+                             from the coarser level on the fly (multigrid.cpp:3-27, same arithmetic); the prolonged field
+                             is never written to HBM */
+    int reserved[3];
 } mgb_gmg_config;
 
 typedef struct mgb_gmg *mgb_gmg_t;

@@ -20,7 +20,7 @@ class GmgConfigStruct(C.Structure):
                 ("coarse_tol", C.c_double), ("coarse_maxit", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
                 ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("rb_fast_arith", C.c_int),
-                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("reserved", C.c_int * 4)]
+                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class GmgStatsStruct(C.Structure):

@@ -508,10 +508,13 @@ __device__ __forceinline__ void rb_stream_step(
 // It needs the final values of one more row on each side, so the stream starts/ends one row further out.
 // MODE 2 (the driver's pre-sweeps): uout = the smoothed u AND ucorr(:= the residual array) = rhs - A uout on the
 //   output rows, i.e. the fine residual of multigrid.hpp:127 without a separate pass that re-reads u and f.
-template <int S, bool EXACT, int MODE>
+// PIN (prolongation fused into the input): uin is the COARSER level's solution (geometry gc) and the rows that
+//   arrive are its bilinear interpolation, evaluated in the two-stage order of multigrid.cpp:3-27 (bit-identical
+//   to k_prolong); the prolonged field is never written to HBM.
+template <int S, bool EXACT, int MODE, bool PIN>
 __global__ void __launch_bounds__(kStreamNT)
 k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
-            double *__restrict__ uout, int rows_per_chunk, double *ucorr, double *__restrict__ partial)
+            double *__restrict__ uout, int rows_per_chunk, double *ucorr, double *__restrict__ partial, LevelGeom gc)
 {
     constexpr int TW = kStreamTW, PF = kStreamPF, H = TW / 2;
     constexpr int WR = 2 * S + 3;
@@ -554,13 +557,26 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     double2 uw[2 * S + 3];
 #pragma unroll
     for (int d = 0; d < 2 * S + 3; ++d) uw[d] = make_double2(0., 0.);
-    double2 pu[PF], pb[PF];
+    double2 pu[PF], pb[PF], ps[PF];                  // ps: second coarse row of an odd fine row (PIN only)
+    // PIN: the two coarse columns this thread's fine pair interpolates from
+    const int Jc = min(max(j0 >> 1, 0), gc.w - 1), Jc1 = min(Jc + 1, gc.w - 1);
+    const ptrdiff_t Pc = gc.pitch;
+    auto fetch = [&](int r, double2 &cu, double2 &cs, double2 &cb) {
+        cb = ld2(b + (ptrdiff_t)r * P + jl);
+        if (!PIN) { cu = ld2(uin + (ptrdiff_t)r * P + jl); return; }
+        const int gi = g.row0 + r;
+        const double *cn = uin + (ptrdiff_t)((gi >> 1) - gc.row0) * Pc;
+        cu = make_double2(cn[Jc], cn[Jc1]);
+        if (gi & 1) cs = make_double2(cn[Pc + Jc], cn[Pc + Jc1]);
+    };
+    // the fine pair (columns j0, j0+1) of global row gi from the coarse values (multigrid.cpp:3-27)
+    auto interpolate = [&](int gi, double2 cu, double2 cs) -> double2 {
+        double a = cu.x, c2 = cu.y;
+        if (gi & 1) { a = __dmul_rn(0.5, __dadd_rn(cu.x, cs.x)); c2 = __dmul_rn(0.5, __dadd_rn(cu.y, cs.y)); }
+        return make_double2(a, __dmul_rn(0.5, __dadd_rn(a, c2)));
+    };
 #pragma unroll
-    for (int p = 0; p < PF; ++p) {
-        int r = min(ifirst + p, ilast);
-        pu[p] = ld2(uin + (ptrdiff_t)r * P + jl);
-        pb[p] = ld2(b + (ptrdiff_t)r * P + jl);
-    }
+    for (int p = 0; p < PF; ++p) fetch(min(ifirst + p, ilast), pu[p], ps[p], pb[p]);
     const int ksteps = (i1 - 1 + 2 * S + X) - ifirst + 1;
     int ro[S + 1];                                   // ring offsets of rows i-2s (s = 0: arriving row)
 #pragma unroll
@@ -578,12 +594,8 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
 #define MGB_STREAM_STEP(p)                                                                                  \
     {                                                                                                       \
         const int i = ifirst + k0 + (p);             /* row arriving at this step */                         \
-        const double2 nu = pu[p], nb = pb[p];                                                               \
-        {                                                                                                   \
-            int r = min(i + PF, ilast);                                                                     \
-            pu[p] = ld2(uin + (ptrdiff_t)r * P + jl);                                                       \
-            pb[p] = ld2(b + (ptrdiff_t)r * P + jl);                                                         \
-        }                                                                                                   \
+        const double2 nu = PIN ? interpolate(g.row0 + min(i, ilast), pu[p], ps[p]) : pu[p], nb = pb[p];     \
+        fetch(min(i + PF, ilast), pu[p], ps[p], pb[p]);                                                     \
         const bool steady = (i >= i_lo) && (i <= i_hi);                                                     \
         if (steady)                                                                                         \
             rb_stream_step<S, EXACT, ((p) & 1), false, BATCH>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst, \

@@ -201,40 +201,48 @@ int read_scalar(mgb_gmg *h, int slot, double *out)
 }
 
 // resident CTAs per SM of one instantiation of the streaming kernel (also raises its dynamic-smem limit)
-template <int S, bool EXACT, int MODE>
+template <int S, bool EXACT, int MODE, bool PIN>
 int stream_occupancy(int *out)
 {
     static int occ = 0;
     constexpr int smem = mgb::stream_smem_bytes<S>();
     if (!occ) {
-        CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT, MODE>, mgb::kStreamNT, smem));
+        CK(cudaFuncSetAttribute(mgb::k_rb_stream<S, EXACT, MODE, PIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgb::k_rb_stream<S, EXACT, MODE, PIN>, mgb::kStreamNT, smem));
         occ = std::max(1, occ);
     }
     *out = occ;
     return MGB_OK;
 }
 
-int prepare_kernels()
+template <int S>
+int prepare_stream()
 {
     int o, rc;
-    if ((rc = stream_occupancy<2, true, 0>(&o)) || (rc = stream_occupancy<2, false, 0>(&o)) || (rc = stream_occupancy<4, true, 0>(&o)) ||
-        (rc = stream_occupancy<4, false, 0>(&o)) || (rc = stream_occupancy<10, true, 0>(&o)) || (rc = stream_occupancy<10, false, 0>(&o)) ||
-        (rc = stream_occupancy<2, true, 1>(&o)) || (rc = stream_occupancy<2, false, 1>(&o)) || (rc = stream_occupancy<4, true, 1>(&o)) ||
-        (rc = stream_occupancy<4, false, 1>(&o)) || (rc = stream_occupancy<10, true, 1>(&o)) || (rc = stream_occupancy<10, false, 1>(&o)) ||
-        (rc = stream_occupancy<2, true, 2>(&o)) || (rc = stream_occupancy<2, false, 2>(&o)) || (rc = stream_occupancy<4, true, 2>(&o)) ||
-        (rc = stream_occupancy<4, false, 2>(&o)) || (rc = stream_occupancy<10, true, 2>(&o)) || (rc = stream_occupancy<10, false, 2>(&o)))
+    if ((rc = stream_occupancy<S, true, 0, false>(&o)) || (rc = stream_occupancy<S, false, 0, false>(&o)) ||
+        (rc = stream_occupancy<S, true, 1, false>(&o)) || (rc = stream_occupancy<S, false, 1, false>(&o)) ||
+        (rc = stream_occupancy<S, true, 2, false>(&o)) || (rc = stream_occupancy<S, false, 2, false>(&o)) ||
+        (rc = stream_occupancy<S, true, 0, true>(&o)) || (rc = stream_occupancy<S, false, 0, true>(&o)) ||
+        (rc = stream_occupancy<S, true, 1, true>(&o)) || (rc = stream_occupancy<S, false, 1, true>(&o)))
         return rc;
+    return MGB_OK;
+}
+
+int prepare_kernels()
+{
+    int rc;
+    if ((rc = prepare_stream<2>()) || (rc = prepare_stream<4>()) || (rc = prepare_stream<10>())) return rc;
     CK(cudaFuncSetAttribute(mgb::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::kTailSmemBytes));
     return MGB_OK;
 }
 
-template <int S, bool EXACT, int MODE>
-int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr)
+template <int S, bool EXACT, int MODE, bool PIN>
+int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr,
+                       const LevelGeom &gc)
 {
     int occ = 1;
     constexpr int smem = mgb::stream_smem_bytes<S>();
-    if (int rc = stream_occupancy<S, EXACT, MODE>(&occ)) return rc;
+    if (int rc = stream_occupancy<S, EXACT, MODE, PIN>(&occ)) return rc;
     const int OW = mgb::kStreamTW - 2 * (S + 2 * (MODE != 0));    // owned columns per CTA (kernel: HC)
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
@@ -254,44 +262,46 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
         }
     }
     if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
-    mgb::k_rb_stream<S, EXACT, MODE><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, h->d_partial);
+    mgb::k_rb_stream<S, EXACT, MODE, PIN><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, h->d_partial, gc);
     // 24 B per point per sweep, S/2 sweeps per launch (+ correction 24 + norm-only residual 16 when fused)
-    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE == 2 ? 24. : 0.))) * npts(g));
+    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE == 2 ? 24. : 0.))) * npts(g) + (PIN ? 8. * (npts(g) + npts(gc)) : 0.));
     if (MODE == 1) h->norm_partials = nx * ny;
     CK(cudaGetLastError());
     return MGB_OK;
 }
 
 // `sweeps` (1, 2 or 5) full red-black sweeps in one pass: in -> out
-// `ext` > 0: also produce `ext` rows of the halo on each interior side (the input must be valid ext + 2*sweeps deep)
-// `ucorr` != nullptr: fused correction + residual norm (kernel MODE 1; owned rows only, ext must be 0)
+template <int S, bool EXACT>
+int launch_rb_stream_s(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr,
+                       double *resid, const LevelGeom *gc)
+{
+    static const LevelGeom none{};
+    if (resid) return launch_rb_stream_t<S, EXACT, 2, false>(h, g, in, rhs, out, resid, none);
+    if (ucorr) return gc ? launch_rb_stream_t<S, EXACT, 1, true>(h, g, in, rhs, out, ucorr, *gc)
+                         : launch_rb_stream_t<S, EXACT, 1, false>(h, g, in, rhs, out, ucorr, none);
+    return gc ? launch_rb_stream_t<S, EXACT, 0, true>(h, g, in, rhs, out, nullptr, *gc)
+              : launch_rb_stream_t<S, EXACT, 0, false>(h, g, in, rhs, out, nullptr, none);
+}
+
+// `sweeps` (1, 2 or 5) full red-black sweeps in one pass: in -> out.
+// `ext` > 0: also produce `ext` rows of the halo on each interior side (the input must be valid ext + 2*sweeps deep).
+// `ucorr`: fused correction + residual norm (kernel MODE 1).  `resid`: also write the residual of the output (MODE 2).
+// `coarse`: `in` is the coarser level's solution and is interpolated on the fly (PIN); it is NOT offset by the view.
 int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const double *rhs, double *out, int ext = 0,
-                     double *ucorr = nullptr, double *resid = nullptr)
+                     double *ucorr = nullptr, double *resid = nullptr, const Level *coarse = nullptr)
 {
     const View v = extended(h->lv[level], ext);
     const LevelGeom &g = v.g;
-    in += v.off; rhs += v.off; out += v.off;
+    if (!coarse) in += v.off;
+    rhs += v.off; out += v.off;
+    if (ucorr) ucorr += v.off;
+    if (resid) resid += v.off;
+    const LevelGeom *gc = coarse ? &coarse->g : nullptr;
     const bool ex = !h->cfg.rb_fast_arith;
-    if (resid) {          // kernel MODE 2: also writes the residual of the smoothed iterate (owned rows; ext must be 0)
-        switch (sweeps) {
-        case 1: return ex ? launch_rb_stream_t<2, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<2, false, 2>(h, g, in, rhs, out, resid);
-        case 2: return ex ? launch_rb_stream_t<4, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<4, false, 2>(h, g, in, rhs, out, resid);
-        case 5: return ex ? launch_rb_stream_t<10, true, 2>(h, g, in, rhs, out, resid) : launch_rb_stream_t<10, false, 2>(h, g, in, rhs, out, resid);
-        default: return fail(MGB_ERR_ARG, "unsupported sweep group");
-        }
-    }
-    if (ucorr) {
-        switch (sweeps) {
-        case 1: return ex ? launch_rb_stream_t<2, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<2, false, 1>(h, g, in, rhs, out, ucorr);
-        case 2: return ex ? launch_rb_stream_t<4, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<4, false, 1>(h, g, in, rhs, out, ucorr);
-        case 5: return ex ? launch_rb_stream_t<10, true, 1>(h, g, in, rhs, out, ucorr) : launch_rb_stream_t<10, false, 1>(h, g, in, rhs, out, ucorr);
-        default: return fail(MGB_ERR_ARG, "unsupported sweep group");
-        }
-    }
     switch (sweeps) {
-    case 1: return ex ? launch_rb_stream_t<2, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<2, false, 0>(h, g, in, rhs, out, nullptr);
-    case 2: return ex ? launch_rb_stream_t<4, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<4, false, 0>(h, g, in, rhs, out, nullptr);
-    case 5: return ex ? launch_rb_stream_t<10, true, 0>(h, g, in, rhs, out, nullptr) : launch_rb_stream_t<10, false, 0>(h, g, in, rhs, out, nullptr);
+    case 1: return ex ? launch_rb_stream_s<2, true>(h, g, in, rhs, out, ucorr, resid, gc) : launch_rb_stream_s<2, false>(h, g, in, rhs, out, ucorr, resid, gc);
+    case 2: return ex ? launch_rb_stream_s<4, true>(h, g, in, rhs, out, ucorr, resid, gc) : launch_rb_stream_s<4, false>(h, g, in, rhs, out, ucorr, resid, gc);
+    case 5: return ex ? launch_rb_stream_s<10, true>(h, g, in, rhs, out, ucorr, resid, gc) : launch_rb_stream_s<10, false>(h, g, in, rhs, out, ucorr, resid, gc);
     default: return fail(MGB_ERR_ARG, "unsupported sweep group");
     }
 }
@@ -299,7 +309,7 @@ int launch_rb_stream(mgb_gmg *h, int level, int sweeps, const double *in, const 
 // Smoothing.  `rhs` must carry valid halo rows to the depth the chosen kernel reads
 // (fused red-black: 2 rows per sweep of the group; everything else: none -- only `sol` is read across rows).
 int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const double *rhs, double *ucorr = nullptr,
-              double *resid = nullptr)
+              double *resid = nullptr, Level *coarse = nullptr)
 {
     Level &L = h->lv[level];
     if (sol == &L.u) { h->u_halo_valid = 0; h->r0_ready = false; }
@@ -320,8 +330,14 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
             const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
             double *uc = (left == grp) ? ucorr : nullptr;           // the last group applies the fused correction
             double *rs = (left == grp) ? resid : nullptr;           // ... or also writes the residual of its output
-            if ((rc = halo_exchange(h, level, *sol, 2 * grp + ((uc || rs) ? 1 : 0)))) return rc;
-            if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, 0, uc, rs))) return rc;
+            const int need = 2 * grp + ((uc || rs) ? 1 : 0);
+            if (coarse && s == 0) {                                 // the first group interpolates its input from the coarser level
+                if ((rc = halo_exchange(h, level + 1, coarse->e, (need + 1) / 2 + 1))) return rc;
+                if ((rc = launch_rb_stream(h, level, grp, coarse->e, rhs, scratch, 0, uc, rs, coarse))) return rc;
+            } else {
+                if ((rc = halo_exchange(h, level, *sol, need))) return rc;
+                if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, 0, uc, rs))) return rc;
+            }
             std::swap(*sol, scratch);
             s += grp - 1;
         } else if (kind == MGB_SMOOTH_GS_RB) {
@@ -488,6 +504,12 @@ struct Depths {
     std::vector<int> din, dout, ext_r;     // per level: input halo the post-smoother reads, halo rows it must
 };                                         // produce for the prolongation above it, halo rows of r made by restriction
 
+// the prolongation (multigrid.cpp:3-27) is evaluated inside the first post-smoothing launch of the finer level
+bool fuse_prolong(mgb_gmg *h)
+{
+    return h->cfg.fuse_prolong && h->cfg.smoother == MGB_SMOOTH_GS_RB && h->cfg.rb_fused && h->cfg.nu > 0;
+}
+
 // the fine residual of multigrid.hpp:127 rides on the last pre-sweep launch of the driver
 bool fuse_resid(mgb_gmg *h)
 {
@@ -530,15 +552,18 @@ bool ca_applicable(mgb_gmg *h)
 
 // fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
 int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out,
-              double *ucorr = nullptr, double *resid = nullptr)
+              double *ucorr = nullptr, double *resid = nullptr, Level *coarse = nullptr)
 {
     int left = sweeps, rc;
     const int x = (ucorr || resid) ? 1 : 0;     // the fused tail reads one more final row on each side
+    bool first = true;
     while (left > 0) {
         const int grp = left >= 5 ? 5 : (left >= 2 ? 2 : 1);
         left -= grp;
-        if ((rc = launch_rb_stream(h, level, grp, *sol, rhs, scratch, left ? ext_out + x + 2 * left : ext_out,
-                                   left ? nullptr : ucorr, left ? nullptr : resid))) return rc;
+        const double *in = (first && coarse) ? coarse->e : *sol;
+        if ((rc = launch_rb_stream(h, level, grp, in, rhs, scratch, left ? ext_out + x + 2 * left : ext_out,
+                                   left ? nullptr : ucorr, left ? nullptr : resid, first ? coarse : nullptr))) return rc;
+        first = false;
         std::swap(*sol, scratch);
     }
     return MGB_OK;
@@ -639,18 +664,26 @@ int one_iteration_ca(mgb_gmg *h)
     }
     if ((rc = launch_tail(h))) return rc;
     for (int j = h->lt; j > ls + 1; --j) {
+        if (fuse_prolong(h)) {
+            if ((rc = do_smooth(h, j - 1, MGB_SMOOTH_GS_RB, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, nullptr, nullptr, &h->lv[j]))) return rc;
+            continue;
+        }
         if ((rc = do_prolong(h, j))) return rc;
         if ((rc = do_smooth(h, j - 1, MGB_SMOOTH_GS_RB, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
     }
     // (5) upward through the sharded levels without any exchange
     for (int j = ls + 1; j > 0; --j) {
         Level &C = h->lv[j], &Fl = h->lv[j - 1];
+        double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+        if (fuse_prolong(h)) {
+            if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc, nullptr, &C))) return rc;
+            continue;
+        }
         const View vf = extended(Fl, d.din[j - 1]);
         dim3 grid((vf.g.w + 2 * mgb::kTPB - 1) / (2 * mgb::kTPB), (vf.g.rows + 3) / 4);
         mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, vf.g, C.e, Fl.e + vf.off);
         count(h, 8. * (npts(vf.g) + npts(C.g)));
         CK(cudaGetLastError());
-        double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
         if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc))) return rc;
     }
     if (fuse_corr(h)) {
@@ -698,8 +731,12 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
             h->stats.coarse_iters_total += (uint64_t)its;
         }
         for (int j = h->lt; j > 0; --j) {
-            if ((rc = do_prolong(h, j))) return rc;
             double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+            if (fuse_prolong(h)) {
+                if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc, nullptr, &h->lv[j]))) return rc;
+                continue;
+            }
+            if ((rc = do_prolong(h, j))) return rc;
             if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
         }
         if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
@@ -725,8 +762,12 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     h->stats.coarse_iters_total += its;
     // :134-139
     for (int j = L - 1; j > 0; --j) {
-        if ((rc = do_prolong(h, j))) return rc;
         double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+        if (fuse_prolong(h)) {
+            if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc, nullptr, &h->lv[j]))) return rc;
+            continue;
+        }
+        if ((rc = do_prolong(h, j))) return rc;
         if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
     }
     if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
@@ -858,7 +899,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->restriction = MGB_RESTRICT_INJECTION;
     c->device = 0; c->rank = 0; c->n_ranks = 1;
     c->tail_max_width = 129; c->use_graph = 1;
-    c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0; c->fuse_residual = 0;
+    c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0; c->fuse_residual = 0; c->fuse_prolong = 0;
     c->tail_max_width = 65;
 }
 
@@ -871,6 +912,7 @@ void mgb_gmg_config_fast(mgb_gmg_config *c)
     c->rb_fast_arith = 1;
     c->fuse_correction = 1;
     c->fuse_residual = 1;
+    c->fuse_prolong = 1;
 }
 
 int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows)

@@ -39,6 +39,7 @@ class GmgConfig:
     rb_fused: int = 1
     fuse_correction: int = 0
     fuse_residual: int = 0
+    fuse_prolong: int = 0
 
     @staticmethod
     def fast(n, levels, **kw):
@@ -49,6 +50,7 @@ class GmgConfig:
         kw.setdefault("rb_fast_arith", 1)
         kw.setdefault("fuse_correction", 1)
         kw.setdefault("fuse_residual", 1)
+        kw.setdefault("fuse_prolong", 1)
         return GmgConfig(n=n, levels=levels, **kw)
 
 
@@ -74,7 +76,7 @@ class Gmg:
         self.lib.mgb_gmg_config_default(C.byref(c))
         for k in ("n", "levels", "length", "alpha", "smoother", "pre_smoother", "n_pre", "nu",
                   "restriction", "coarse_tol", "coarse_maxit", "device", "rank", "n_ranks",
-                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual"):
+                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong"):
             setattr(c, k, getattr(cfg, k))
         if cfg.nccl_id:
             C.memmove(c.nccl_id, cfg.nccl_id, min(128, len(cfg.nccl_id)))

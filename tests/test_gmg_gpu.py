@@ -256,6 +256,23 @@ def test_fused_residual_in_pre_sweeps_equals_separate_pass(N, L):
     assert abs(res[(1, 0)][1] - res[(1, 1)][1]) <= 1e-6 * res[(1, 0)][1]
 
 
+@pytest.mark.parametrize("N,L", [(257, 8), (1025, 10), (2049, 4), (129, 3)])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_fused_prolongation_equals_separate_kernel(N, L, fast):
+    """the first post-smoothing launch of a level interpolates its input from the coarser level on the fly: the
+    interpolation arithmetic is that of k_prolong, so whole iterations agree bit for bit (both arithmetic modes)"""
+    out = []
+    for fuse in (0, 1):
+        for corr in (0, 1):
+            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_prolong=fuse, fuse_correction=corr)) as g:
+                g.set_rhs_test(1); g.set_u(None)
+                rel = g.run_cycles(3)
+                out.append((g.get_u(), rel))
+    for u, rel in out[1:]:
+        assert np.array_equal(u, out[0][0])
+        assert abs(rel - out[0][1]) <= 1e-9 * out[0][1]
+
+
 def test_device_sampled_rhs_close_to_host(orc):
     N = 129
     with Gmg(GmgConfig(n=N, levels=3)) as g:
