@@ -150,6 +150,10 @@ int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double 
  * residual.  This is the timed region of bench.py. */
 int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres);
 
+/* the fine-level part of the upward leg (multigrid.hpp:134-144 for j = 1): E(1) -> E(0) prolongation, nu sweeps on
+ * level 0 against R(0), u += err, and sum (f - A u)^2 of the new u.  One fused launch on the fast path. */
+int mgb_gmg_fine_leg(mgb_gmg_t h, double *sumsq);
+
 /* measurement hooks */
 typedef struct mgb_gmg_stats {
     uint64_t kernel_launches;      /* kernels launched by this handle since create/reset */

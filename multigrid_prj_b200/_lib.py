@@ -60,6 +60,7 @@ SYMBOLS = {
     "mgb_gmg_prolong": (_i, [_vp, _i]),
     "mgb_gmg_set_cycle": (_i, [_vp, _i, _i, _i, _d, _i]),
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
+    "mgb_gmg_fine_leg": (_i, [_vp, _pd]),
     "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),
     "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),
     "mgb_gmg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),

@@ -169,6 +169,11 @@ class Gmg:
         check(self.lib.mgb_gmg_cycle(self.h, C.byref(rel), C.byref(its)))
         return rel.value, its.value
 
+    def fine_leg(self, want_norm=False):
+        ss = C.c_double()
+        check(self.lib.mgb_gmg_fine_leg(self.h, C.byref(ss) if want_norm else None))
+        return ss.value
+
     def solve(self, tol=1e-11, maxiter=1000, check_every=1):
         hist = np.zeros(maxiter + 1)
         n = C.c_int()
