@@ -245,8 +245,8 @@ def main():
         run_k = lambda: g.fine_leg()
         kname = (f"k_rb_stream<{2 * cfg.nu}, EXACT=0, MODE=1, PIN=1>: prolongation + {cfg.nu} red-black sweeps + correction + "
                  f"residual norm in one launch ({cfg.nu} x 24 + 10 + 24 + 16 B/pt algorithmic)")
-        moved = 34.0 * n * rows0                      # read res, u, coarse err (2 B/pt); write u
-        traffic, traffic_src = 2.278e9, "profiles/r01_ncu_fine_leg_full.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch at 8193^2)"
+        moved = 26.0 * n * rows0                      # read res 8, u 8, coarse err 2; write u 8
+        traffic, traffic_src = 1.725148e9, "profiles/r01_ncu_fine_leg_full.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch at 8193^2)"
         if n != 8193:
             traffic, traffic_src = None, None
     else:
