@@ -225,6 +225,11 @@ int mgb_amg_residual(mgb_amg_t h, int level, double *norm);
 /* replaces the body of AMG::apply_AMG() after initialization (src/AMG.cpp:282-304) */
 int mgb_amg_apply(mgb_amg_t h, double *residual_norm);
 
+/* NOT in the reference: a convergent correction-scheme V(nu1,nu2) cycle on the same
+ * hierarchy -- the reference's pass restricts the solution and is not an iteration.  hist[0] = ||b - A x||_2 on entry,
+ * then one entry per cycle (maxit+1 doubles); stops at hist <= tol * hist[0]. */
+int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coarse_sweeps, double *hist, int *n_hist);
+
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
 int mgb_amg_reset_stats(mgb_amg_t h);
 void *mgb_amg_stream(mgb_amg_t h);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "mgb_amg_prolong": (_i, [_vp, _i]),
     "mgb_amg_residual": (_i, [_vp, _i, _pd]),
     "mgb_amg_apply": (_i, [_vp, _pd]),
+    "mgb_amg_solve": (_i, [_vp, _d, _i, _i, _i, _i, _vp, _pi]),
     "mgb_amg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
     "mgb_amg_reset_stats": (_i, [_vp]),
     "mgb_amg_stream": (_vp, [_vp]),

@@ -101,6 +101,13 @@ class Amg:
         check(self.lib.mgb_amg_apply(self.h, C.byref(r) if want_residual else None))
         return r.value
 
+    def solve(self, tol=1e-8, maxit=50, nu1=2, nu2=2, coarse=20):
+        """correction-scheme V-cycles (not in the reference); returns the residual history"""
+        hist = np.zeros(maxit + 1)
+        n = C.c_int()
+        check(self.lib.mgb_amg_solve(self.h, tol, maxit, nu1, nu2, coarse, hist.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return hist[:n.value].copy()
+
     def sync(self):
         check(self.lib.mgb_amg_sync(self.h))
 

@@ -165,6 +165,16 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
     }
 }
 
+// slot-ordered copy of a level vector (keeps the SELL kernels' right-hand side in step with L.b)
+__global__ void __launch_bounds__(256)
+k_amg_to_slots(const int *__restrict__ row_of_slot, int n_slots, const double *__restrict__ v, double *__restrict__ v_s)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_slots) return;
+    const int i = row_of_slot[p];
+    v_s[p] = i >= 0 ? v[i] : 0.;
+}
+
 // ---- residual r = b - A x and its squared norm (AMG/src/AMG.cpp:256-275) ------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(256)

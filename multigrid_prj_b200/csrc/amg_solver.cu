@@ -684,6 +684,65 @@ int mgb_amg_apply(mgb_amg_t h, double *residual_norm)
     return MGB_OK;
 }
 
+// Convergent correction-scheme V-cycle on the same hierarchy (NOT in the reference, whose
+// one-pass scheme restricts the solution and is not an iteration): per level nu1 sweeps, r = b - A x, b_c = P^T r,
+// x_c = 0, recurse, x += P x_c, nu2 sweeps; `coarse` sweeps on the last level.  hist[0] = ||b - A x0||_2, then one
+// entry per cycle; stops when hist <= tol * hist[0] or after maxit cycles.
+int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coarse, double *hist, int *n_hist)
+{
+    if (!h || !hist || !n_hist || maxit < 0 || nu1 < 0 || nu2 < 0 || coarse < 1) return mgb_set_error(MGB_ERR_ARG, "bad argument");
+    ACK(cudaSetDevice(h->cfg.device));
+    const int L = (int)h->lv.size();
+    const int kind = h->cfg.smoother;
+    int rc, n = 0;
+    double nrm = 0.;
+    if ((rc = do_residual(h, 0, &nrm))) return rc;
+    hist[n++] = nrm;
+    const double target = tol * nrm;
+    for (int it = 0; it < maxit && nrm > target; ++it) {
+        for (int l = 0; l < L - 1; ++l) {                                  // downward
+            AmgLevel &F = h->lv[l], &C = h->lv[l + 1];
+            if (nu1 > 0 && (rc = do_smooth(h, l, kind, nu1))) return rc;
+            {   // r = b - A x into F.tmp (no host read-back)
+                const mgb::CsrDev A = F.A.view();
+                if (h->cfg.exact_order) mgb::k_amg_residual<true><<<(A.n_rows + 255) / 256, 256, 0, h->st>>>(A, F.x, F.b, F.tmp, h->d_partial);
+                else mgb::k_amg_sell<0><<<(F.sell.n_slots + 255) / 256, 256, 0, h->st>>>(F.sell.view(), F.x, F.sell.b_s, F.tmp, h->d_partial, 0, F.sell.n_slots);
+                tally(h, sweep_bytes(F));
+            }
+            const mgb::CsrDev R = F.R.view();                              // b_c = P^T r
+            if (R.n_rows) {
+                if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(R.n_rows + 255) / 256, 256, 0, h->st>>>(R, F.tmp, C.b);
+                else mgb::k_amg_spmv<false><<<(R.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, F.tmp, C.b);
+                tally(h, 12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols);
+                if (C.sell.n_slots) {
+                    mgb::k_amg_to_slots<<<(C.sell.n_slots + 255) / 256, 256, 0, h->st>>>(C.sell.row_of_slot, C.sell.n_slots, C.b, C.sell.b_s);
+                    tally(h, 16. * C.A.n_rows);
+                }
+                ACK(cudaMemsetAsync(C.x, 0, sizeof(double) * (size_t)C.A.n_rows, h->st));
+            }
+            ACK(cudaGetLastError());
+        }
+        if ((rc = do_smooth(h, L - 1, kind, coarse))) return rc;
+        for (int l = L - 2; l >= 0; --l) {                                  // upward
+            if ((rc = do_prolong(h, l))) return rc;
+            if (nu2 > 0 && (rc = do_smooth(h, l, kind, nu2))) return rc;
+        }
+        h->stats.cycles++;
+        if ((rc = do_residual(h, 0, &nrm))) return rc;
+        hist[n++] = nrm;
+    }
+    *n_hist = n;
+    // the coarse right-hand sides were overwritten by restricted residuals: put the reference's P^T b back
+    for (int l = 1; l < L; ++l) {
+        AmgLevel &C = h->lv[l];
+        if (!C.A.n_rows) continue;
+        ACK(cudaMemcpyAsync(C.b, C.h_rhs.data(), sizeof(double) * (size_t)C.A.n_rows, cudaMemcpyHostToDevice, h->st));
+        if (C.sell.n_slots) mgb::k_amg_to_slots<<<(C.sell.n_slots + 255) / 256, 256, 0, h->st>>>(C.sell.row_of_slot, C.sell.n_slots, C.b, C.sell.b_s);
+    }
+    ACK(cudaStreamSynchronize(h->st));
+    return MGB_OK;
+}
+
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s)
 {
     if (!h || !s) return mgb_set_error(MGB_ERR_ARG, "null argument");

@@ -131,6 +131,26 @@ def test_fast_path_pass_on_mesh1():
     assert abs(res - c["res"]) < 0.5 * c["res"]
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_correction_scheme_cycle_converges(fast):
+    """beyond the reference (its one-pass scheme is not an iteration): V(2,2) correction-scheme cycles on the same
+    hierarchy converge to the solution of A x = b; checked against a sparse direct solve"""
+    import scipy.sparse.linalg as spla
+    c = load_case("mesh1")
+    A, b = c["A"][0], c["rhs"][0]
+    with Amg(A.ptr, A.col, A.val, b, levels=5, fast=fast) as a:
+        hist = a.solve(tol=1e-10, maxit=60)
+        x = a.vector(0, 0)
+        rhs1 = a.vector(1, 1)
+    assert hist[-1] <= 1e-10 * hist[0] and hist.size <= 61, hist
+    assert np.all(hist[1:] < hist[:-1])
+    xs = spla.spsolve(A.to_scipy().tocsc(), b)
+    assert np.linalg.norm(x - xs) <= 1e-8 * np.linalg.norm(xs)
+    assert np.array_equal(rhs1, c["rhs"][1])        # the reference's coarse right-hand sides are restored
+    print(f"mesh1 correction-scheme V(2,2), {'multicolour' if fast else 'lexicographic'} GS: {hist.size - 1} cycles, "
+          f"mean reduction {(hist[-1] / hist[0]) ** (1 / (hist.size - 1)):.3f} per cycle")
+
+
 def test_amg_argument_errors():
     from multigrid_prj_b200 import MgbError
     c = load_case("mesh2")
