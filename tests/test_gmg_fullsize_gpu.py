@@ -25,7 +25,8 @@ def test_fast_path_converges_to_the_analytic_solution(exact):
         hist = g.solve(tol=2e-10, maxiter=30)
         u = g.get_u()
     assert hist[-1] <= 2e-10 and hist.size <= 14, hist            # the reference's TOL=1e-11 is below the fp64 floor here
-    assert np.all(hist[1:6] < 0.2 * hist[0:5])                     # >= 5x per cycle while above the floor
+    assert np.all(hist[2:7] < 0.2 * hist[1:6])                     # >= 5x per cycle once the boundary data is in (the first
+    # iteration RAISES the residual, as in the reference: WebInterface/MGGS4.txt goes 1 -> 1.50349)
     err = np.abs(u - exact).max() / np.abs(exact).max()
     assert err < 5e-6, err                                         # O(h^2) discretisation error, h = 10/8192
     assert np.array_equal(u[0], exact[0]) or np.allclose(u[0], exact[0], rtol=1e-13)   # Dirichlet rows hold g
