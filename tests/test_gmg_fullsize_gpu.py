@@ -33,7 +33,8 @@ def test_fast_path_converges_to_the_analytic_solution(exact):
 
 
 def test_parity_mode_jacobi_cycle_reaches_the_same_solution(exact):
-    with Gmg(GmgConfig(n=N, levels=L, smoother=G.JACOBI, pre_smoother=G.GS_RB)) as g:
+    """the reference's own configuration for -smt 1: exact lexicographic GS pre-sweeps, Jacobi cycle, injection"""
+    with Gmg(GmgConfig(n=N, levels=L, smoother=G.JACOBI, pre_smoother=G.GS_LEX)) as g:
         g.set_rhs_test(1); g.set_u(None)
         rel = g.run_cycles(14)
         u = g.get_u()
