@@ -230,6 +230,20 @@ int mgb_amg_apply(mgb_amg_t h, double *residual_norm);
  * then one entry per cycle (maxit+1 doubles); stops at hist <= tol * hist[0]. */
 int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coarse_sweeps, double *hist, int *n_hist);
 
+/* The setup stages one by one, as RestrictionOperator exposes them (include/AMG.hpp:150-369) and AMG/debugtest.cpp
+ * calls them.  Host side in this round (O(nnz), the reference's semantics); matrices are opaque host-CSR handles. */
+typedef struct mgb_csr *mgb_csr_t;
+int mgb_csr_create(size_t n_rows, size_t n_cols, const int64_t *row_ptr, const int64_t *col, const double *val, mgb_csr_t *out);
+void mgb_csr_destroy(mgb_csr_t m);
+int mgb_csr_info(mgb_csr_t m, size_t *n_rows, size_t *n_cols, size_t *nnz);
+int mgb_csr_get(mgb_csr_t m, int64_t *row_ptr, int64_t *col, double *val);
+/* replaces select_strong_connections + select_coarse_nodes (AMG.hpp:132-198): coarse_mask[i] & 0xC0 != 0 <=> node i is FINE */
+int mgb_amg_select_coarse_nodes(mgb_csr_t A, double eps, int64_t start, unsigned char *coarse_mask, size_t *n_coarse);
+/* replaces build_prolongation_matrix (AMG.hpp:230-300) */
+int mgb_amg_build_prolongation(mgb_csr_t A, double eps, const unsigned char *coarse_mask, mgb_csr_t *P);
+/* replaces build_coarse_matrix (AMG.hpp:303-369) */
+int mgb_amg_build_coarse_matrix(mgb_csr_t A, mgb_csr_t P, mgb_csr_t *Ac);
+
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
 int mgb_amg_reset_stats(mgb_amg_t h);
 void *mgb_amg_stream(mgb_amg_t h);

@@ -82,6 +82,13 @@ SYMBOLS = {
     "mgb_amg_residual": (_i, [_vp, _i, _pd]),
     "mgb_amg_apply": (_i, [_vp, _pd]),
     "mgb_amg_solve": (_i, [_vp, _d, _i, _i, _i, _i, _vp, _pi]),
+    "mgb_csr_create": (_i, [C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "mgb_csr_destroy": (None, [_vp]),
+    "mgb_csr_info": (_i, [_vp] + [C.POINTER(C.c_size_t)] * 3),
+    "mgb_csr_get": (_i, [_vp, _vp, _vp, _vp]),
+    "mgb_amg_select_coarse_nodes": (_i, [_vp, _d, C.c_int64, _vp, C.POINTER(C.c_size_t)]),
+    "mgb_amg_build_prolongation": (_i, [_vp, _d, _vp, C.POINTER(_vp)]),
+    "mgb_amg_build_coarse_matrix": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "mgb_amg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
     "mgb_amg_reset_stats": (_i, [_vp]),
     "mgb_amg_stream": (_vp, [_vp]),

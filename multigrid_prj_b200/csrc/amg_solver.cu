@@ -743,6 +743,72 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
     return MGB_OK;
 }
 
+// ---- the setup stages one by one (RestrictionOperator's public methods, AMG/include/AMG.hpp:150-369) ----------------
+// The reference's second driver (AMG/debugtest.cpp) calls them directly.  They run on the host in O(nnz) (the device
+// setup is the next item of SURVEY.md section 8f); matrices cross the boundary as opaque host-CSR handles.
+struct mgb_csr { HostCsr m; };
+
+int mgb_csr_create(size_t n_rows, size_t n_cols, const int64_t *ptr, const int64_t *col, const double *val, mgb_csr_t *out)
+{
+    if (!ptr || !out || n_rows > (size_t)INT32_MAX || n_cols > (size_t)INT32_MAX || ptr[n_rows] > (int64_t)INT32_MAX)
+        return mgb_set_error(MGB_ERR_ARG, "bad CSR arguments");
+    mgb_csr *c = new mgb_csr();
+    c->m.n_rows = (int)n_rows; c->m.n_cols = (int)n_cols;
+    c->m.ptr.assign(n_rows + 1, 0);
+    for (size_t i = 0; i < n_rows; ++i) {
+        for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k)
+            if (val[k] != 0) { c->m.col.push_back((int)col[k]); c->m.val.push_back(val[k]); }     // CSRMatrix.cpp:13-14
+        c->m.ptr[i + 1] = (int)c->m.col.size();
+    }
+    *out = c;
+    return MGB_OK;
+}
+void mgb_csr_destroy(mgb_csr_t c) { delete c; }
+int mgb_csr_info(mgb_csr_t c, size_t *n_rows, size_t *n_cols, size_t *nnz)
+{
+    if (!c) return mgb_set_error(MGB_ERR_ARG, "null matrix");
+    if (n_rows) *n_rows = (size_t)c->m.n_rows;
+    if (n_cols) *n_cols = (size_t)c->m.n_cols;
+    if (nnz) *nnz = (size_t)c->m.nnz();
+    return MGB_OK;
+}
+int mgb_csr_get(mgb_csr_t c, int64_t *ptr, int64_t *col, double *val)
+{
+    if (!c || !ptr || !col || !val) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    return copy_csr(c->m, ptr, col, val);
+}
+// RestrictionOperator::select_coarse_nodes (AMG.hpp:150-198); start < 0 selects n/2 (the reference draws it at random)
+int mgb_amg_select_coarse_nodes(mgb_csr_t A, double eps, int64_t start, unsigned char *coarse_mask, size_t *n_coarse)
+{
+    if (!A || !coarse_mask || !n_coarse) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    std::vector<unsigned char> state;
+    const int nc = split_coarse_fine(A->m, eps, start >= 0 ? (long)start : A->m.n_rows / 2, state);
+    std::copy(state.begin(), state.end(), coarse_mask);
+    *n_coarse = (size_t)nc;
+    return MGB_OK;
+}
+// RestrictionOperator::build_prolongation_matrix (AMG.hpp:230-300)
+int mgb_amg_build_prolongation(mgb_csr_t A, double eps, const unsigned char *coarse_mask, mgb_csr_t *P)
+{
+    if (!A || !coarse_mask || !P) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    std::vector<unsigned char> state(coarse_mask, coarse_mask + A->m.n_rows);
+    int nc = 0;
+    for (unsigned char b : state) nc += !(b & 0xC0);
+    mgb_csr *c = new mgb_csr();
+    c->m = interpolation(A->m, eps, state, nc);
+    *P = c;
+    return MGB_OK;
+}
+// RestrictionOperator::build_coarse_matrix (AMG.hpp:303-369)
+int mgb_amg_build_coarse_matrix(mgb_csr_t A, mgb_csr_t P, mgb_csr_t *Ac)
+{
+    if (!A || !P || !Ac || P->m.n_rows != A->m.n_rows) return mgb_set_error(MGB_ERR_ARG, "bad Galerkin arguments");
+    mgb_csr *c = new mgb_csr();
+    c->m = galerkin(A->m, P->m);
+    *Ac = c;
+    return MGB_OK;
+}
+
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s)
 {
     if (!h || !s) return mgb_set_error(MGB_ERR_ARG, "null argument");

@@ -119,4 +119,107 @@ public:
     std::vector<double> get_solution() { return get_x_levels(0); }
 };
 
+// RestrictionOperator (AMG.hpp:90-452): the setup stages and the residual helpers, as AMG/debugtest.cpp uses them.
+class RestrictionOperator {
+    static void ok(int rc) { if (rc != MGB_OK) throw std::runtime_error(std::string("libmgb200: ") + mgb_last_error()); }
+    struct Handle {                        // host-CSR handle of the C ABI built from a CSRMatrix
+        mgb_csr_t h = nullptr;
+        explicit Handle(CSRMatrix &A)
+        {
+            std::vector<int64_t> ptr(A.rows() + 1, 0), col;
+            std::vector<double> val;
+            for (size_t i = 0; i < A.rows(); ++i) {
+                for (const auto &e : A.nonZerosInRow(i)) { col.push_back((int64_t)e.first); val.push_back(e.second); }
+                ptr[i + 1] = (int64_t)col.size();
+            }
+            ok(mgb_csr_create(A.rows(), A.cols(), ptr.data(), col.data(), val.data(), &h));
+        }
+        ~Handle() { mgb_csr_destroy(h); }
+    };
+    static std::unique_ptr<CSRMatrix> to_matrix(mgb_csr_t m)
+    {
+        size_t nr = 0, nc = 0, nnz = 0;
+        ok(mgb_csr_info(m, &nr, &nc, &nnz));
+        std::vector<int64_t> ptr(nr + 1), col(nnz ? nnz : 1);
+        std::vector<double> val(nnz ? nnz : 1);
+        ok(mgb_csr_get(m, ptr.data(), col.data(), val.data()));
+        Matrix tmp(nr, nc);
+        for (size_t i = 0; i < nr; ++i)
+            for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) tmp.data()[i][(size_t)col[k]] = val[k];
+        tmp.count_non_zeros();
+        auto out = std::make_unique<CSRMatrix>(tmp);
+        out->copy_from(tmp);
+        return out;
+    }
+    static long start_index()
+    {
+        const char *s = std::getenv("MGB_AMG_START");
+        return s ? std::atol(s) : -1;
+    }
+    template <bool MASKED>
+    double residual(CSRMatrix &A, const std::vector<double> &x, const std::vector<double> &rhs, std::vector<double> &res)
+    {
+        auto &L = MultiGridAMG::detail::level_of(A);
+        L.bind_rhs(rhs);
+        L.bind_x(const_cast<std::vector<double> &>(x));
+        double norm = 0.;
+        ok(mgb_amg_residual(L.h, 0, &norm));
+        std::vector<double> r(L.n);
+        ok(mgb_amg_get_vector(L.h, 0, 2, r.data()));
+        for (size_t i = 0; i < L.n; ++i) res.at(MASKED ? L.at(i) : i) = r[i];
+        L.flush();                         // the caller reads x on the host after asking for a residual
+        return norm;
+    }
+
+public:
+    size_t select_coarse_nodes(CSRMatrix &A, std::vector<unsigned char> &coarse_mask)          // AMG.hpp:150-198
+    {
+        Handle a(A);
+        size_t nc = 0;
+        coarse_mask.resize(A.rows());
+        ok(mgb_amg_select_coarse_nodes(a.h, EPSILON, start_index(), coarse_mask.data(), &nc));
+        return nc;
+    }
+    void build_component_mask(const std::vector<unsigned char> &coarse_mask, std::vector<size_t> &component_mask,
+                              const size_t &num_coarse_nodes, std::map<size_t, size_t> &reversed)     // AMG.hpp:201-224
+    {
+        component_mask.resize(num_coarse_nodes);
+        size_t k = 0;
+        for (size_t i = 0; i < coarse_mask.size(); ++i)
+            if (!(coarse_mask[i] & 0xC0)) { component_mask.at(k) = i; reversed[i] = k; ++k; }
+    }
+    void build_prolongation_matrix(CSRMatrix &A, std::unique_ptr<CSRMatrix> &P, size_t &, std::vector<unsigned char> &coarse_mask,
+                                   std::map<size_t, size_t> &)                                       // AMG.hpp:230-300
+    {
+        Handle a(A);
+        mgb_csr_t p = nullptr;
+        ok(mgb_amg_build_prolongation(a.h, EPSILON, coarse_mask.data(), &p));
+        P = to_matrix(p);
+        mgb_csr_destroy(p);
+    }
+    void build_coarse_matrix(CSRMatrix &A, CSRMatrix &P, std::unique_ptr<CSRMatrix> &coarse_matrix)  // AMG.hpp:303-369
+    {
+        Handle a(A), p(P);
+        mgb_csr_t c = nullptr;
+        ok(mgb_amg_build_coarse_matrix(a.h, p.h, &c));
+        coarse_matrix = to_matrix(c);
+        mgb_csr_destroy(c);
+    }
+    void build_coarse_rhs(const std::vector<double> &fine_rhs, CSRMatrix &P, std::vector<double> &coarse_rhs,
+                          std::vector<size_t> &component_mask)                                        // AMG.hpp:374-395
+    {
+        for (size_t j = 0; j < P.rows(); ++j)
+            for (const auto &e : P.nonZerosInRow(j)) coarse_rhs.at(component_mask.at(e.first)) += e.second * fine_rhs.at(j);
+    }
+    double compute_residual(CSRMatrix &A, const std::vector<double> &x, const std::vector<double> &rhs, std::vector<double> &res)
+    {
+        return residual<false>(A, x, rhs, res);                                                        // AMG.hpp:397-418
+    }
+    double compute_residual_with_mask(CSRMatrix &A, const std::vector<double> &x, const std::vector<double> &rhs,
+                                      std::vector<double> &res)
+    {
+        return residual<true>(A, x, rhs, res);                                                         // AMG.hpp:420-442
+    }
+};
+
 #endif
