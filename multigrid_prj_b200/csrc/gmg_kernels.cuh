@@ -508,28 +508,36 @@ __device__ __forceinline__ void rb_stream_step(
 // It needs the final values of one more row on each side, so the stream starts/ends one row further out.
 // MODE 2 (the driver's pre-sweeps): uout = the smoothed u AND ucorr(:= the residual array) = rhs - A uout on the
 //   output rows, i.e. the fine residual of multigrid.hpp:127 without a separate pass that re-reads u and f.
+// MODE 3 = MODE 2 + the restriction of that residual to the next coarser level (geometry gc, array `partial`) in
+//   the same pass (north_star: "residual+restriction fused into a single pass"): full weighting
+//   [1 2 1; 2 4 2; 1 2 1]/16 (restr = 2) or (half) injection (restr = 0, scale), evaluated in the term order of
+//   k_restrict, so the coarse residual is bit-identical to the separate kernel's.  The 3x3 neighbourhood comes from a
+//   4-row register window of the thread's own residual pairs plus, for column j0-1, the adjacent thread's value
+//   published through a 4-row shared ring one step earlier.
 // PIN (prolongation fused into the input): uin is the COARSER level's solution (geometry gc) and the rows that
 //   arrive are its bilinear interpolation, evaluated in the two-stage order of multigrid.cpp:3-27 (bit-identical
 //   to k_prolong); the prolonged field is never written to HBM.
 template <int S, bool EXACT, int MODE, bool PIN>
 __global__ void __launch_bounds__(kStreamNT)
 k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b,
-            double *__restrict__ uout, int rows_per_chunk, double *ucorr, double *__restrict__ partial, LevelGeom gc)
+            double *__restrict__ uout, int rows_per_chunk, double *ucorr, double *__restrict__ partial, LevelGeom gc,
+            int restr, double rscale)
 {
     constexpr int TW = kStreamTW, PF = kStreamPF, H = TW / 2;
     constexpr int WR = 2 * S + 3;
-    constexpr int X = (MODE != 0) ? 1 : 0;
+    constexpr int X = (MODE == 3) ? 2 : ((MODE != 0) ? 1 : 0);
     constexpr int BATCH = (MODE == 1 && S > 5) ? 5 : S;     // MODE 1 is register-bound: operands in two batches
     static_assert(PF == 4, "the main loop is unrolled by 4 rows");
     extern __shared__ double smem[];
     double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
     double *sb = smem + WR * TW;
     __shared__ double red[kStreamNT / 32];
+    __shared__ double sr[(MODE == 3) ? 4 * kStreamNT : 1];     // MODE 3: odd-column residuals of the last 4 rows
 
     const int t = threadIdx.x;
     // halo columns per side: S for the S half-sweeps; MODE 1 reads FINAL values of the lateral neighbours, i.e. one
     // more valid column, and a column pair is the unit of ownership
-    constexpr int HC = S + 2 * X;
+    constexpr int HC = S + 2 * (X > 0);
     const int OW = TW - 2 * HC;
     const int jbase = blockIdx.x * OW - HC;          // global column of tile column 0 (even)
     const int j0 = jbase + 2 * t;                    // this thread's even column
@@ -577,12 +585,15 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     };
 #pragma unroll
     for (int p = 0; p < PF; ++p) fetch(min(ifirst + p, ilast), pu[p], ps[p], pb[p]);
-    const int ksteps = (i1 - 1 + 2 * S + X) - ifirst + 1;
+    const int ksteps = (i1 - 1 + 2 * S + X) - ifirst + 1 + (MODE == 3 ? 1 : 0);
     int ro[S + 1];                                   // ring offsets of rows i-2s (s = 0: arriving row)
 #pragma unroll
     for (int s = 0; s <= S; ++s) ro[s] = ((WR - 2 * s) % WR) * TW + t;
     int roq = ((WR - (2 * S + 1)) % WR) * TW + t;    // ring offset of row i-2S-1 (MODE 1: the residual row)
     double2 pc[PF];                                  // MODE 1: rows of ucorr, requested PF steps ahead
+    double2 rr[4];                                   // MODE 3: own residual pairs of rows q, q-1, q-2, q-3
+#pragma unroll
+    for (int d = 0; d < 4; ++d) rr[d] = make_double2(0., 0.);
     double acc = 0.;
     if (MODE == 1) {
 #pragma unroll
@@ -604,20 +615,26 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
             rb_stream_step<S, EXACT, ((p) & 1), true, BATCH>(g, uw, ro, nu, nb, su, sb, i, bc0, bc1, ifirst, \
                                                       ilast, first_is_bdry, last_is_bdry, glast, inv_diag); \
         const int r = i - 2 * S;                     /* final after this step */                             \
-        if (MODE == 0 || MODE == 2) {                                                                       \
+        if (MODE == 0 || MODE == 2 || MODE == 3) {                                                          \
             if (r >= i0 && r < i1 && own) {                                                                 \
                 double *dstp = uout + (ptrdiff_t)r * P + j0;                                                \
                 if (j0 + 1 < g.w) st2(dstp, uw[2 * S]); else dstp[0] = uw[2 * S].x;                         \
             }                                                                                               \
         }                                                                                                   \
-        if (MODE == 2) {                                                                                    \
+        if (MODE == 2 || MODE == 3) {                                                                       \
             const int q = r - 1;                     /* rows q-1, q, q+1 are final: residual of row q */     \
-            if (q >= i0 && q < i1 && own) {                                                                 \
+            /* MODE 3 needs the residual one row beyond the output rows and in the lateral halo pair as well */ \
+            const int fin_lo = first_is_bdry ? ifirst : ifirst + S, fin_hi = last_is_bdry ? ilast : ilast - S; /* final rows */ \
+            const bool rows_ok = (MODE == 3) ? (q >= i0 - 1 && q <= i1 && q + g.row0 >= 0 && q <= glast &&   \
+                                                (q - 1 >= fin_lo || q + g.row0 == 0) && (q + 1 <= fin_hi || q == glast)) \
+                                             : (q >= i0 && q < i1);                                        \
+            const bool cols_ok = (MODE == 3) ? (2 * t >= HC - 2 && 2 * t < TW - HC + 2 && j0 >= 0 && j0 < g.w) : own; \
+            double2 rv = make_double2(0., 0.);                                                              \
+            if (rows_ok && cols_ok) {                                                                       \
                 const double2 c = uw[2 * S + 1], up = uw[2 * S + 2], dn = uw[2 * S];                        \
                 const double lf = su[roq + H - 1], rt = su[roq + 1];                                        \
                 const double b0 = sb[roq], b1 = sb[roq + H];                                                \
                 const bool brow = (q + g.row0 == 0) || (q == glast);                                        \
-                double2 rv;                                                                                 \
                 if (EXACT) {                                                                                \
                     rv.x = (bc0 || brow) ? __dsub_rn(b0, c.x) : resid_point(b0, up.x, lf, c.x, c.y, dn.x, g.off, g.diag); \
                     rv.y = (bc1 || brow) ? __dsub_rn(b1, c.y) : resid_point(b1, up.y, c.x, c.y, rt, dn.y, g.off, g.diag); \
@@ -628,8 +645,33 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
                     rv.x = w0 * fma(q0, (up.x + dn.x) + (lf + c.y), b0 - c.x);                              \
                     rv.y = w1 * fma(q1, (up.y + dn.y) + (c.x + rt), b1 - c.y);                              \
                 }                                                                                           \
-                double *dstp = ucorr + (ptrdiff_t)q * P + j0;                                               \
-                if (j0 + 1 < g.w) st2(dstp, rv); else dstp[0] = rv.x;                                       \
+                if (q >= i0 && q < i1 && own) {                                                             \
+                    double *dstp = ucorr + (ptrdiff_t)q * P + j0;                                           \
+                    if (j0 + 1 < g.w) st2(dstp, rv); else dstp[0] = rv.x;                                   \
+                }                                                                                           \
+            }                                                                                               \
+            if (MODE == 3) {                                                                                \
+                rr[3] = rr[2]; rr[2] = rr[1]; rr[1] = rr[0]; rr[0] = rv;                                    \
+                const int k4 = (k0 + (p)) & 3;       /* ring slot of row q (rows advance by one per step) */  \
+                sr[k4 * kStreamNT + t] = rv.y;                                                              \
+                /* coarse row centred on fine row c = q-2 (rows c-1, c, c+1 were published in earlier steps) */ \
+                const int cq = q - 2, gq = g.row0 + cq;                                                     \
+                if (((gq & 1) == 0) && cq >= i0 && cq < i1 && own) {                                        \
+                    const int gI = gq >> 1, J = j0 >> 1;                                                    \
+                    const double c0 = rr[2].x;                                                              \
+                    double v;                                                                               \
+                    if (gI == 0 || gI == gc.w - 1 || J == 0 || J == gc.w - 1) v = c0;                       \
+                    else if (restr != 2) v = __dmul_rn(rscale, c0);                                         \
+                    else {                                                                                  \
+                        const double wm = sr[((k4 + 1) & 3) * kStreamNT + t - 1];      /* row c-1 = q-3, column j0-1 */ \
+                        const double wc = sr[((k4 + 2) & 3) * kStreamNT + t - 1];      /* row c   = q-2 */    \
+                        const double wp = sr[((k4 + 3) & 3) * kStreamNT + t - 1];      /* row c+1 = q-1 */    \
+                        const double edge = __dadd_rn(__dadd_rn(__dadd_rn(rr[3].x, wc), rr[2].y), rr[1].x); \
+                        const double corner = __dadd_rn(__dadd_rn(__dadd_rn(wm, rr[3].y), wp), rr[1].y);    \
+                        v = __dadd_rn(__dadd_rn(__dmul_rn(0.25, c0), __dmul_rn(0.125, edge)), __dmul_rn(0.0625, corner)); \
+                    }                                                                                       \
+                    partial[(ptrdiff_t)(gI - gc.row0) * gc.pitch + J] = v;                                  \
+                }                                                                                           \
             }                                                                                               \
             roq += TW; if (roq >= WR * TW) roq -= WR * TW;                                                  \
         }                                                                                                   \

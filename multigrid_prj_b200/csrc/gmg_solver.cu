@@ -107,6 +107,9 @@ struct mgb_gmg {
     int lt = -1;                      // first level of the persistent coarse tail (-1: no tail kernel)
     int u_halo_valid = 0;             // halo rows of u known to be current (communication-avoiding path)
     bool r0_ready = false;            // the fused pre-sweep launch already wrote the fine residual into r (level 0)
+    bool r1_ready = false;            // ... and its restriction to level 1 (kernel MODE 3)
+    const Level *restrict_into = nullptr;   // set around the launch that should also restrict its residual
+    bool skip_restrict_l1 = false;
     int norm_partials = 0;            // > 0: the last fine post-smoothing launch left that many partial sums of the
                                       // new iterate's squared residual in d_partial (fused correction + norm)
     cudaStream_t st = nullptr;
@@ -222,6 +225,7 @@ int prepare_stream()
     if ((rc = stream_occupancy<S, true, 0, false>(&o)) || (rc = stream_occupancy<S, false, 0, false>(&o)) ||
         (rc = stream_occupancy<S, true, 1, false>(&o)) || (rc = stream_occupancy<S, false, 1, false>(&o)) ||
         (rc = stream_occupancy<S, true, 2, false>(&o)) || (rc = stream_occupancy<S, false, 2, false>(&o)) ||
+        (rc = stream_occupancy<S, true, 3, false>(&o)) || (rc = stream_occupancy<S, false, 3, false>(&o)) ||
         (rc = stream_occupancy<S, true, 0, true>(&o)) || (rc = stream_occupancy<S, false, 0, true>(&o)) ||
         (rc = stream_occupancy<S, true, 1, true>(&o)) || (rc = stream_occupancy<S, false, 1, true>(&o)))
         return rc;
@@ -238,12 +242,13 @@ int prepare_kernels()
 
 template <int S, bool EXACT, int MODE, bool PIN>
 int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr,
-                       const LevelGeom &gc)
+                       const LevelGeom &gc, double *coarse_out = nullptr, int restr = 0, double rscale = 1.0)
 {
     int occ = 1;
     constexpr int smem = mgb::stream_smem_bytes<S>();
     if (int rc = stream_occupancy<S, EXACT, MODE, PIN>(&occ)) return rc;
     const int OW = mgb::kStreamTW - 2 * (S + 2 * (MODE != 0));    // owned columns per CTA (kernel: HC)
+    double *aux = (MODE == 3) ? coarse_out : h->d_partial;
     const int nx = (g.w + OW - 1) / OW;
     const int slots = h->n_sm * occ;
     // rows per chunk: a CTA needs (rc + 2S) steps and the grid needs ceil(nx*ny/slots) waves; pick the
@@ -262,9 +267,9 @@ int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const d
         }
     }
     if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
-    mgb::k_rb_stream<S, EXACT, MODE, PIN><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, h->d_partial, gc);
+    mgb::k_rb_stream<S, EXACT, MODE, PIN><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, aux, gc, restr, rscale);
     // 24 B per point per sweep, S/2 sweeps per launch (+ correction 24 + norm-only residual 16 when fused)
-    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE == 2 ? 24. : 0.))) * npts(g) + (PIN ? 8. * (npts(g) + npts(gc)) : 0.));
+    count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE >= 2 ? 24. : 0.))) * npts(g) + ((PIN || MODE == 3) ? 8. * (npts(g) + npts(gc)) : 0.));
     if (MODE == 1) h->norm_partials = nx * ny;
     CK(cudaGetLastError());
     return MGB_OK;
@@ -276,6 +281,11 @@ int launch_rb_stream_s(mgb_gmg *h, const LevelGeom &g, const double *in, const d
                        double *resid, const LevelGeom *gc)
 {
     static const LevelGeom none{};
+    if (resid && h->restrict_into) {       // MODE 3: residual + its restriction to the next level in the same pass
+        const Level &C = *h->restrict_into;
+        const double scale = (h->cfg.restriction == MGB_RESTRICT_HALF_INJECTION) ? 0.5 : 1.0;
+        return launch_rb_stream_t<S, EXACT, 3, false>(h, g, in, rhs, out, resid, C.g, C.r, h->cfg.restriction, scale);
+    }
     if (resid) return launch_rb_stream_t<S, EXACT, 2, false>(h, g, in, rhs, out, resid, none);
     if (ucorr) return gc ? launch_rb_stream_t<S, EXACT, 1, true>(h, g, in, rhs, out, ucorr, *gc)
                          : launch_rb_stream_t<S, EXACT, 1, false>(h, g, in, rhs, out, ucorr, none);
@@ -421,7 +431,10 @@ int do_restrict(mgb_gmg *h)
     const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
     if ((rc = halo_exchange(h, 0, h->lv[0].r, kHalo))) return rc;
     const int lend = h->lt >= 0 ? h->lt : L - 1;      // the tail kernel restricts below its first level itself
+    const bool skip1 = h->skip_restrict_l1;
+    h->skip_restrict_l1 = false;
     for (int l = 1; l <= lend; ++l) {
+        if (l == 1 && skip1) continue;                  // level 1 was restricted inside the pre-sweep launch (MODE 3)
         Level &F = h->lv[l - 1], &C = h->lv[l];
         LevelGeom gc = C.g;
         double *rc_ptr = C.r;
@@ -716,8 +729,11 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     int rc;
     h->norm_partials = 0;
     // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
+    const bool skip_first_restriction = h->r0_ready && h->r1_ready;
     if (h->r0_ready) h->r0_ready = false;
     else if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
+    h->r1_ready = false;
+    h->skip_restrict_l1 = skip_first_restriction;
     if ((rc = do_restrict(h))) return rc;
     if (h->lt >= 0) {
         // restriction below lt, coarse solve and the upward leg up to level lt: one persistent CTA
@@ -795,8 +811,13 @@ int one_iteration(mgb_gmg *h)
     Level &F = h->lv[0];
     int rc;
     if (fuse_resid(h)) {
-        if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f, nullptr, F.r))) return rc;
+        const bool with_restriction = h->cfg.n_ranks == 1 && h->lv.size() > 1;
+        h->restrict_into = with_restriction ? &h->lv[1] : nullptr;
+        rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f, nullptr, F.r);
+        h->restrict_into = nullptr;
+        if (rc) return rc;
         h->r0_ready = true;
+        h->r1_ready = with_restriction;
     } else if ((rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f))) return rc;
     if ((rc = do_cycle(h, nullptr, nullptr))) return rc;
     if (h->norm_partials > 0) {          // the fused last launch already left the new iterate's residual partial sums

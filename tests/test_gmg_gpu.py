@@ -238,18 +238,21 @@ def test_fused_correction_and_norm_equal_separate_passes(N, L, fast):
         assert np.allclose(rel, out[0][1], rtol=1e-6, atol=1e-14)
 
 
-@pytest.mark.parametrize("N,L", [(257, 8), (1025, 10), (513, 2)])
-def test_fused_residual_in_pre_sweeps_equals_separate_pass(N, L):
-    """exact arithmetic: the residual written by the last pre-sweep launch is the one the separate pass computes,
-    bit for bit, so whole iterations agree bit for bit; fast arithmetic: agreement to rounding"""
+@pytest.mark.parametrize("N,L", [(257, 8), (1025, 10), (513, 2), (2049, 3)])
+@pytest.mark.parametrize("restr", [G.FULL_WEIGHTING, G.HALF_INJECTION])
+def test_fused_residual_and_restriction_in_pre_sweeps_equal_separate_passes(N, L, restr):
+    """north_star: residual + restriction fused into a single pass.  Exact arithmetic: the residual and its
+    restriction to level 1 written by the last pre-sweep launch are the ones the separate kernels compute, bit for
+    bit, so whole iterations agree bit for bit; fast arithmetic: agreement to rounding"""
     res = {}
     for fast in (0, 1):
         for fuse in (0, 1):
-            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_residual=fuse, fuse_correction=0)) as g:
+            with Gmg(GmgConfig.fast(N, L, rb_fast_arith=fast, fuse_residual=fuse, fuse_correction=0, restriction=restr)) as g:
                 g.set_rhs_test(1); g.set_u(None)
                 rel = g.run_cycles(3)
-                res[(fast, fuse)] = (g.get_u(), rel, g.get_level(0, G.VEC_R))
-    assert np.array_equal(res[(0, 0)][0], res[(0, 1)][0]) and np.array_equal(res[(0, 0)][2], res[(0, 1)][2])
+                res[(fast, fuse)] = (g.get_u(), rel, g.get_level(0, G.VEC_R), g.get_level(1, G.VEC_R))
+    for k in (0, 2, 3):
+        assert np.array_equal(res[(0, 0)][k], res[(0, 1)][k]), k
     assert res[(0, 0)][1] == res[(0, 1)][1]
     scale = np.abs(res[(1, 0)][0]).max()
     assert np.abs(res[(1, 0)][0] - res[(1, 1)][0]).max() <= 1e-12 * scale
