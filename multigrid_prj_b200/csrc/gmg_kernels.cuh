@@ -532,7 +532,7 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     double *su = smem;                 // [WR][TW]: [slot][0..H) even columns, [slot][H..TW) odd columns
     double *sb = smem + WR * TW;
     __shared__ double red[kStreamNT / 32];
-    __shared__ double sr[(MODE == 3) ? 4 * kStreamNT : 1];     // MODE 3: odd-column residuals of the last 4 rows
+    __shared__ double sr[(MODE == 3) ? 8 * kStreamNT : 1];     // MODE 3: residual pairs of the last 4 rows ([row][even|odd][t])
 
     const int t = threadIdx.x;
     // halo columns per side: S for the S half-sweeps; MODE 1 reads FINAL values of the lateral neighbours, i.e. one
@@ -591,9 +591,6 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
     for (int s = 0; s <= S; ++s) ro[s] = ((WR - 2 * s) % WR) * TW + t;
     int roq = ((WR - (2 * S + 1)) % WR) * TW + t;    // ring offset of row i-2S-1 (MODE 1: the residual row)
     double2 pc[PF];                                  // MODE 1: rows of ucorr, requested PF steps ahead
-    double2 rr[4];                                   // MODE 3: own residual pairs of rows q, q-1, q-2, q-3
-#pragma unroll
-    for (int d = 0; d < 4; ++d) rr[d] = make_double2(0., 0.);
     double acc = 0.;
     if (MODE == 1) {
 #pragma unroll
@@ -651,23 +648,23 @@ k_rb_stream(LevelGeom g, const double *__restrict__ uin, const double *__restric
                 }                                                                                           \
             }                                                                                               \
             if (MODE == 3) {                                                                                \
-                rr[3] = rr[2]; rr[2] = rr[1]; rr[1] = rr[0]; rr[0] = rv;                                    \
-                const int k4 = (k0 + (p)) & 3;       /* ring slot of row q (rows advance by one per step) */  \
-                sr[k4 * kStreamNT + t] = rv.y;                                                              \
+                constexpr int NT2 = 2 * kStreamNT;                                                          \
+                const int k4 = (p) & 3;              /* ring slot of row q: k0 is a multiple of 4 */          \
+                sr[k4 * NT2 + t] = rv.x; sr[k4 * NT2 + kStreamNT + t] = rv.y;                               \
                 /* coarse row centred on fine row c = q-2 (rows c-1, c, c+1 were published in earlier steps) */ \
                 const int cq = q - 2, gq = g.row0 + cq;                                                     \
                 if (((gq & 1) == 0) && cq >= i0 && cq < i1 && own) {                                        \
                     const int gI = gq >> 1, J = j0 >> 1;                                                    \
-                    const double c0 = rr[2].x;                                                              \
+                    const double *rm = sr + ((k4 + 1) & 3) * NT2 + t;      /* row c-1 = q-3 */                \
+                    const double *rc = sr + ((k4 + 2) & 3) * NT2 + t;      /* row c   = q-2 */                \
+                    const double *rp = sr + ((k4 + 3) & 3) * NT2 + t;      /* row c+1 = q-1 */                \
+                    const double c0 = rc[0];                                                                \
                     double v;                                                                               \
                     if (gI == 0 || gI == gc.w - 1 || J == 0 || J == gc.w - 1) v = c0;                       \
                     else if (restr != 2) v = __dmul_rn(rscale, c0);                                         \
-                    else {                                                                                  \
-                        const double wm = sr[((k4 + 1) & 3) * kStreamNT + t - 1];      /* row c-1 = q-3, column j0-1 */ \
-                        const double wc = sr[((k4 + 2) & 3) * kStreamNT + t - 1];      /* row c   = q-2 */    \
-                        const double wp = sr[((k4 + 3) & 3) * kStreamNT + t - 1];      /* row c+1 = q-1 */    \
-                        const double edge = __dadd_rn(__dadd_rn(__dadd_rn(rr[3].x, wc), rr[2].y), rr[1].x); \
-                        const double corner = __dadd_rn(__dadd_rn(__dadd_rn(wm, rr[3].y), wp), rr[1].y);    \
+                    else {   /* [x][t] = column j0, [y][t] = column j0+1, [y][t-1] = column j0-1 */           \
+                        const double edge = __dadd_rn(__dadd_rn(__dadd_rn(rm[0], rc[kStreamNT - 1]), rc[kStreamNT]), rp[0]); \
+                        const double corner = __dadd_rn(__dadd_rn(__dadd_rn(rm[kStreamNT - 1], rm[kStreamNT]), rp[kStreamNT - 1]), rp[kStreamNT]); \
                         v = __dadd_rn(__dadd_rn(__dmul_rn(0.25, c0), __dmul_rn(0.125, edge)), __dmul_rn(0.0625, corner)); \
                     }                                                                                       \
                     partial[(ptrdiff_t)(gI - gc.row0) * gc.pitch + J] = v;                                  \
