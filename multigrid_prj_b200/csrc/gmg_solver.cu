@@ -112,6 +112,7 @@ struct mgb_gmg {
     bool skip_restrict_l1 = false;
     int norm_partials = 0;            // > 0: the last fine post-smoothing launch left that many partial sums of the
                                       // new iterate's squared residual in d_partial (fused correction + norm)
+    unsigned scal_local = 0;          // bit s: d_scal[s] holds only this rank's part; summed over ranks when it is read
     cudaStream_t st = nullptr;
     mgb::NcclComm comm = nullptr;
     double *d_partial = nullptr;      // per-CTA partial sums
@@ -123,7 +124,7 @@ struct mgb_gmg {
     int n_sm = 148;
     mgb_gmg_stats stats{};
     // CUDA graphs of `period` driver iterations, keyed by the buffer-pointer state they were captured in
-    struct IterGraph { std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; };
+    struct IterGraph { std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; unsigned scal_local; };
     std::vector<IterGraph> graphs;
 
     double **vec(int level, int which)
@@ -184,19 +185,28 @@ int halo_exchange(mgb_gmg *h, int level, double *v, int depth)
     return MGB_OK;
 }
 
-// reduce d_partial[0..n) into d_scal[slot]; sum over ranks when the level is sharded
-int reduce_partials(mgb_gmg *h, int n, int slot, bool sharded)
+// reduce d_partial[0..n) into d_scal[slot]; sum over ranks when the level is sharded.  `defer`: leave this
+// rank's part and form the global sum only when the value is read (read_scalar) -- the driver loop of
+// run_cycles never looks at intermediate norms, so K iterations cost one all-reduce instead of K.
+int reduce_partials(mgb_gmg *h, int n, int slot, bool sharded, bool defer = false)
 {
     mgb::k_reduce_partials<<<1, 1024, 0, h->st>>>(h->d_partial, n, h->d_scal + slot);
     count(h, 0.);
     CK(cudaGetLastError());
-    if (sharded && h->cfg.n_ranks > 1)
-        NK(mgb::nccl().AllReduce(h->d_scal + slot, h->d_scal + slot, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+    h->scal_local &= ~(1u << slot);
+    if (sharded && h->cfg.n_ranks > 1) {
+        if (defer) h->scal_local |= 1u << slot;
+        else NK(mgb::nccl().AllReduce(h->d_scal + slot, h->d_scal + slot, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+    }
     return MGB_OK;
 }
 
 int read_scalar(mgb_gmg *h, int slot, double *out)
 {
+    if (h->scal_local & (1u << slot)) {          // collective: every rank reads the same values at the same points
+        NK(mgb::nccl().AllReduce(h->d_scal + slot, h->d_scal + slot, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+        h->scal_local &= ~(1u << slot);
+    }
     CK(cudaMemcpyAsync(h->h_scal + slot, h->d_scal + slot, sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     *out = h->h_scal[slot];
@@ -511,8 +521,8 @@ int finish_cycle(mgb_gmg *h)
 
 // ---- communication-avoiding schedule for the fused red-black path on slabs --------------------------------
 // Every fused kernel recomputes halo rows from a deeper input halo instead of receiving them, so one driver
-// iteration needs 3 point-to-point exchange groups (u; the fine residual; all restricted residuals + the
-// gather of the first replicated level) and 1 all-reduce, instead of one exchange per operator.
+// iteration needs 2 point-to-point exchange groups (u; all restricted residuals + the gather of the first
+// replicated level) instead of one exchange per operator; the norm's all-reduce happens when the norm is read.
 struct Depths {
     std::vector<int> din, dout, ext_r;     // per level: input halo the post-smoother reads, halo rows it must
 };                                         // produce for the prolongation above it, halo rows of r made by restriction
@@ -550,6 +560,13 @@ Depths plan_depths(mgb_gmg *h)
     return d;
 }
 
+// halo rows of the fine residual the cycle reads, and of u the pre-sweep launch reads to produce them
+int ca_resid_depth(mgb_gmg *, const Depths &d) { return std::max(d.din[0], d.ext_r[0]); }
+int ca_u_depth(mgb_gmg *h, const Depths &d)
+{
+    return 2 * h->cfg.n_pre + 1 + (fuse_resid(h) ? ca_resid_depth(h, d) : 0);
+}
+
 bool ca_applicable(mgb_gmg *h)
 {
     if (h->cfg.n_ranks <= 1 || !h->cfg.rb_fused || h->cfg.smoother != MGB_SMOOTH_GS_RB || h->cfg.pre_smoother != MGB_SMOOTH_GS_RB)
@@ -558,7 +575,7 @@ bool ca_applicable(mgb_gmg *h)
         h->cfg.restriction != MGB_RESTRICT_INJECTION) return false;
     if (h->lt < 0 || h->lt <= h->ls) return false;       // the replicated part must end in the tail kernel
     const Depths d = plan_depths(h);
-    int need = std::max(d.ext_r[0], 2 * h->cfg.n_pre + 1);
+    int need = std::max(d.ext_r[0], ca_u_depth(h, d));
     for (int l = 0; l <= h->ls; ++l) need = std::max(need, d.din[l]);
     return need + 2 <= kHalo && need <= h->lv[h->ls].g.rows / 2;
 }
@@ -590,23 +607,25 @@ int one_iteration_ca(mgb_gmg *h)
     auto &N = mgb::nccl();
     int rc;
     h->norm_partials = 0;
-    // (1) u: one exchange serves the pre-sweeps (2 rows per sweep) and the residual after them (+1)
-    const int ext_u = 2 * h->cfg.n_pre + 1;
+    // (1) u: one exchange serves the pre-sweeps (2 rows per sweep) and the residual after them (+1).  With the
+    // residual fused into the pre-sweep launch, the launch also recomputes the `dr` halo rows of the residual the
+    // cycle reads (rhs of the fine post-smoother, stencil of the restriction cascade) from a deeper halo of u,
+    // which removes the exchange of the residual altogether.
+    const int dr = ca_resid_depth(h, d);
+    const int ext_u = ca_u_depth(h, d);
     if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
     h->u_halo_valid = 0;
     if (fuse_resid(h)) {
-        if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 0, nullptr, F.r))) return rc;
+        if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, dr, nullptr, F.r))) return rc;
     } else {
+        // (2) unfused: fine residual on the owned rows, then ONE deep exchange of it
         if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 1))) return rc;
-    }
-    // (2) fine residual on the owned rows, then ONE deep exchange of it
-    if (!fuse_resid(h)) {
         dim3 grid = march_grid(F.g);
         mgb::k_residual<true><<<grid, mgb::kTPB, 0, h->st>>>(F.g, F.u, F.f, F.r, h->d_partial);
         count(h, 24. * npts(F.g));
         CK(cudaGetLastError());
+        if ((rc = halo_exchange(h, 0, F.r, dr))) return rc;
     }
-    if ((rc = halo_exchange(h, 0, F.r, std::max(d.din[0], d.ext_r[0])))) return rc;
     // (3) restriction down the sharded levels, halo rows recomputed; then the first replicated level's slab
     const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
     for (int l = 1; l <= std::min(ls + 1, h->lt); ++l) {
@@ -706,7 +725,7 @@ int one_iteration_ca(mgb_gmg *h)
         h->u_halo_valid = ext_u;
         const int np = h->norm_partials;
         h->norm_partials = 0;
-        return reduce_partials(h, np, 1, true);
+        return reduce_partials(h, np, 1, true, true);
     }
     if ((rc = finish_cycle(h))) return rc;
     // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
@@ -851,6 +870,7 @@ int run_iterations(mgb_gmg *h, int cycles)
             if (!g && cycles < 4) { if ((rc = one_iteration(h))) return rc; --cycles; continue; }   // not worth a capture
             if (!g) {
                 const mgb_gmg_stats before = h->stats;
+                const unsigned local_before = h->scal_local;
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
                 int period = 0;
@@ -860,8 +880,9 @@ int run_iterations(mgb_gmg *h, int cycles)
                 // capturing executes nothing: restore the counters and (after an odd number of swaps) the pointers
                 mgb_gmg::IterGraph ng{key, nullptr, period, h->stats.kernel_launches - before.kernel_launches,
                                       h->stats.bytes_algorithmic - before.bytes_algorithmic,
-                                      h->stats.reserved[0] - before.reserved[0]};
+                                      h->stats.reserved[0] - before.reserved[0], h->scal_local & 2u};
                 h->stats = before;
+                h->scal_local = local_before;
                 if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
                 if (pointer_state(h) != key) { cudaGraphDestroy(graph); return fail(MGB_ERR_STATE, "buffer rotation has no short period"); }
@@ -877,6 +898,7 @@ int run_iterations(mgb_gmg *h, int cycles)
                 h->stats.bytes_algorithmic += g->bytes;
                 h->stats.reserved[0] += g->exchanges;
                 h->stats.cycles += g->period;
+                h->scal_local = (h->scal_local & ~2u) | g->scal_local;
                 cycles -= g->period;
                 continue;
             }

@@ -90,6 +90,15 @@ def main():
             report(f"[{mode}] solve: history", hist.size == hist_ref.size and np.allclose(hist, hist_ref, rtol=1e-9))
             report(f"[{mode}] solve: solution bit-identical", np.array_equal(got, want), f"maxdiff {np.abs(got - want).max():.3e}")
             print(f"      exchanges posted by rank 0: {g.lib and g.stats()}", flush=True)
+        # (3) the same iterations as CUDA-graph launches (norm all-reduce deferred to the read at the end)
+        g.set_rhs_test(1); g.set_u(None)
+        rel = g.run_cycles(6)
+        got = assemble(g, n, g.get_u)
+        if rank == 0:
+            ref.set_rhs_test(1); ref.set_u(None)
+            rel_ref = ref.run_cycles(6)
+            report(f"[{mode}] run_cycles(6): solution bit-identical", np.array_equal(got, ref.get_u()))
+            report(f"[{mode}] run_cycles(6): final residual", abs(rel - rel_ref) <= 1e-9 * rel_ref, f"{rel} vs {rel_ref}")
         g.close()
         if ref is not None:
             ref.close()
