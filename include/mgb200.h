@@ -85,7 +85,11 @@ typedef struct mgb_gmg_config {
     int fuse_prolong;     /* red-black fused path only: the first post-smoothing launch of a level interpolates its input
                              from the coarser level on the fly (multigrid.cpp:3-27, same arithmetic); the prolonged field
                              is never written to HBM */
-    int reserved[3];
+    int reserved0;
+    double jacobi_omega;  /* MGB_SMOOTH_JACOBI: u <- u + omega (u_jacobi - u) on interior points.  The reference is
+                             omega = 1 (solvers.hpp:64-83) and that value keeps the bit-identical path; other values
+                             (north_star: weighted Jacobi) run level by level without the persistent tail kernel.
+                             <= 0 is read as 1 */
 } mgb_gmg_config;
 
 typedef struct mgb_gmg *mgb_gmg_t;
@@ -186,7 +190,15 @@ typedef struct mgb_amg_config {
     int device;
     int64_t start_index[16]; /* node the C/F splitting of level l starts from; the reference draws it from
                               std::random_device (src/Utilities.cpp:30-40); < 0 selects n/2 */
-    int reserved[8];
+    /* --- beyond the reference --- */
+    int hybrid_gs;         /* row-block sharded levels only.  0: ghost entries are refreshed after EVERY colour, the
+                              multicolour sweep equals the single-GPU sweep bit for bit; 1: once per sweep ("hybrid"
+                              Gauss-Seidel: Jacobi-like across block boundaries, one exchange instead of n_colours) */
+    int shard_min_rows;    /* a level is cut into row blocks while it keeps at least this many rows per rank; smaller
+                              levels are replicated on every rank (<= 0: 16384) */
+    double jacobi_omega;   /* MGB_SMOOTH_JACOBI: x <- x + omega (D^-1 (b - (A - D) x) - x); the reference is omega = 1
+                              (<= 0 is read as 1) */
+    int reserved[4];
 } mgb_amg_config;
 
 typedef struct mgb_amg *mgb_amg_t;
@@ -202,6 +214,22 @@ void mgb_amg_config_fast(mgb_amg_config *cfg);      /* multicolour GS + vector k
 int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *row_ptr, const int64_t *col,
                             const double *val, const double *rhs, mgb_amg_t *out);
 void mgb_amg_destroy(mgb_amg_t h);
+
+/* Row-block sharded AMG over the GPUs of one box (the reference is single-process).  One process
+ * per GPU; EVERY rank passes the same level-0 system and builds the same hierarchy on its host (the setup is
+ * deterministic), then keeps on its device only the rows [row0, row0+rows) of each sharded level's operators
+ * (mgb_amg_partition).  Vectors keep global indexing; the ghost entries a rank's rows reference are refreshed by
+ * grouped ncclSend/ncclRecv from precomputed index lists (mgb_amg_halo_plan), norms by ncclAllReduce, and levels below
+ * cfg->shard_min_rows rows per rank are replicated (their restricted vector is all-gathered once per visit).
+ * Lexicographic Gauss-Seidel is sequential across blocks: sharded levels take MGB_SMOOTH_GS_RB or MGB_SMOOTH_JACOBI.
+ * nccl_id: from mgb_nccl_unique_id() on rank 0, same on all ranks (ignored when n_ranks == 1). */
+int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *row_ptr, const int64_t *col,
+                           const double *val, const double *rhs, int rank, int n_ranks,
+                           const unsigned char nccl_id[128], mgb_amg_t *out);
+/* the contiguous block of n rows (or vector entries) that `rank` owns.  Host-only, no device needed. */
+int mgb_amg_partition(size_t n, int n_ranks, int rank, size_t *row0, size_t *rows);
+/* rows of `level` this handle works on, and whether the level is sharded (0: replicated, whole on every rank) */
+int mgb_amg_level_rows(mgb_amg_t h, int level, size_t *row0, size_t *rows, int *sharded);
 
 /* hierarchy queries (the reference prints the level sizes, src/AMG.cpp:85-86,111) */
 int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t *nnz_p, size_t *n_coarse,
@@ -243,6 +271,16 @@ int mgb_amg_select_coarse_nodes(mgb_csr_t A, double eps, int64_t start, unsigned
 int mgb_amg_build_prolongation(mgb_csr_t A, double eps, const unsigned char *coarse_mask, mgb_csr_t *P);
 /* replaces build_coarse_matrix (AMG.hpp:303-369) */
 int mgb_amg_build_coarse_matrix(mgb_csr_t A, mgb_csr_t P, mgb_csr_t *Ac);
+
+/* Ghost-exchange plan of operator M for `rank` (host-only; what mgb_amg_create_sharded builds internally, exported so
+ * that the index lists can be checked without a GPU).  The rank owns the rows mgb_amg_partition(n_rows) of M and the
+ * vector entries mgb_amg_partition(n_cols).  recv lists the entries of other ranks its rows reference, send the
+ * entries of its own block that other ranks' rows reference.  group_of_col (may be NULL, then n_groups = 1) assigns
+ * every vector entry to a group (the colour of a multicolour sweep); the lists are ordered by (group, peer, index):
+ * segment (g, p) of send_idx is [send_ptr[g*n_ranks+p], send_ptr[g*n_ranks+p+1]).  *_ptr hold n_groups*n_ranks+1
+ * entries; pass send_idx = recv_idx = NULL to obtain the sizes (the last entry of each ptr array) first. */
+int mgb_amg_halo_plan(mgb_csr_t M, int n_ranks, int rank, const int *group_of_col, int n_groups,
+                      int64_t *send_ptr, int64_t *send_idx, int64_t *recv_ptr, int64_t *recv_idx);
 
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
 int mgb_amg_reset_stats(mgb_amg_t h);

@@ -20,7 +20,8 @@ class GmgConfigStruct(C.Structure):
                 ("coarse_tol", C.c_double), ("coarse_maxit", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
                 ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("rb_fast_arith", C.c_int),
-                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("reserved", C.c_int * 3)]
+                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("reserved0", C.c_int),
+                ("jacobi_omega", C.c_double)]
 
 
 class GmgStatsStruct(C.Structure):
@@ -33,7 +34,8 @@ class AmgConfigStruct(C.Structure):
     # mirrors mgb_amg_config in include/mgb200.h
     _fields_ = [("levels", C.c_int), ("eps", C.c_double), ("smoother", C.c_int), ("pre_sweeps", C.c_int),
                 ("coarse_sweeps", C.c_int), ("post_sweeps", C.c_int), ("exact_order", C.c_int), ("device", C.c_int),
-                ("start_index", C.c_int64 * 16), ("reserved", C.c_int * 8)]
+                ("start_index", C.c_int64 * 16), ("hybrid_gs", C.c_int), ("shard_min_rows", C.c_int),
+                ("jacobi_omega", C.c_double), ("reserved", C.c_int * 4)]
 
 
 # every symbol include/mgb200.h declares: name -> (restype, argtypes)
@@ -71,6 +73,10 @@ SYMBOLS = {
     "mgb_amg_config_fast": (None, [C.POINTER(AmgConfigStruct)]),
     "mgb_amg_create_from_csr": (_i, [C.POINTER(AmgConfigStruct), C.c_size_t, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "mgb_amg_destroy": (None, [_vp]),
+    "mgb_amg_create_sharded": (_i, [C.POINTER(AmgConfigStruct), C.c_size_t, _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "mgb_amg_partition": (_i, [C.c_size_t, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mgb_amg_level_rows": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _pi]),
+    "mgb_amg_halo_plan": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "mgb_amg_level_info": (_i, [_vp, _i] + [C.POINTER(C.c_size_t)] * 4 + [_pi, _pi]),
     "mgb_amg_get_matrix": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "mgb_amg_get_schedule": (_i, [_vp, _i, _i, _vp]),

@@ -14,7 +14,9 @@ GS_LEX, JACOBI, GS_MULTICOLOUR = 0, 1, 3
 
 
 class Amg:
-    def __init__(self, ptr, col, val, rhs, levels=5, fast=False, starts=None, **kw):
+    def __init__(self, ptr, col, val, rhs, levels=5, fast=False, starts=None, rank=0, n_ranks=1, nccl_id=None, **kw):
+        """rank / n_ranks / nccl_id: row-block sharded over one box (mgb_amg_create_sharded); every rank passes the
+        same system.  Other keywords set fields of mgb_amg_config (hybrid_gs, shard_min_rows, jacobi_omega, ...)."""
         self.lib = load()
         c = AmgConfigStruct()
         (self.lib.mgb_amg_config_fast if fast else self.lib.mgb_amg_config_default)(C.byref(c))
@@ -32,7 +34,13 @@ class Amg:
         self.levels = levels
         self.h = C.c_void_p()
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(self.lib.mgb_amg_create_from_csr(C.byref(c), self.n, p(ptr), p(col), p(val), p(rhs), C.byref(self.h)))
+        self.rank, self.n_ranks = rank, n_ranks
+        if n_ranks > 1:
+            idb = (C.c_ubyte * 128)(*bytes(nccl_id))
+            check(self.lib.mgb_amg_create_sharded(C.byref(c), self.n, p(ptr), p(col), p(val), p(rhs), rank, n_ranks,
+                                                  C.cast(idb, C.c_void_p), C.byref(self.h)))
+        else:
+            check(self.lib.mgb_amg_create_from_csr(C.byref(c), self.n, p(ptr), p(col), p(val), p(rhs), C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -57,6 +65,12 @@ class Amg:
         check(self.lib.mgb_amg_level_info(self.h, level, *[C.byref(x) for x in v], C.byref(w), C.byref(k)))
         return {"n": v[0].value, "nnz_a": v[1].value, "nnz_p": v[2].value, "n_coarse": v[3].value,
                 "wavefronts": w.value, "colours": k.value}
+
+    def rows(self, level):
+        """(row0, rows, sharded): the rows of `level` this rank works on"""
+        r0, rows, sh = C.c_size_t(), C.c_size_t(), C.c_int()
+        check(self.lib.mgb_amg_level_rows(self.h, level, C.byref(r0), C.byref(rows), C.byref(sh)))
+        return r0.value, rows.value, bool(sh.value)
 
     def matrix(self, level, which):
         """(ptr, col, val) of A_level (which=0) or P_level (which=1)"""
@@ -121,3 +135,32 @@ class Amg:
 
     def reset_stats(self):
         check(self.lib.mgb_amg_reset_stats(self.h))
+
+
+def partition(n, n_ranks, rank):
+    """(row0, rows) of the block of an n-long index space that `rank` owns (mgb_amg_partition; host only)"""
+    r0, rows = C.c_size_t(), C.c_size_t()
+    check(load().mgb_amg_partition(n, n_ranks, rank, C.byref(r0), C.byref(rows)))
+    return r0.value, rows.value
+
+
+def halo_plan(ptr, col, val, shape, n_ranks, rank, group_of_col=None, n_groups=1):
+    """ghost-exchange plan of a CSR operator for `rank` (mgb_amg_halo_plan; host only).
+    Returns (send_ptr, send_idx, recv_ptr, recv_idx); segment (g, p) = ptr[g * n_ranks + p : g * n_ranks + p + 2]."""
+    lib = load()
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64); col = np.ascontiguousarray(col, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    m = C.c_void_p()
+    check(lib.mgb_csr_create(shape[0], shape[1], p(ptr), p(col), p(val), C.byref(m)))
+    try:
+        g = None if group_of_col is None else np.ascontiguousarray(group_of_col, dtype=np.int32)
+        ng = 1 if g is None else n_groups
+        sp, rp = np.zeros(ng * n_ranks + 1, np.int64), np.zeros(ng * n_ranks + 1, np.int64)
+        gp = None if g is None else p(g)
+        check(lib.mgb_amg_halo_plan(m, n_ranks, rank, gp, ng, p(sp), None, p(rp), None))
+        si, ri = np.zeros(max(int(sp[-1]), 1), np.int64), np.zeros(max(int(rp[-1]), 1), np.int64)
+        check(lib.mgb_amg_halo_plan(m, n_ranks, rank, gp, ng, p(sp), p(si), p(rp), p(ri)))
+        return sp, si[:int(sp[-1])], rp, ri[:int(rp[-1])]
+    finally:
+        lib.mgb_csr_destroy(m)

@@ -39,19 +39,38 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + ["-shared", "-o", LIB, "-I", os.path.join(ROOT, "include")] + sources()
-    cmd += ["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "1") == "1" else []
+def _compile_one(args):
+    src, obj, flags, verbose = args
+    cmd = [_nvcc()] + flags + ["-c", "-o", obj, "-I", os.path.join(ROOT, "include"), src, "-ccbin", "/usr/bin/g++"]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         print(" ".join(cmd))
-    env = dict(os.environ)
+    subprocess.check_call(cmd)
+    return obj
+
+
+def build_lib(force=False, verbose=False):
+    """one object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link"""
+    if not force and not _stale():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + [os.path.join(ROOT, "include", "mgb200.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append((src, obj, flags, verbose))
     # the image's $CC/$CXX wrappers are not usable as nvcc host compilers for shared objects
-    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+    with ThreadPoolExecutor(max(len(jobs), 1)) as ex:
+        list(ex.map(_compile_one, jobs))
+    cmd = [_nvcc()] + flags[:2] + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++"]
+    cmd += ["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "1") == "1" else []
+    subprocess.check_call(cmd)
     return LIB
 
 

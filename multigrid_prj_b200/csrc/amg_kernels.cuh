@@ -89,14 +89,20 @@ k_amg_gs_color_vec(CsrDev A, const double *__restrict__ diag, double *x, const d
     if (ok && lane == 0) x[i] = (b[i] - sum) / diag[i];
 }
 
-// Jacobi: xnew = (b - sum_{j != i} a_ij x_j) / a_ii for every row (vector form)
+// weighted Jacobi: xhat = (b - sum_{j != i} a_ij x_j) / a_ii, xnew = x + omega (xhat - x); omega == 1 stores xhat itself
+// (the reference's smoothers are unweighted).  Rows [row0, row1): the block this rank owns.
+__device__ __forceinline__ double relax(double xhat, double xold, double omega)
+{
+    return omega == 1. ? xhat : xold + omega * (xhat - xold);
+}
+
 __global__ void __launch_bounds__(256)
 k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__restrict__ x, const double *__restrict__ b,
-                 double *__restrict__ xnew)
+                 double *__restrict__ xnew, double omega, int row0, int row1)
 {
     const int lane = threadIdx.x & (kLanes - 1);
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
-    const bool ok = i < A.n_rows;
+    const int i = row0 + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const bool ok = i < row1;
     double sum = 0.;
     if (ok)
         for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) {
@@ -104,7 +110,7 @@ k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__rest
             if (j != i) sum += A.val[k] * x[j];
         }
     sum = subwarp_sum(sum);
-    if (ok && lane == 0) xnew[i] = (b[i] - sum) / diag[i];
+    if (ok && lane == 0) xnew[i] = relax((b[i] - sum) / diag[i], x[i], omega);
 }
 
 // ---- fast path: sliced-ELLPACK copy of the level operator ---------------------------------------------------------------
@@ -128,7 +134,7 @@ struct SellDev {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *out, double *__restrict__ partial,
-           int first, int last)
+           int first, int last, double omega)
 {
     __shared__ double red[8];
     const int p = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +153,9 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
                 const double ri = bi - (sum + d * x[i]);
                 if (out) out[i] = ri;
                 acc = ri * ri;
-            } else
+            } else if (MODE == 1)
+                out[i] = relax((bi - sum) / d, x[i], omega);
+            else
                 out[i] = (bi - sum) / d;
         }
     }
@@ -179,13 +187,13 @@ k_amg_to_slots(const int *__restrict__ row_of_slot, int n_slots, const double *_
 template <bool EXACT>
 __global__ void __launch_bounds__(256)
 k_amg_residual(CsrDev A, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r,
-               double *__restrict__ partial)
+               double *__restrict__ partial, int row0, int row1)
 {
     __shared__ double red[8];
     double acc = 0.;
     if (EXACT) {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < A.n_rows) {
+        const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < row1) {
             double Ax = 0.;
             for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) Ax = __dadd_rn(Ax, __dmul_rn(A.val[k], x[A.col[k]]));
             const double ri = __dsub_rn(b[i], Ax);
@@ -194,8 +202,8 @@ k_amg_residual(CsrDev A, const double *__restrict__ x, const double *__restrict_
         }
     } else {
         const int lane = threadIdx.x & (kLanes - 1);
-        const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
-        const bool ok = i < A.n_rows;
+        const int i = row0 + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+        const bool ok = i < row1;
         double Ax = 0.;
         if (ok)
             for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) Ax += A.val[k] * x[A.col[k]];
@@ -224,18 +232,18 @@ k_amg_residual(CsrDev A, const double *__restrict__ x, const double *__restrict_
 // rows i in ascending order, which is the order in which the reference's scatter loop adds them
 template <bool EXACT>
 __global__ void __launch_bounds__(256)
-k_amg_spmv(CsrDev R, const double *__restrict__ xin, double *__restrict__ xout)
+k_amg_spmv(CsrDev R, const double *__restrict__ xin, double *__restrict__ xout, int row0, int row1)
 {
     if (EXACT) {
-        const int m = blockIdx.x * blockDim.x + threadIdx.x;
-        if (m >= R.n_rows) return;
+        const int m = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+        if (m >= row1) return;
         double s = 0.;
         for (int k = R.ptr[m]; k < R.ptr[m + 1]; ++k) s = __dadd_rn(s, __dmul_rn(R.val[k], xin[R.col[k]]));
         xout[m] = s;
     } else {
         const int lane = threadIdx.x & (kLanes - 1);
-        const int m = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
-        const bool ok = m < R.n_rows;
+        const int m = row0 + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+        const bool ok = m < row1;
         double s = 0.;
         if (ok)
             for (int k = R.ptr[m] + lane; k < R.ptr[m + 1]; k += kLanes) s += R.val[k] * xin[R.col[k]];
@@ -246,13 +254,29 @@ k_amg_spmv(CsrDev R, const double *__restrict__ xin, double *__restrict__ xout)
 
 // prolongation x_f += P x_c (AMG/src/AMG.cpp:218-232): the reference adds term by term INTO x_f[i]
 __global__ void __launch_bounds__(256)
-k_amg_prolong_add(CsrDev P, const double *__restrict__ xc, double *__restrict__ xf)
+k_amg_prolong_add(CsrDev P, const double *__restrict__ xc, double *__restrict__ xf, int row0, int row1)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_rows) return;
+    const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row1) return;
     double v = xf[i];
     for (int k = P.ptr[i]; k < P.ptr[i + 1]; ++k) v = __dadd_rn(v, __dmul_rn(P.val[k], xc[P.col[k]]));
     xf[i] = v;
+}
+
+// ---- ghost-entry exchange of a row-block sharded level (vectors keep GLOBAL indexing on every rank) -----------------
+// pack: buf[t] = v[idx[t]] for the entries peers need from this rank; unpack: v[idx[t]] = buf[t] for the ghost
+// entries this rank's rows reference.  The index lists are precomputed on the host (amg_solver.cu: halo_plan).
+__global__ void __launch_bounds__(256)
+k_amg_pack(const double *__restrict__ v, const int *__restrict__ idx, double *__restrict__ buf, int first, int last)
+{
+    const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < last) buf[t] = v[idx[t]];
+}
+__global__ void __launch_bounds__(256)
+k_amg_unpack(double *__restrict__ v, const int *__restrict__ idx, const double *__restrict__ buf, int first, int last)
+{
+    const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < last) v[idx[t]] = buf[t];
 }
 
 // ---- on-device greedy colouring (Jones-Plassmann rounds) ------------------------------------------------------------

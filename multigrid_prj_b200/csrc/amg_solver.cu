@@ -12,6 +12,7 @@
 // on the device.  (Device-side setup is the next item of SURVEY.md section 8f.)
 #include "../../include/mgb200.h"
 #include "amg_kernels.cuh"
+#include "nccl_dyn.h"
 
 #include <algorithm>
 #include <cmath>
@@ -28,6 +29,12 @@ namespace {
         cudaError_t e_ = (call);                                                              \
         if (e_ != cudaSuccess)                                                                \
             return mgb_set_error(MGB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define ANK(call)                                                                             \
+    do {                                                                                      \
+        int e_ = (call);                                                                      \
+        if (e_ != mgb::kNcclSuccess)                                                          \
+            return mgb_set_error(MGB_ERR_NCCL, std::string(#call) + ": " + mgb::nccl().GetErrorString(e_)); \
     } while (0)
 
 struct HostCsr {
@@ -178,6 +185,89 @@ HostCsr galerkin(const HostCsr &A, const HostCsr &P)
     return Ac;
 }
 
+// ---- row-block sharding ----------------------------------------------------------------------
+// rank r owns the entries [n r / R, n (r+1) / R) of a length-n index space (rows of an operator, entries of a vector)
+struct Block { int r0 = 0, r1 = 0; int size() const { return r1 - r0; } };
+inline Block block_of(int n, int n_ranks, int rank)
+{
+    Block b;
+    b.r0 = (int)((long long)n * rank / n_ranks);
+    b.r1 = (int)((long long)n * (rank + 1) / n_ranks);
+    return b;
+}
+inline int owner_of(int n, int n_ranks, int i)
+{
+    int r = (int)std::min<long long>((long long)i * n_ranks / std::max(n, 1), n_ranks - 1);
+    while (r + 1 < n_ranks && block_of(n, n_ranks, r + 1).r0 <= i) ++r;
+    while (r > 0 && block_of(n, n_ranks, r).r0 > i) --r;
+    return r;
+}
+
+// Ghost-exchange plan of operator M for one rank: which vector entries (columns of M, global indices) it must receive
+// because its rows reference them, and which of its own entries the other ranks' rows reference.  Ordered by
+// (group, peer, index) so that one group -- one colour of a multicolour sweep -- is a contiguous range of the lists.
+struct HaloPlan {
+    int n_groups = 1, n_ranks = 1;
+    std::vector<int> send_ptr, send_idx, recv_ptr, recv_idx;       // ptr: n_groups * n_ranks + 1
+    int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+    int n_send() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
+    int n_recv() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
+    bool empty() const { return n_send() == 0 && n_recv() == 0; }
+    void release() { cudaFree(d_send_idx); cudaFree(d_recv_idx); d_send_idx = d_recv_idx = nullptr; }
+};
+
+void order_segments(int n_groups, int n_ranks, int n_cols, const int *group_of_col, std::vector<int> &entries /* (index) */,
+                    const std::vector<int> &peer_of_entry, std::vector<int> &ptr, std::vector<int> &idx)
+{
+    const int n_seg = n_groups * n_ranks;
+    ptr.assign(n_seg + 1, 0);
+    auto seg_of = [&](size_t e) { return (group_of_col ? group_of_col[entries[e]] : 0) * n_ranks + peer_of_entry[e]; };
+    for (size_t e = 0; e < entries.size(); ++e) ptr[seg_of(e) + 1]++;
+    for (int q = 0; q < n_seg; ++q) ptr[q + 1] += ptr[q];
+    idx.assign(entries.size(), 0);
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (size_t e = 0; e < entries.size(); ++e) idx[fill[seg_of(e)]++] = entries[e];   // entries arrive ascending per peer
+    (void)n_cols;
+}
+
+HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_col, int n_groups)
+{
+    HaloPlan H;
+    H.n_groups = std::max(n_groups, 1); H.n_ranks = n_ranks;
+    const Block mine_rows = block_of(M.n_rows, n_ranks, rank), mine_cols = block_of(M.n_cols, n_ranks, rank);
+    std::vector<int> entries, peer;
+    // receive: columns outside my block that my rows reference (ascending, hence ascending per peer)
+    {
+        std::vector<unsigned char> need(M.n_cols, 0);
+        for (int i = mine_rows.r0; i < mine_rows.r1; ++i)
+            for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) {
+                const int j = M.col[k];
+                if (j < mine_cols.r0 || j >= mine_cols.r1) need[j] = 1;
+            }
+        for (int j = 0; j < M.n_cols; ++j) if (need[j]) { entries.push_back(j); peer.push_back(owner_of(M.n_cols, n_ranks, j)); }
+        order_segments(H.n_groups, n_ranks, M.n_cols, group_of_col, entries, peer, H.recv_ptr, H.recv_idx);
+    }
+    // send: my entries that the rows of rank q reference, q by q (the same ascending order q derives for its receive list)
+    {
+        entries.clear(); peer.clear();
+        std::vector<int> stamp(std::max(mine_cols.size(), 1), -1);
+        for (int q = 0; q < n_ranks; ++q) {
+            if (q == rank) continue;
+            const Block rows_q = block_of(M.n_rows, n_ranks, q);
+            std::vector<int> hit;
+            for (int i = rows_q.r0; i < rows_q.r1; ++i)
+                for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) {
+                    const int j = M.col[k];
+                    if (j >= mine_cols.r0 && j < mine_cols.r1 && stamp[j - mine_cols.r0] != q) { stamp[j - mine_cols.r0] = q; hit.push_back(j); }
+                }
+            std::sort(hit.begin(), hit.end());
+            for (int j : hit) { entries.push_back(j); peer.push_back(q); }
+        }
+        order_segments(H.n_groups, n_ranks, M.n_cols, group_of_col, entries, peer, H.send_ptr, H.send_idx);
+    }
+    return H;
+}
+
 struct DevCsr {
     int n_rows = 0, n_cols = 0, nnz = 0;
     int *ptr = nullptr, *col = nullptr;
@@ -210,6 +300,14 @@ struct AmgLevel {
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
     Schedule lex, colour;
     SellCopy sell;
+    // sharding: rows [own.r0, own.r1) of this level are smoothed here (the whole level when it is replicated)
+    bool sharded = false;
+    Block own;                                 // rows this rank works on
+    size_t own_nnz = 0;                        // entries of A in those rows
+    HaloPlan haloA, haloA_colour;              // ghosts of x for A (all at once / colour by colour)
+    HaloPlan haloR, haloP;                     // ghosts of the fine vector for R = P^T, of the coarse vector for P
+    Block own_c;                               // rows of R this rank computes (block of the next level)
+    bool x_halo_ok = true;                     // the ghost entries of x hold the owners' current values
 };
 
 }  // namespace
@@ -220,6 +318,10 @@ struct mgb_amg {
     cudaStream_t st = nullptr;
     double *d_partial = nullptr, *d_scal = nullptr, *h_scal = nullptr;
     mgb_gmg_stats stats{};
+    int rank = 0, n_ranks = 1;
+    mgb::NcclComm comm = nullptr;
+    double *d_send = nullptr, *d_recv = nullptr;      // packed ghost entries
+    double omega = 1.0;
 };
 
 namespace {
@@ -238,16 +340,17 @@ int upload(const HostCsr &H, DevCsr &D, cudaStream_t st)
     return MGB_OK;
 }
 
-int upload_schedule(const std::vector<int> &group_of_row, int n_groups, Schedule &S, cudaStream_t st)
+// group_of_row covers the whole level (queries, halo plans); the device row lists hold the rows [own.r0, own.r1) only
+int upload_schedule(const std::vector<int> &group_of_row, int n_groups, Schedule &S, cudaStream_t st, Block own)
 {
-    const int n = (int)group_of_row.size();
+    const int n = own.size();
     S.n_groups = n_groups;
     S.h_group = group_of_row;
     S.h_ptr.assign(n_groups + 1, 0);
-    for (int g : group_of_row) S.h_ptr[g + 1]++;
+    for (int i = own.r0; i < own.r1; ++i) S.h_ptr[group_of_row[i] + 1]++;
     for (int g = 0; g < n_groups; ++g) S.h_ptr[g + 1] += S.h_ptr[g];
     std::vector<int> rows(std::max(n, 1)), fill(S.h_ptr.begin(), S.h_ptr.end() - 1);
-    for (int i = 0; i < n; ++i) rows[fill[group_of_row[i]]++] = i;       // ascending inside a group
+    for (int i = own.r0; i < own.r1; ++i) rows[fill[group_of_row[i]]++] = i;       // ascending inside a group
     ACK(cudaMalloc(&S.d_ptr, sizeof(int) * (size_t)(n_groups + 1)));
     ACK(cudaMalloc(&S.d_rows, sizeof(int) * (size_t)std::max(n, 1)));
     ACK(cudaMemcpyAsync(S.d_ptr, S.h_ptr.data(), sizeof(int) * (size_t)(n_groups + 1), cudaMemcpyHostToDevice, st));
@@ -257,7 +360,7 @@ int upload_schedule(const std::vector<int> &group_of_row, int n_groups, Schedule
 }
 
 inline void tally(mgb_amg *h, double bytes) { h->stats.kernel_launches++; h->stats.bytes_algorithmic += bytes; }
-inline double sweep_bytes(const AmgLevel &L) { return 12. * L.A.nnz + 28. * L.A.n_rows; }
+inline double sweep_bytes(const AmgLevel &L) { return 12. * (double)L.own_nnz + 28. * L.own.size(); }   // SURVEY.md section 8d, rows of this rank
 
 // level schedule of the lexicographic sweep: wave(i) = 1 + max wave(j) over the couplings j < i
 int build_lex_schedule(mgb_amg *h, AmgLevel &L)
@@ -271,7 +374,7 @@ int build_lex_schedule(mgb_amg *h, AmgLevel &L)
         wave[i] = w;
         n_waves = std::max(n_waves, w + 1);
     }
-    return upload_schedule(wave, n_waves, L.lex, h->st);
+    return upload_schedule(wave, n_waves, L.lex, h->st, L.own);
 }
 
 // greedy colouring on the device (Jones-Plassmann rounds); the colour lists are then laid out on the host
@@ -299,20 +402,20 @@ int build_colouring(mgb_amg *h, AmgLevel &L)
     colour.resize(n);
     int nc = 0;
     for (int c : colour) { if (c < 0) return mgb_set_error(MGB_ERR_STATE, "colouring did not finish"); nc = std::max(nc, c + 1); }
-    return upload_schedule(colour, nc, L.colour, h->st);
+    return upload_schedule(colour, nc, L.colour, h->st, L.own);
 }
 
 // colour-sorted SELL-32 copy (off-diagonal entries) + slot-ordered diagonal and rhs
 int build_sell(mgb_amg *h, AmgLevel &L)
 {
     const HostCsr &A = L.hA;
-    const int n = A.n_rows, ncol = L.colour.n_groups;
+    const int ncol = L.colour.n_groups;
     SellCopy &S = L.sell;
     std::vector<int> row_of_slot;
     S.colour_slot_ptr.assign(ncol + 1, 0);
     {
         std::vector<std::vector<int>> by_colour(std::max(ncol, 1));
-        for (int i = 0; i < n; ++i) by_colour[L.colour.h_group[i]].push_back(i);
+        for (int i = L.own.r0; i < L.own.r1; ++i) by_colour[L.colour.h_group[i]].push_back(i);
         for (int c = 0; c < ncol; ++c) {
             S.colour_slot_ptr[c] = (int)row_of_slot.size();
             row_of_slot.insert(row_of_slot.end(), by_colour[c].begin(), by_colour[c].end());
@@ -364,12 +467,88 @@ int build_sell(mgb_amg *h, AmgLevel &L)
     return MGB_OK;
 }
 
+// ---- ghost exchange -----------------------------------------------------------------------------------------------
+int upload_plan(HaloPlan &H)
+{
+    if (H.n_send()) {
+        ACK(cudaMalloc(&H.d_send_idx, sizeof(int) * (size_t)H.n_send()));
+        ACK(cudaMemcpy(H.d_send_idx, H.send_idx.data(), sizeof(int) * (size_t)H.n_send(), cudaMemcpyHostToDevice));
+    }
+    if (H.n_recv()) {
+        ACK(cudaMalloc(&H.d_recv_idx, sizeof(int) * (size_t)H.n_recv()));
+        ACK(cudaMemcpy(H.d_recv_idx, H.recv_idx.data(), sizeof(int) * (size_t)H.n_recv(), cudaMemcpyHostToDevice));
+    }
+    return MGB_OK;
+}
+
+// refresh the ghost entries of `v` listed in groups [g0, g1) of the plan: pack -> grouped ncclSend/ncclRecv -> unpack,
+// all on the compute stream
+int exchange(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
+{
+    if (h->n_ranks == 1 || H.empty()) return MGB_OK;
+    const int R = H.n_ranks;
+    const int s0 = H.send_ptr[g0 * R], s1 = H.send_ptr[g1 * R], r0 = H.recv_ptr[g0 * R], r1 = H.recv_ptr[g1 * R];
+    // (every rank walks the same (group, peer) segments, so an empty range here is empty on the peers' side too
+    //  only segment by segment: the NCCL calls below are issued per non-empty segment)
+    if (s1 > s0) {
+        mgb::k_amg_pack<<<(s1 - s0 + 255) / 256, 256, 0, h->st>>>(v, H.d_send_idx, h->d_send, s0, s1);
+        tally(h, 12. * (s1 - s0));
+    }
+    auto &N = mgb::nccl();
+    if (s1 > s0 || r1 > r0) {
+        ANK(N.GroupStart());
+        for (int g = g0; g < g1; ++g)
+            for (int p = 0; p < R; ++p) {
+                const int q = g * R + p;
+                const int ns = H.send_ptr[q + 1] - H.send_ptr[q], nr = H.recv_ptr[q + 1] - H.recv_ptr[q];
+                if (ns) ANK(N.Send(h->d_send + H.send_ptr[q], (size_t)ns, mgb::kNcclFloat64, p, h->comm, h->st));
+                if (nr) ANK(N.Recv(h->d_recv + H.recv_ptr[q], (size_t)nr, mgb::kNcclFloat64, p, h->comm, h->st));
+            }
+        ANK(N.GroupEnd());
+    }
+    if (r1 > r0) {
+        mgb::k_amg_unpack<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, h->d_recv, r0, r1);
+        tally(h, 12. * (r1 - r0));
+    }
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+inline int exchange_all(mgb_amg *h, const HaloPlan &H, double *v) { return exchange(h, H, 0, H.n_groups, v); }
+
+// every rank contributes its block of a replicated level's vector (in place, grouped send/recv)
+int allgather_blocks(mgb_amg *h, int n, double *v)
+{
+    if (h->n_ranks == 1) return MGB_OK;
+    auto &N = mgb::nccl();
+    const Block mine = block_of(n, h->n_ranks, h->rank);
+    ANK(N.GroupStart());
+    for (int p = 0; p < h->n_ranks; ++p) {
+        if (p == h->rank) continue;
+        const Block theirs = block_of(n, h->n_ranks, p);
+        if (mine.size()) ANK(N.Send(v + mine.r0, (size_t)mine.size(), mgb::kNcclFloat64, p, h->comm, h->st));
+        if (theirs.size()) ANK(N.Recv(v + theirs.r0, (size_t)theirs.size(), mgb::kNcclFloat64, p, h->comm, h->st));
+    }
+    ANK(N.GroupEnd());
+    return MGB_OK;
+}
+
+inline int need_x_halo(mgb_amg *h, AmgLevel &L)
+{
+    if (L.x_halo_ok || !L.sharded) { L.x_halo_ok = true; return MGB_OK; }
+    if (int rc = exchange_all(h, L.haloA, L.x)) return rc;
+    L.x_halo_ok = true;
+    return MGB_OK;
+}
+
 int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
 {
     AmgLevel &L = h->lv[level];
     const mgb::CsrDev A = L.A.view();
     if (A.n_rows == 0 || sweeps <= 0) return MGB_OK;
+    const int rows = L.own.size();
+    int rc;
     if (kind == MGB_SMOOTH_GS_LEX) {
+        if (L.sharded) return mgb_set_error(MGB_ERR_ARG, "lexicographic Gauss-Seidel is sequential across row blocks: sharded levels take the multicolour or Jacobi smoother");
         if (A.n_rows <= (1 << 18)) {
             mgb::k_amg_gs_lex_cta<<<1, 1024, 0, h->st>>>(A, L.diag, L.x, L.b, L.lex.d_ptr, L.lex.d_rows, L.lex.n_groups, sweeps);
             tally(h, sweep_bytes(L) * sweeps);
@@ -382,26 +561,34 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
                 }
         }
     } else if (kind == MGB_SMOOTH_GS_RB) {            // multicolour Gauss-Seidel
-        for (int s = 0; s < sweeps; ++s)
+        if ((rc = need_x_halo(h, L))) return rc;
+        const bool per_colour = L.sharded && !h->cfg.hybrid_gs;
+        for (int s = 0; s < sweeps; ++s) {
             for (int c = 0; c < L.colour.n_groups; ++c) {
                 const int a = L.colour.h_ptr[c], b = L.colour.h_ptr[c + 1];
-                if (h->cfg.exact_order)
-                    mgb::k_amg_gs_rows_exact<<<(b - a + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
-                else {
+                if (h->cfg.exact_order) {
+                    if (b > a) mgb::k_amg_gs_rows_exact<<<(b - a + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.colour.d_rows, a, b);
+                } else {
                     const int p0 = L.sell.colour_slot_ptr[c], p1 = L.sell.colour_slot_ptr[c + 1];
                     if (p1 > p0)
-                        mgb::k_amg_sell<2><<<(p1 - p0 + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.x, nullptr, p0, p1);
+                        mgb::k_amg_sell<2><<<(p1 - p0 + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.x, nullptr, p0, p1, 1.0);
                 }
-                tally(h, sweep_bytes(L) * (double)(b - a) / A.n_rows);
+                if (rows) tally(h, sweep_bytes(L) * (double)(b - a) / rows);
+                // the rows of the next colours (here and on the peers) read this colour's new values
+                if (per_colour && (rc = exchange(h, L.haloA_colour, c, c + 1, L.x))) return rc;
             }
+            if (L.sharded && h->cfg.hybrid_gs && (rc = exchange_all(h, L.haloA, L.x))) return rc;
+        }
     } else if (kind == MGB_SMOOTH_JACOBI) {
+        if ((rc = need_x_halo(h, L))) return rc;
         for (int s = 0; s < sweeps; ++s) {
-            if (h->cfg.exact_order)
-                mgb::k_amg_jacobi_vec<<<(A.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp);
-            else
-                mgb::k_amg_sell<1><<<(L.sell.n_slots + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, nullptr, 0, L.sell.n_slots);
+            if (h->cfg.exact_order) {
+                if (rows) mgb::k_amg_jacobi_vec<<<(rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp, h->omega, L.own.r0, L.own.r1);
+            } else if (L.sell.n_slots)
+                mgb::k_amg_sell<1><<<(L.sell.n_slots + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, nullptr, 0, L.sell.n_slots, h->omega);
             tally(h, sweep_bytes(L));
             std::swap(L.x, L.tmp);
+            if (L.sharded && (rc = exchange_all(h, L.haloA, L.x))) return rc;      // the new iterate has no ghosts yet
         }
     } else
         return mgb_set_error(MGB_ERR_ARG, "unknown AMG smoother");
@@ -409,38 +596,66 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
     return MGB_OK;
 }
 
+// r = b - A x on this rank's rows into L.tmp, sum of squares into d_scal[0] (all ranks: the global sum)
+int residual_to_tmp(mgb_amg *h, AmgLevel &L, bool want_norm)
+{
+    const mgb::CsrDev A = L.A.view();
+    int rc, blocks;
+    if ((rc = need_x_halo(h, L))) return rc;
+    const int rows = L.own.size();
+    if (h->cfg.exact_order) {
+        blocks = (rows + 255) / 256;
+        if (blocks) mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial, L.own.r0, L.own.r1);
+    } else {
+        blocks = (L.sell.n_slots + 255) / 256;
+        if (blocks) mgb::k_amg_sell<0><<<blocks, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, h->d_partial, 0, L.sell.n_slots, 1.0);
+    }
+    tally(h, sweep_bytes(L));
+    if (want_norm) {
+        mgb::k_amg_reduce<<<1, 1024, 0, h->st>>>(h->d_partial, blocks, h->d_scal);
+        tally(h, 0.);
+        if (L.sharded) ANK(mgb::nccl().AllReduce(h->d_scal, h->d_scal, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+    }
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
 int do_residual(mgb_amg *h, int level, double *norm)
 {
     AmgLevel &L = h->lv[level];
-    const mgb::CsrDev A = L.A.view();
-    int blocks;
-    if (h->cfg.exact_order) {
-        blocks = (A.n_rows + 255) / 256;
-        mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial);
-    } else {
-        blocks = (L.sell.n_slots + 255) / 256;
-        mgb::k_amg_sell<0><<<blocks, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, h->d_partial, 0, L.sell.n_slots);
-    }
-    tally(h, sweep_bytes(L));
-    mgb::k_amg_reduce<<<1, 1024, 0, h->st>>>(h->d_partial, blocks, h->d_scal);
-    tally(h, 0.);
-    ACK(cudaGetLastError());
+    if (int rc = residual_to_tmp(h, L, true)) return rc;
     ACK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->st));
     ACK(cudaStreamSynchronize(h->st));
     *norm = std::sqrt(h->h_scal[0]);
     return MGB_OK;
 }
 
-// x_{level} = P^T x_{level-1}  (AMG.cpp:50-74)
-int do_restrict(mgb_amg *h, int level)
+// out_{level} = P^T in_{level-1} as a gather over R = P^T (AMG.cpp:50-74); `in` is the fine level's x or tmp
+int restrict_vec(mgb_amg *h, int level, double *in, double *out)
 {
     AmgLevel &F = h->lv[level - 1], &C = h->lv[level];
     const mgb::CsrDev R = F.R.view();
     if (R.n_rows == 0) return MGB_OK;
-    if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(R.n_rows + 255) / 256, 256, 0, h->st>>>(R, F.x, C.x);
-    else mgb::k_amg_spmv<false><<<(R.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, F.x, C.x);
-    tally(h, 12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols);
+    int rc;
+    if (F.sharded && (rc = exchange_all(h, F.haloR, in))) return rc;        // fine entries of other blocks my coarse rows gather
+    const int rows = F.own_c.size();
+    if (rows) {
+        if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(rows + 255) / 256, 256, 0, h->st>>>(R, in, out, F.own_c.r0, F.own_c.r1);
+        else mgb::k_amg_spmv<false><<<(rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, in, out, F.own_c.r0, F.own_c.r1);
+    }
+    const double share = R.n_rows ? (double)rows / R.n_rows : 0.;
+    tally(h, (12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols) * share);
     ACK(cudaGetLastError());
+    if (F.sharded && !C.sharded && (rc = allgather_blocks(h, R.n_rows, out))) return rc;   // first replicated level: whole on every rank
+    return MGB_OK;
+}
+
+// x_{level} = P^T x_{level-1}
+int do_restrict(mgb_amg *h, int level)
+{
+    AmgLevel &F = h->lv[level - 1], &C = h->lv[level];
+    if (int rc = restrict_vec(h, level, F.x, C.x)) return rc;
+    C.x_halo_ok = !C.sharded;
     return MGB_OK;
 }
 
@@ -450,9 +665,13 @@ int do_prolong(mgb_amg *h, int level)
     AmgLevel &F = h->lv[level], &C = h->lv[level + 1];
     const mgb::CsrDev P = F.P.view();
     if (P.n_rows == 0) return MGB_OK;
-    mgb::k_amg_prolong_add<<<(P.n_rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x);
-    tally(h, 12. * P.nnz + 20. * P.n_rows + 8. * P.n_cols);
+    int rc;
+    if (C.sharded && (rc = exchange_all(h, F.haloP, C.x))) return rc;        // coarse entries of other blocks my fine rows interpolate from
+    const int rows = F.own.size();
+    if (rows) mgb::k_amg_prolong_add<<<(rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x, F.own.r0, F.own.r1);
+    tally(h, (12. * P.nnz + 20. * P.n_rows + 8. * P.n_cols) * (P.n_rows ? (double)rows / P.n_rows : 0.));
     ACK(cudaGetLastError());
+    F.x_halo_ok = !F.sharded;
     return MGB_OK;
 }
 
@@ -470,6 +689,9 @@ void mgb_amg_config_default(mgb_amg_config *c)
     c->exact_order = 1;
     c->device = 0;
     for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
+    c->hybrid_gs = 0;
+    c->shard_min_rows = 16384;
+    c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
 }
 
 void mgb_amg_config_fast(mgb_amg_config *c)
@@ -482,10 +704,27 @@ void mgb_amg_config_fast(mgb_amg_config *c)
 int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
                             const double *val, const double *rhs, mgb_amg_t *out)
 {
+    return mgb_amg_create_sharded(cfg, n, ptr, col, val, rhs, 0, 1, nullptr, out);
+}
+
+int mgb_amg_partition(size_t n, int n_ranks, int rank, size_t *row0, size_t *rows)
+{
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n > (size_t)INT32_MAX || !row0 || !rows) return mgb_set_error(MGB_ERR_ARG, "bad partition arguments");
+    const Block b = block_of((int)n, n_ranks, rank);
+    *row0 = (size_t)b.r0; *rows = (size_t)b.size();
+    return MGB_OK;
+}
+
+int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
+                           const double *val, const double *rhs, int rank, int n_ranks,
+                           const unsigned char nccl_id[128], mgb_amg_t *out)
+{
     if (!cfg || !ptr || !col || !val || !rhs || !out) return mgb_set_error(MGB_ERR_ARG, "null argument");
     *out = nullptr;
     if (cfg->levels < 1 || cfg->levels > 16) return mgb_set_error(MGB_ERR_ARG, "1 <= levels <= 16");
     if (n == 0 || n > (size_t)1 << 30 || ptr[n] > (int64_t)INT32_MAX) return mgb_set_error(MGB_ERR_ARG, "matrix too large for int32 indices");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return mgb_set_error(MGB_ERR_ARG, "bad rank / n_ranks");
+    if (n_ranks > 1 && !nccl_id) return mgb_set_error(MGB_ERR_ARG, "n_ranks > 1 needs the ncclUniqueId of mgb_nccl_unique_id()");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -494,7 +733,17 @@ int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *
     ACK(cudaSetDevice(cfg->device));
     mgb_amg *h = new mgb_amg();
     h->cfg = *cfg;
+    h->rank = rank; h->n_ranks = n_ranks;
+    h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
+    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 16384;
     ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    if (n_ranks > 1) {
+        auto &Nc = mgb::nccl();
+        if (!Nc.load()) { delete h; return mgb_set_error(MGB_ERR_NCCL, Nc.error); }
+        mgb::NcclUniqueId id;
+        std::memcpy(&id, nccl_id, sizeof(id));
+        ANK(Nc.CommInitRank(&h->comm, n_ranks, id, rank));
+    }
     h->lv.resize(cfg->levels);
     // level 0: CSRMatrix::copy_from drops exact zeros (CSRMatrix.cpp:13-14); rows must be column-sorted (they come from a map)
     {
@@ -523,8 +772,17 @@ int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *
             for (int k = F.hP.ptr[i]; k < F.hP.ptr[i + 1]; ++k) C.h_rhs[F.hP.col[k]] += F.hP.val[k] * F.h_rhs[i];
         C.hA = galerkin(F.hA, F.hP);
     }
+    // which levels are cut into row blocks, and the rows of every level this rank works on
+    for (int l = 0; l < cfg->levels; ++l) {
+        AmgLevel &L = h->lv[l];
+        const int nl = L.hA.n_rows;
+        L.sharded = n_ranks > 1 && (long long)nl >= (long long)min_rows * n_ranks && (l == 0 || h->lv[l - 1].sharded);
+        L.own = L.sharded ? block_of(nl, n_ranks, rank) : Block{0, nl};
+        L.own_nnz = (size_t)(L.hA.ptr[L.own.r1] - L.hA.ptr[L.own.r0]);
+        L.x_halo_ok = true;                                   // x = 0 everywhere
+    }
     // upload
-    size_t max_blocks = 1;
+    size_t max_blocks = 1, max_halo = 1;
     for (int l = 0; l < cfg->levels; ++l) {
         AmgLevel &L = h->lv[l];
         const int nl = L.hA.n_rows;
@@ -536,6 +794,7 @@ int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *
         ACK(cudaMalloc(&L.diag, bytes)); ACK(cudaMalloc(&L.x, bytes)); ACK(cudaMalloc(&L.b, bytes)); ACK(cudaMalloc(&L.tmp, bytes));
         ACK(cudaMemcpyAsync(L.diag, dg.data(), bytes, cudaMemcpyHostToDevice, h->st));
         ACK(cudaMemsetAsync(L.x, 0, bytes, h->st));
+        ACK(cudaMemsetAsync(L.tmp, 0, bytes, h->st));
         if (nl) ACK(cudaMemcpyAsync(L.b, L.h_rhs.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, h->st));
         ACK(cudaStreamSynchronize(h->st));
         if (l + 1 < cfg->levels) {
@@ -543,11 +802,35 @@ int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *
             HostCsr R = transpose(L.hP);
             if ((rc = upload(R, L.R, h->st))) return rc;
             ACK(cudaStreamSynchronize(h->st));
+            const AmgLevel &C = h->lv[l + 1];
+            // rows of R this rank gathers: its block of the coarse level whenever the fine level is sharded (a replicated
+            // coarse level is then completed by an all-gather), everything otherwise
+            L.own_c = L.sharded ? block_of(R.n_rows, n_ranks, rank) : Block{0, R.n_rows};
+            if (L.sharded) {
+                L.haloR = halo_plan(R, n_ranks, rank, nullptr, 1);
+                if ((rc = upload_plan(L.haloR))) return rc;
+                if (C.sharded) {
+                    L.haloP = halo_plan(L.hP, n_ranks, rank, nullptr, 1);
+                    if ((rc = upload_plan(L.haloP))) return rc;
+                }
+                max_halo = std::max<size_t>(max_halo, std::max({L.haloR.n_send(), L.haloR.n_recv(), L.haloP.n_send(), L.haloP.n_recv()}));
+            }
         }
         if ((rc = build_lex_schedule(h, L))) return rc;
-        if ((rc = build_colouring(h, L))) return rc;
+        if ((rc = build_colouring(h, L))) return rc;       // on the whole graph: every rank derives the same colours
         if ((rc = build_sell(h, L))) return rc;
+        if (L.sharded) {
+            L.haloA = halo_plan(L.hA, n_ranks, rank, nullptr, 1);
+            L.haloA_colour = halo_plan(L.hA, n_ranks, rank, L.colour.h_group.data(), L.colour.n_groups);
+            if ((rc = upload_plan(L.haloA))) return rc;
+            if ((rc = upload_plan(L.haloA_colour))) return rc;
+            max_halo = std::max<size_t>(max_halo, std::max(L.haloA.n_send(), L.haloA.n_recv()));
+        }
         max_blocks = std::max(max_blocks, (size_t)(nl * mgb::kLanes + 255) / 256 + 1);
+    }
+    if (n_ranks > 1) {
+        ACK(cudaMalloc(&h->d_send, sizeof(double) * max_halo));
+        ACK(cudaMalloc(&h->d_recv, sizeof(double) * max_halo));
     }
     ACK(cudaMalloc(&h->d_partial, sizeof(double) * max_blocks));
     ACK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
@@ -563,9 +846,11 @@ void mgb_amg_destroy(mgb_amg_t h)
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &L : h->lv) {
         L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release();
+        L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
     }
-    cudaFree(h->d_partial); cudaFree(h->d_scal);
+    cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFree(h->d_send); cudaFree(h->d_recv);
+    if (h->comm) mgb::nccl().CommDestroy(h->comm);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -582,6 +867,16 @@ int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t 
     if (n_coarse) *n_coarse = (size_t)L.hP.n_cols;
     if (n_waves) *n_waves = L.lex.n_groups;
     if (n_colours) *n_colours = L.colour.n_groups;
+    return MGB_OK;
+}
+
+int mgb_amg_level_rows(mgb_amg_t h, int level, size_t *row0, size_t *rows, int *sharded)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "bad level");
+    const AmgLevel &L = h->lv[level];
+    if (row0) *row0 = (size_t)L.own.r0;
+    if (rows) *rows = (size_t)L.own.size();
+    if (sharded) *sharded = L.sharded ? 1 : 0;
     return MGB_OK;
 }
 
@@ -623,6 +918,7 @@ int mgb_amg_set_vector(mgb_amg_t h, int level, int which, const double *host)
     ACK(cudaSetDevice(h->cfg.device));
     if (L.A.n_rows) ACK(cudaMemcpyAsync(which == 0 ? L.x : L.b, host, sizeof(double) * (size_t)L.A.n_rows, cudaMemcpyHostToDevice, h->st));
     ACK(cudaStreamSynchronize(h->st));
+    if (which == 0) L.x_halo_ok = true;            // every rank passes the whole vector: ghosts included
     if (which == 1 && L.sell.n_slots) {           // keep the slot-ordered copy of the right-hand side in step
         std::vector<int> ros(L.sell.n_slots);
         ACK(cudaMemcpy(ros.data(), L.sell.row_of_slot, sizeof(int) * (size_t)L.sell.n_slots, cudaMemcpyDeviceToHost));
@@ -703,22 +999,15 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
         for (int l = 0; l < L - 1; ++l) {                                  // downward
             AmgLevel &F = h->lv[l], &C = h->lv[l + 1];
             if (nu1 > 0 && (rc = do_smooth(h, l, kind, nu1))) return rc;
-            {   // r = b - A x into F.tmp (no host read-back)
-                const mgb::CsrDev A = F.A.view();
-                if (h->cfg.exact_order) mgb::k_amg_residual<true><<<(A.n_rows + 255) / 256, 256, 0, h->st>>>(A, F.x, F.b, F.tmp, h->d_partial);
-                else mgb::k_amg_sell<0><<<(F.sell.n_slots + 255) / 256, 256, 0, h->st>>>(F.sell.view(), F.x, F.sell.b_s, F.tmp, h->d_partial, 0, F.sell.n_slots);
-                tally(h, sweep_bytes(F));
-            }
-            const mgb::CsrDev R = F.R.view();                              // b_c = P^T r
-            if (R.n_rows) {
-                if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(R.n_rows + 255) / 256, 256, 0, h->st>>>(R, F.tmp, C.b);
-                else mgb::k_amg_spmv<false><<<(R.n_rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, F.tmp, C.b);
-                tally(h, 12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols);
+            if ((rc = residual_to_tmp(h, F, false))) return rc;               // r = b - A x into F.tmp (no host read-back)
+            if (F.R.n_rows) {                                                  // b_c = P^T r, x_c = 0
+                if ((rc = restrict_vec(h, l + 1, F.tmp, C.b))) return rc;
                 if (C.sell.n_slots) {
                     mgb::k_amg_to_slots<<<(C.sell.n_slots + 255) / 256, 256, 0, h->st>>>(C.sell.row_of_slot, C.sell.n_slots, C.b, C.sell.b_s);
-                    tally(h, 16. * C.A.n_rows);
+                    tally(h, 16. * C.own.size());
                 }
                 ACK(cudaMemsetAsync(C.x, 0, sizeof(double) * (size_t)C.A.n_rows, h->st));
+                C.x_halo_ok = true;
             }
             ACK(cudaGetLastError());
         }
@@ -806,6 +1095,23 @@ int mgb_amg_build_coarse_matrix(mgb_csr_t A, mgb_csr_t P, mgb_csr_t *Ac)
     mgb_csr *c = new mgb_csr();
     c->m = galerkin(A->m, P->m);
     *Ac = c;
+    return MGB_OK;
+}
+
+// host-only view of the ghost-exchange plan (what mgb_amg_create_sharded builds for A, R and P of every sharded level)
+int mgb_amg_halo_plan(mgb_csr_t M, int n_ranks, int rank, const int *group_of_col, int n_groups,
+                      int64_t *send_ptr, int64_t *send_idx, int64_t *recv_ptr, int64_t *recv_idx)
+{
+    if (!M || n_ranks < 1 || rank < 0 || rank >= n_ranks || !send_ptr || !recv_ptr) return mgb_set_error(MGB_ERR_ARG, "bad halo-plan arguments");
+    if (!group_of_col) n_groups = 1;
+    if (n_groups < 1) return mgb_set_error(MGB_ERR_ARG, "n_groups < 1");
+    if (group_of_col)
+        for (int j = 0; j < M->m.n_cols; ++j)
+            if (group_of_col[j] < 0 || group_of_col[j] >= n_groups) return mgb_set_error(MGB_ERR_ARG, "group_of_col out of range");
+    const HaloPlan H = halo_plan(M->m, n_ranks, rank, group_of_col, n_groups);
+    for (size_t q = 0; q < H.send_ptr.size(); ++q) { send_ptr[q] = H.send_ptr[q]; recv_ptr[q] = H.recv_ptr[q]; }
+    if (send_idx) for (size_t t = 0; t < H.send_idx.size(); ++t) send_idx[t] = H.send_idx[t];
+    if (recv_idx) for (size_t t = 0; t < H.recv_idx.size(); ++t) recv_idx[t] = H.recv_idx[t];
     return MGB_OK;
 }
 

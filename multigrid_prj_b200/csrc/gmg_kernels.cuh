@@ -116,7 +116,7 @@ __device__ __forceinline__ bool on_bdry(const LevelGeom &g, int gi, int j)
 
 // ---- Jacobi sweep, out of place (solvers.hpp:64-83; the reference writes `temp` then swaps) --
 __global__ void __launch_bounds__(kTPB)
-k_jacobi(LevelGeom g, const double *__restrict__ u, const double *__restrict__ b, double *__restrict__ out)
+k_jacobi(LevelGeom g, const double *__restrict__ u, const double *__restrict__ b, double *__restrict__ out, double omega)
 {
     March m(g);
     if (m.i0 >= g.rows) return;
@@ -133,6 +133,10 @@ k_jacobi(LevelGeom g, const double *__restrict__ u, const double *__restrict__ b
         double2 o;
         o.x = on_bdry(g, gi, m.j0) ? bb.x : smooth_point(bb.x, up.x, left, ce.y, dn.x, g.off, g.diag);
         o.y = on_bdry(g, gi, m.j0 + 1) ? bb.y : smooth_point(bb.y, up.y, ce.x, right, dn.y, g.off, g.diag);
+        if (omega != 1.) {                  // weighted Jacobi (north_star); the reference is omega = 1 (solvers.hpp:64-83)
+            if (!on_bdry(g, gi, m.j0)) o.x = ce.x + omega * (o.x - ce.x);
+            if (!on_bdry(g, gi, m.j0 + 1)) o.y = ce.y + omega * (o.y - ce.y);
+        }
         if (m.has1) st2(out + (size_t)i * P + m.j0, o);
         else if (m.has0) out[(size_t)i * P + m.j0] = o.x;
         up = ce; ce = dn;

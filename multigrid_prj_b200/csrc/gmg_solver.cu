@@ -341,7 +341,7 @@ int do_smooth(mgb_gmg *h, int level, int kind, int sweeps, double **sol, const d
     for (int s = 0; s < sweeps; ++s) {
         if (kind == MGB_SMOOTH_JACOBI) {
             if ((rc = halo_exchange(h, level, *sol, 1))) return rc;
-            mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, scratch);
+            mgb::k_jacobi<<<grid, mgb::kTPB, 0, h->st>>>(g, *sol, rhs, scratch, h->cfg.jacobi_omega);
             count(h, 24. * npts(g));
             std::swap(*sol, scratch);                               // solvers.hpp:83 sol.swap(temp)
         } else if (kind == MGB_SMOOTH_GS_RB && h->cfg.rb_fused) {
@@ -944,6 +944,7 @@ void mgb_gmg_config_default(mgb_gmg_config *c)
     c->tail_max_width = 129; c->use_graph = 1;
     c->rb_fast_arith = 0; c->rb_fused = 1; c->fuse_correction = 0; c->fuse_residual = 0; c->fuse_prolong = 0;
     c->tail_max_width = 65;
+    c->jacobi_omega = 1.0;                                              // solvers.hpp:64-83: unweighted
 }
 
 void mgb_gmg_config_fast(mgb_gmg_config *c)
@@ -1040,7 +1041,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     }
     // persistent coarse tail: every level from lt down (side <= tail_max_width, replicated, at most 12 levels)
     h->lt = -1;
-    if (cfg->tail_max_width > 0) {
+    if (!(h->cfg.jacobi_omega > 0.)) h->cfg.jacobi_omega = 1.0;           // zero-filled structs: the reference's omega
+    if (cfg->tail_max_width > 0 && h->cfg.jacobi_omega == 1.0) {          // the tail kernel implements the reference's unweighted Jacobi only
         for (int l = 0; l < L; ++l)
             if (h->lv[l].g.w <= cfg->tail_max_width && !h->lv[l].sharded && L - l <= mgb::kTailMaxLevels) { h->lt = l; break; }
     }

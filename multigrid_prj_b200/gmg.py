@@ -40,6 +40,7 @@ class GmgConfig:
     fuse_correction: int = 0
     fuse_residual: int = 0
     fuse_prolong: int = 0
+    jacobi_omega: float = 1.0
 
     @staticmethod
     def fast(n, levels, **kw):
@@ -76,7 +77,8 @@ class Gmg:
         self.lib.mgb_gmg_config_default(C.byref(c))
         for k in ("n", "levels", "length", "alpha", "smoother", "pre_smoother", "n_pre", "nu",
                   "restriction", "coarse_tol", "coarse_maxit", "device", "rank", "n_ranks",
-                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong"):
+                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong",
+                  "jacobi_omega"):
             setattr(c, k, getattr(cfg, k))
         if cfg.nccl_id:
             C.memmove(c.nccl_id, cfg.nccl_id, min(128, len(cfg.nccl_id)))

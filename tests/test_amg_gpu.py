@@ -164,3 +164,27 @@ def test_amg_argument_errors():
             a.restrict(0)                     # level 0 cannot be restricted to (AMG.cpp:54-57)
     with pytest.raises(MgbError):
         Amg(A.ptr, A.col[::-1].copy(), A.val, c["rhs"][0], levels=2)
+
+
+def test_weighted_jacobi_against_numpy():
+    """north_star: weighted Jacobi.  x <- x + omega (D^-1 (b - (A - D) x) - x); omega = 1 is the reference's
+    unweighted update and stays bit-identical to the unweighted kernel"""
+    c = load_case("mesh1")
+    A, b = c["A"][0], c["rhs"][0]
+    S = A.to_scipy().tocsr()
+    d = S.diagonal()
+    x0 = np.random.default_rng(4).standard_normal(A.n_rows)
+    for exact in (1, 0):
+        for omega in (1.0, 0.8, 2.0 / 3.0):
+            with Amg(A.ptr, A.col, A.val, b, levels=2, exact_order=exact, jacobi_omega=omega) as a:
+                a.set_vector(0, 0, x0)
+                a.smooth(0, M.JACOBI, 3)
+                x = a.vector(0, 0)
+            ref = x0.copy()
+            for _ in range(3):
+                xhat = (b - (S @ ref - d * ref)) / d
+                ref = xhat if omega == 1.0 else ref + omega * (xhat - ref)
+            assert np.allclose(x, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), (exact, omega)
+    # a single-GPU handle reports every level as whole and unsharded
+    with Amg(A.ptr, A.col, A.val, b, levels=2) as a:
+        assert a.rows(0) == (0, A.n_rows, False)

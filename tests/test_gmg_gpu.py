@@ -295,3 +295,38 @@ def test_argument_errors():
             g.cycle()                          # no rhs yet
         with pytest.raises(MgbError):
             g.prolong(2)
+
+
+@pytest.mark.parametrize("omega", [0.8, 2.0 / 3.0])
+def test_weighted_jacobi(orc, omega):
+    """north_star: weighted Jacobi.  u <- u + omega (u_J - u) with u_J the reference's sweep (solvers.hpp:64-83);
+    omega = 1 is covered bit for bit by test_sweeps_bit_exact_per_level.  Checked against the oracle's unweighted sweep
+    combined on the host, per level, and as the smoother of a converging solve (damped Jacobi smooths where the
+    reference's omega = 1 does not damp the highest frequency)."""
+    N, L = 129, 4
+    rng = np.random.default_rng(21)
+    u0, b0 = rng.standard_normal(N * N), rng.standard_normal(N * N)
+    with Gmg(GmgConfig(n=N, levels=L, jacobi_omega=omega)) as g:
+        for level in range(L):
+            s = 2 ** level
+            g.set_level(level, G.VEC_E, strided(u0, N, s))
+            g.set_level(level, G.VEC_R, strided(b0, N, s))
+            g.smooth(level, G.JACOBI, sweeps=2)
+            got = g.get_level(level, G.VEC_E)
+            ref = u0.copy()
+            for _ in range(2):
+                uj = ref.copy()
+                orc.sweep(oracle.JACOBI, N, W, 1.0, level, uj, b0)
+                new = ref + omega * (uj - ref)
+                w = (N - 1) // s + 1
+                m = np.zeros((w, w), bool); m[0, :] = m[-1, :] = m[:, 0] = m[:, -1] = True       # boundary rows: u = b
+                new_l, uj_l = strided(new, N, s).reshape(w, w), strided(uj, N, s).reshape(w, w)
+                new_l[m] = uj_l[m]
+                ref = ref.copy()
+                ref.reshape(N, N)[::s, ::s] = new_l
+            assert np.allclose(got, strided(ref, N, s), rtol=1e-13, atol=1e-13), level
+    b = orc.rhs(N, W, 1)
+    with Gmg(GmgConfig(n=N, levels=L, smoother=G.JACOBI, jacobi_omega=omega)) as g:
+        g.set_rhs(b.reshape(N, N)); g.set_u(None)
+        hist = g.solve()
+    assert hist[-1] <= 1e-11 and hist.size <= 60, hist
