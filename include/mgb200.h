@@ -198,7 +198,14 @@ typedef struct mgb_amg_config {
                               levels are replicated on every rank (<= 0: 16384) */
     double jacobi_omega;   /* MGB_SMOOTH_JACOBI: x <- x + omega (D^-1 (b - (A - D) x) - x); the reference is omega = 1
                               (<= 0 is read as 1) */
-    int reserved[4];
+    int tail_max_rows;     /* north_star item 3: the trailing levels whose row count is <= this (and that are not sharded)
+                              run inside ONE persistent single-CTA kernel per pass / cycle (mgb_amg_apply, mgb_amg_solve)
+                              instead of one launch per colour and transfer; results are unchanged.
+                              0: default (4000: measured optimum on B200, profiles/r01_amg_scale_1gpu_4M_tailsweep.json), < 0: off */
+    int cycle_graph;       /* mgb_amg_solve: 0 (default) = one cycle (all launches, ghost exchanges and the norm) is captured
+                              in a CUDA graph once and replayed -- the coarse levels are launch-latency bound; < 0: off.
+                              (Jacobi swaps buffers every sweep and always runs uncaptured.) */
+    int reserved[2];
 } mgb_amg_config;
 
 typedef struct mgb_amg *mgb_amg_t;

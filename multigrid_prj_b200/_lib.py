@@ -35,7 +35,8 @@ class AmgConfigStruct(C.Structure):
     _fields_ = [("levels", C.c_int), ("eps", C.c_double), ("smoother", C.c_int), ("pre_sweeps", C.c_int),
                 ("coarse_sweeps", C.c_int), ("post_sweeps", C.c_int), ("exact_order", C.c_int), ("device", C.c_int),
                 ("start_index", C.c_int64 * 16), ("hybrid_gs", C.c_int), ("shard_min_rows", C.c_int),
-                ("jacobi_omega", C.c_double), ("reserved", C.c_int * 4)]
+                ("jacobi_omega", C.c_double), ("tail_max_rows", C.c_int), ("cycle_graph", C.c_int),
+                ("reserved", C.c_int * 2)]
 
 
 # every symbol include/mgb200.h declares: name -> (restype, argtypes)

@@ -36,8 +36,8 @@ __device__ __forceinline__ double subwarp_sum(double v)
 }
 
 // ---- Gauss-Seidel row update, reference order (AMG/include/Utilities.hpp:44-58) --------------------------
-__device__ __forceinline__ void gs_row_exact(const CsrDev &A, const double *__restrict__ diag, double *x,
-                                             const double *__restrict__ b, int i)
+// (plain pointers: the tail kernel of amg_tail.cuh calls these row functions on vectors it also writes)
+__device__ __forceinline__ void gs_row_exact(const CsrDev &A, const double *diag, double *x, const double *b, int i)
 {
     double sum = 0.;
     for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
@@ -45,6 +45,68 @@ __device__ __forceinline__ void gs_row_exact(const CsrDev &A, const double *__re
         if (j != i) sum = __dadd_rn(sum, __dmul_rn(A.val[k], x[j]));
     }
     x[i] = __ddiv_rn(__dsub_rn(b[i], sum), diag[i]);
+}
+
+// ---- row functions shared by the per-level kernels and the persistent tail (amg_tail.cuh) ------------------------------
+// fast arithmetic, one thread per row: off-diagonal entries in ascending column order, fused multiply-add -- the
+// operation sequence of the SELL kernels below
+__device__ __forceinline__ double offdiag_dot_fast(const CsrDev &A, const double *x, int i)
+{
+    double sum = 0.;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        const int j = A.col[k];
+        if (j != i) sum += A.val[k] * x[j];
+    }
+    return sum;
+}
+// kLanes lanes per row (lane l takes entries l, l + kLanes, ...), tree reduction; every lane of the warp must call
+__device__ __forceinline__ double offdiag_dot_vec(const CsrDev &A, const double *x, int i, int lane, bool ok)
+{
+    double sum = 0.;
+    if (ok)
+        for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) {
+            const int j = A.col[k];
+            if (j != i) sum += A.val[k] * x[j];
+        }
+    return subwarp_sum(sum);
+}
+__device__ __forceinline__ double row_dot_vec(const CsrDev &A, const double *x, int i, int lane, bool ok)
+{
+    double sum = 0.;
+    if (ok)
+        for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) sum += A.val[k] * x[A.col[k]];
+    return subwarp_sum(sum);
+}
+// one thread per row, every entry in ascending column order, fused multiply-add (k_amg_sell<3>)
+__device__ __forceinline__ double row_dot_fast(const CsrDev &A, const double *x, int i)
+{
+    double sum = 0.;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) sum += A.val[k] * x[A.col[k]];
+    return sum;
+}
+// reference order, unfused IEEE operations
+__device__ __forceinline__ double residual_row_exact(const CsrDev &A, const double *x, const double *b, int i)
+{
+    double Ax = 0.;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) Ax = __dadd_rn(Ax, __dmul_rn(A.val[k], x[A.col[k]]));
+    return __dsub_rn(b[i], Ax);
+}
+__device__ __forceinline__ double spmv_row_exact(const CsrDev &R, const double *xin, int m)
+{
+    double s = 0.;
+    for (int k = R.ptr[m]; k < R.ptr[m + 1]; ++k) s = __dadd_rn(s, __dmul_rn(R.val[k], xin[R.col[k]]));
+    return s;
+}
+// x_f[i] += sum_k P(i,k) x_c[k], term by term INTO x_f[i] as the reference does (AMG/src/AMG.cpp:218-232)
+__device__ __forceinline__ void prolong_row_add(const CsrDev &P, const double *xc, double *xf, int i)
+{
+    double v = xf[i];
+    for (int k = P.ptr[i]; k < P.ptr[i + 1]; ++k) v = __dadd_rn(v, __dmul_rn(P.val[k], xc[P.col[k]]));
+    xf[i] = v;
+}
+__device__ __forceinline__ double relax(double xhat, double xold, double omega)
+{
+    return omega == 1. ? xhat : xold + omega * (xhat - xold);
 }
 
 // rows[first..last) are mutually independent (one wavefront of the level schedule, or one colour)
@@ -91,11 +153,6 @@ k_amg_gs_color_vec(CsrDev A, const double *__restrict__ diag, double *x, const d
 
 // weighted Jacobi: xhat = (b - sum_{j != i} a_ij x_j) / a_ii, xnew = x + omega (xhat - x); omega == 1 stores xhat itself
 // (the reference's smoothers are unweighted).  Rows [row0, row1): the block this rank owns.
-__device__ __forceinline__ double relax(double xhat, double xold, double omega)
-{
-    return omega == 1. ? xhat : xold + omega * (xhat - xold);
-}
-
 __global__ void __launch_bounds__(256)
 k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__restrict__ x, const double *__restrict__ b,
                  double *__restrict__ xnew, double omega, int row0, int row1)
@@ -103,13 +160,7 @@ k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__rest
     const int lane = threadIdx.x & (kLanes - 1);
     const int i = row0 + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
     const bool ok = i < row1;
-    double sum = 0.;
-    if (ok)
-        for (int k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += kLanes) {
-            const int j = A.col[k];
-            if (j != i) sum += A.val[k] * x[j];
-        }
-    sum = subwarp_sum(sum);
+    const double sum = offdiag_dot_vec(A, x, ok ? i : 0, lane, ok);
     if (ok && lane == 0) xnew[i] = relax((b[i] - sum) / diag[i], x[i], omega);
 }
 
@@ -129,8 +180,12 @@ struct SellDev {
     const double *diag_s, *b_s;  // diagonal and right-hand side in slot order
 };
 
+// The operator stream (col, val, diag, rhs, row map) is read exactly once per launch: it is loaded with the streaming
+// (evict-first) hint so that it does not push the vector x -- gathered ~7 times per sweep, once from every colour --
+// out of the 126 MB L2.  ncu before the hint: 793 MB of DRAM traffic for a 447 MB (algorithmic) Jacobi sweep, L2 hit
+// rate 25 % (profiles/r01_ncu_amg_ops_4M.txt).
 // MODE 0: r = b - A x (+ sum r^2 per CTA); MODE 1: Jacobi into `out`; MODE 2: Gauss-Seidel on the slots
-// [first, last) of one colour, in place on x
+// [first, last) of one colour, in place on x; MODE 3: plain product out[row] = sum (restriction, R = P^T)
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *out, double *__restrict__ partial,
@@ -140,23 +195,27 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
     const int p = first + blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0.;
     if (p < last) {
-        const int i = A.row_of_slot[p];
+        const int i = __ldcs(A.row_of_slot + p);
         if (i >= 0) {
             const int s = p >> 5;
-            const int base = A.slice_ptr[s] + (p & 31);
-            const int len = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
+            const int b0 = A.slice_ptr[s];
+            const int base = b0 + (p & 31);
+            const int len = (A.slice_ptr[s + 1] - b0) >> 5;
             double sum = 0.;
 #pragma unroll 4
-            for (int k = 0; k < len; ++k) sum += A.val[base + 32 * k] * x[A.col[base + 32 * k]];
-            const double d = A.diag_s[p], bi = b_s[p];
-            if (MODE == 0) {
-                const double ri = bi - (sum + d * x[i]);
-                if (out) out[i] = ri;
-                acc = ri * ri;
-            } else if (MODE == 1)
-                out[i] = relax((bi - sum) / d, x[i], omega);
-            else
-                out[i] = (bi - sum) / d;
+            for (int k = 0; k < len; ++k) sum += __ldcs(A.val + base + 32 * k) * x[__ldcs(A.col + base + 32 * k)];
+            if (MODE == 3) out[i] = sum;
+            else {
+                const double d = __ldcs(A.diag_s + p), bi = __ldcs(b_s + p);
+                if (MODE == 0) {
+                    const double ri = bi - (sum + d * x[i]);
+                    if (out) out[i] = ri;
+                    acc = ri * ri;
+                } else if (MODE == 1)
+                    out[i] = relax((bi - sum) / d, x[i], omega);
+                else
+                    out[i] = (bi - sum) / d;
+            }
         }
     }
     if (MODE == 0) {
@@ -194,9 +253,7 @@ k_amg_residual(CsrDev A, const double *__restrict__ x, const double *__restrict_
     if (EXACT) {
         const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
         if (i < row1) {
-            double Ax = 0.;
-            for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) Ax = __dadd_rn(Ax, __dmul_rn(A.val[k], x[A.col[k]]));
-            const double ri = __dsub_rn(b[i], Ax);
+            const double ri = residual_row_exact(A, x, b, i);
             if (r) r[i] = ri;
             acc = ri * ri;
         }
@@ -237,17 +294,12 @@ k_amg_spmv(CsrDev R, const double *__restrict__ xin, double *__restrict__ xout, 
     if (EXACT) {
         const int m = row0 + blockIdx.x * blockDim.x + threadIdx.x;
         if (m >= row1) return;
-        double s = 0.;
-        for (int k = R.ptr[m]; k < R.ptr[m + 1]; ++k) s = __dadd_rn(s, __dmul_rn(R.val[k], xin[R.col[k]]));
-        xout[m] = s;
+        xout[m] = spmv_row_exact(R, xin, m);
     } else {
         const int lane = threadIdx.x & (kLanes - 1);
         const int m = row0 + (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
         const bool ok = m < row1;
-        double s = 0.;
-        if (ok)
-            for (int k = R.ptr[m] + lane; k < R.ptr[m + 1]; k += kLanes) s += R.val[k] * xin[R.col[k]];
-        s = subwarp_sum(s);
+        const double s = row_dot_vec(R, xin, ok ? m : 0, lane, ok);
         if (ok && lane == 0) xout[m] = s;
     }
 }
@@ -258,9 +310,7 @@ k_amg_prolong_add(CsrDev P, const double *__restrict__ xc, double *__restrict__ 
 {
     const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row1) return;
-    double v = xf[i];
-    for (int k = P.ptr[i]; k < P.ptr[i + 1]; ++k) v = __dadd_rn(v, __dmul_rn(P.val[k], xc[P.col[k]]));
-    xf[i] = v;
+    prolong_row_add(P, xc, xf, i);
 }
 
 // ---- ghost-entry exchange of a row-block sharded level (vectors keep GLOBAL indexing on every rank) -----------------

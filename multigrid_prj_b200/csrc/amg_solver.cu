@@ -12,6 +12,7 @@
 // on the device.  (Device-side setup is the next item of SURVEY.md section 8f.)
 #include "../../include/mgb200.h"
 #include "amg_kernels.cuh"
+#include "amg_tail.cuh"
 #include "nccl_dyn.h"
 
 #include <algorithm>
@@ -299,7 +300,7 @@ struct AmgLevel {
     DevCsr A, P, R;
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
     Schedule lex, colour;
-    SellCopy sell;
+    SellCopy sell, sellR;                      // fast-path copies of A (colour-sorted) and of this rank's rows of R
     // sharding: rows [own.r0, own.r1) of this level are smoothed here (the whole level when it is replicated)
     bool sharded = false;
     Block own;                                 // rows this rank works on
@@ -322,6 +323,11 @@ struct mgb_amg {
     mgb::NcclComm comm = nullptr;
     double *d_send = nullptr, *d_recv = nullptr;      // packed ghost entries
     double omega = 1.0;
+    int lt = -1;                                      // first level of the persistent coarse tail (-1: none)
+    // one correction-scheme cycle captured as a CUDA graph (per sweep counts); void when a buffer swap moved x / tmp
+    struct CycleGraph { int nu1, nu2, coarse; uint64_t epoch; cudaGraphExec_t exec; uint64_t launches; double bytes; };
+    std::vector<CycleGraph> graphs;
+    uint64_t ptr_epoch = 0;
 };
 
 namespace {
@@ -405,35 +411,23 @@ int build_colouring(mgb_amg *h, AmgLevel &L)
     return upload_schedule(colour, nc, L.colour, h->st, L.own);
 }
 
-// colour-sorted SELL-32 copy (off-diagonal entries) + slot-ordered diagonal and rhs
-int build_sell(mgb_amg *h, AmgLevel &L)
+// SELL-32 copy of the rows `row_of_slot` (already padded to slices, -1 = padding slot) of M; skip_diag drops a_ii.
+// diag / rhs (may be null) are copied in slot order.
+int upload_sell(const HostCsr &M, const std::vector<int> &row_of_slot, bool skip_diag, const double *rhs, SellCopy &S)
 {
-    const HostCsr &A = L.hA;
-    const int ncol = L.colour.n_groups;
-    SellCopy &S = L.sell;
-    std::vector<int> row_of_slot;
-    S.colour_slot_ptr.assign(ncol + 1, 0);
-    {
-        std::vector<std::vector<int>> by_colour(std::max(ncol, 1));
-        for (int i = L.own.r0; i < L.own.r1; ++i) by_colour[L.colour.h_group[i]].push_back(i);
-        for (int c = 0; c < ncol; ++c) {
-            S.colour_slot_ptr[c] = (int)row_of_slot.size();
-            row_of_slot.insert(row_of_slot.end(), by_colour[c].begin(), by_colour[c].end());
-            while (row_of_slot.size() % 32) row_of_slot.push_back(-1);        // every colour starts on a slice boundary
-        }
-        S.colour_slot_ptr[ncol] = (int)row_of_slot.size();
-    }
     S.n_slots = (int)row_of_slot.size();
     const int n_slices = S.n_slots / 32;
     std::vector<int> slice_ptr(n_slices + 1, 0);
+    auto row_len = [&](int i) {
+        int len = M.ptr[i + 1] - M.ptr[i];
+        if (skip_diag) for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) len -= (M.col[k] == i);
+        return len;
+    };
     for (int s = 0; s < n_slices; ++s) {
         int longest = 0;
         for (int q = 0; q < 32; ++q) {
             const int i = row_of_slot[32 * s + q];
-            if (i < 0) continue;
-            int len = 0;
-            for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) len += (A.col[k] != i);
-            longest = std::max(longest, len);
+            if (i >= 0) longest = std::max(longest, row_len(i));
         }
         slice_ptr[s + 1] = slice_ptr[s] + 32 * longest;
     }
@@ -445,12 +439,12 @@ int build_sell(mgb_amg *h, AmgLevel &L)
         if (i < 0) continue;
         int k2 = 0;
         const int base = slice_ptr[p >> 5] + (p & 31);
-        for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
-            if (A.col[k] == i) continue;
-            col[base + 32 * k2] = A.col[k]; val[base + 32 * k2] = A.val[k]; ++k2;
+        for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) {
+            if (skip_diag && M.col[k] == i) continue;
+            col[base + 32 * k2] = M.col[k]; val[base + 32 * k2] = M.val[k]; ++k2;
         }
-        diag_s[p] = A.at(i, i);
-        b_s[p] = L.h_rhs[i];
+        if (skip_diag) diag_s[p] = M.at(i, i);
+        if (rhs) b_s[p] = rhs[i];
     }
     ACK(cudaMalloc(&S.slice_ptr, sizeof(int) * (size_t)(n_slices + 1)));
     ACK(cudaMalloc(&S.col, sizeof(int) * col.size()));
@@ -465,6 +459,50 @@ int build_sell(mgb_amg *h, AmgLevel &L)
     ACK(cudaMemcpy(S.diag_s, diag_s.data(), sizeof(double) * diag_s.size(), cudaMemcpyHostToDevice));
     ACK(cudaMemcpy(S.b_s, b_s.data(), sizeof(double) * b_s.size(), cudaMemcpyHostToDevice));
     return MGB_OK;
+}
+
+// Inside windows of kSellWindow consecutive rows, longer rows first (SELL-C-sigma): the 32 rows of a slice then have
+// nearly the same length and the padding of the slice almost vanishes, while rows stay close to their neighbours
+// (the gathers of x keep their locality).  The rows of a list are mutually independent or order-free, so any order
+// gives the same values.
+constexpr int kSellWindow = 512;
+void sort_windows_by_length(const HostCsr &M, std::vector<int> &rows)
+{
+    for (size_t w = 0; w < rows.size(); w += kSellWindow) {
+        const size_t e = std::min(rows.size(), w + kSellWindow);
+        std::stable_sort(rows.begin() + w, rows.begin() + e,
+                         [&](int a, int b) { return M.ptr[a + 1] - M.ptr[a] > M.ptr[b + 1] - M.ptr[b]; });
+    }
+}
+
+// colour-sorted SELL-32 copy of A (off-diagonal entries) + slot-ordered diagonal and rhs: rows of this rank only
+int build_sell(mgb_amg *h, AmgLevel &L)
+{
+    (void)h;
+    const int ncol = L.colour.n_groups;
+    SellCopy &S = L.sell;
+    std::vector<int> row_of_slot;
+    S.colour_slot_ptr.assign(ncol + 1, 0);
+    std::vector<std::vector<int>> by_colour(std::max(ncol, 1));
+    for (int i = L.own.r0; i < L.own.r1; ++i) by_colour[L.colour.h_group[i]].push_back(i);
+    for (int c = 0; c < ncol; ++c) {
+        S.colour_slot_ptr[c] = (int)row_of_slot.size();
+        sort_windows_by_length(L.hA, by_colour[c]);
+        row_of_slot.insert(row_of_slot.end(), by_colour[c].begin(), by_colour[c].end());
+        while (row_of_slot.size() % 32) row_of_slot.push_back(-1);        // every colour starts on a slice boundary
+    }
+    S.colour_slot_ptr[ncol] = (int)row_of_slot.size();
+    return upload_sell(L.hA, row_of_slot, true, L.h_rhs.data(), S);
+}
+
+// SELL-32 copy of the rows [own_c.r0, own_c.r1) of R = P^T for the fast restriction (one thread per coarse row)
+int build_sell_restriction(const HostCsr &R, Block rows, SellCopy &S)
+{
+    std::vector<int> list;
+    for (int m = rows.r0; m < rows.r1; ++m) list.push_back(m);
+    sort_windows_by_length(R, list);
+    while (list.size() % 32) list.push_back(-1);
+    return upload_sell(R, list, false, nullptr, S);
 }
 
 // ---- ghost exchange -----------------------------------------------------------------------------------------------
@@ -588,6 +626,7 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
                 mgb::k_amg_sell<1><<<(L.sell.n_slots + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, nullptr, 0, L.sell.n_slots, h->omega);
             tally(h, sweep_bytes(L));
             std::swap(L.x, L.tmp);
+            h->ptr_epoch++;                                                         // captured graphs hold the old pointers
             if (L.sharded && (rc = exchange_all(h, L.haloA, L.x))) return rc;      // the new iterate has no ghosts yet
         }
     } else
@@ -641,7 +680,7 @@ int restrict_vec(mgb_amg *h, int level, double *in, double *out)
     const int rows = F.own_c.size();
     if (rows) {
         if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(rows + 255) / 256, 256, 0, h->st>>>(R, in, out, F.own_c.r0, F.own_c.r1);
-        else mgb::k_amg_spmv<false><<<(rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(R, in, out, F.own_c.r0, F.own_c.r1);
+        else mgb::k_amg_sell<3><<<(F.sellR.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellR.view(), in, nullptr, out, nullptr, 0, F.sellR.n_slots, 1.0);
     }
     const double share = R.n_rows ? (double)rows / R.n_rows : 0.;
     tally(h, (12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols) * share);
@@ -675,6 +714,34 @@ int do_prolong(mgb_amg *h, int level)
     return MGB_OK;
 }
 
+// levels lt .. L-1 in one launch (amg_tail.cuh).  mode 0: the reference's pass, mode 1: correction scheme.
+int launch_tail(mgb_amg *h, int mode, int pre, int coarse, int post)
+{
+    const int L = (int)h->lv.size();
+    const int kind = h->cfg.smoother;
+    mgb::AmgTailParams p{};
+    p.nlev = L - h->lt;
+    p.kind = kind; p.exact = h->cfg.exact_order; p.mode = mode;
+    p.pre = pre; p.coarse = coarse; p.post = post; p.omega = h->omega;
+    double bytes = 0.;
+    for (int l = h->lt; l < L; ++l) {
+        AmgLevel &lv = h->lv[l];
+        const Schedule &S = kind == MGB_SMOOTH_GS_LEX ? lv.lex : lv.colour;
+        mgb::AmgTailLevel &t = p.lv[l - h->lt];
+        t.A = lv.A.view(); t.P = lv.P.view(); t.R = lv.R.view();
+        t.diag = lv.diag; t.x = lv.x; t.b = lv.b; t.tmp = lv.tmp;
+        t.grp_ptr = S.d_ptr; t.grp_rows = S.d_rows; t.n_groups = S.n_groups;
+        const int sweeps = (l == L - 1) ? coarse : pre + post;
+        bytes += sweep_bytes(lv) * (sweeps + (mode == 1 && l < L - 1 ? 1 : 0));
+        if (l < L - 1) bytes += 2. * (12. * lv.P.nnz + 16. * lv.P.n_rows + 10. * lv.P.n_cols);
+        lv.x_halo_ok = true;
+    }
+    mgb::k_amg_tail<<<1, mgb::kAmgTailThreads, 0, h->st>>>(p);
+    tally(h, bytes);
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -692,6 +759,7 @@ void mgb_amg_config_default(mgb_amg_config *c)
     c->hybrid_gs = 0;
     c->shard_min_rows = 16384;
     c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
+    c->tail_max_rows = 4000;
 }
 
 void mgb_amg_config_fast(mgb_amg_config *c)
@@ -781,6 +849,15 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         L.own_nnz = (size_t)(L.hA.ptr[L.own.r1] - L.hA.ptr[L.own.r0]);
         L.x_halo_ok = true;                                   // x = 0 everywhere
     }
+    // persistent coarse tail: the trailing run of small, unsharded levels (at most kAmgTailMaxLevels of them)
+    {
+        const int cap = cfg->tail_max_rows == 0 ? 4000 : cfg->tail_max_rows;
+        h->lt = -1;
+        for (int l = cfg->levels - 1; l >= 0 && cap > 0; --l) {
+            if (h->lv[l].hA.n_rows > cap || h->lv[l].sharded || cfg->levels - l > mgb::kAmgTailMaxLevels) break;
+            h->lt = l;
+        }
+    }
     // upload
     size_t max_blocks = 1, max_halo = 1;
     for (int l = 0; l < cfg->levels; ++l) {
@@ -806,6 +883,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
             // rows of R this rank gathers: its block of the coarse level whenever the fine level is sharded (a replicated
             // coarse level is then completed by an all-gather), everything otherwise
             L.own_c = L.sharded ? block_of(R.n_rows, n_ranks, rank) : Block{0, R.n_rows};
+            if (!cfg->exact_order && (rc = build_sell_restriction(R, L.own_c, L.sellR))) return rc;
             if (L.sharded) {
                 L.haloR = halo_plan(R, n_ranks, rank, nullptr, 1);
                 if ((rc = upload_plan(L.haloR))) return rc;
@@ -844,8 +922,9 @@ void mgb_amg_destroy(mgb_amg_t h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (auto &L : h->lv) {
-        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release();
+        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellR.release();
         L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
     }
@@ -965,12 +1044,15 @@ int mgb_amg_apply(mgb_amg_t h, double *residual_norm)
     if (!h) return mgb_set_error(MGB_ERR_ARG, "null handle");
     ACK(cudaSetDevice(h->cfg.device));
     const int L = (int)h->lv.size();
+    const int T = h->lt >= 0 ? h->lt : L - 1;          // the levels T .. L-1 are one launch when the tail is on
     int rc, i;
-    for (i = 0; i < L - 1; ++i) {
+    for (i = 0; i < T; ++i) {
         if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.pre_sweeps))) return rc;
         if ((rc = do_restrict(h, i + 1))) return rc;
     }
-    if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.coarse_sweeps))) return rc;
+    if (h->lt >= 0) {
+        if ((rc = launch_tail(h, 0, h->cfg.pre_sweeps, h->cfg.coarse_sweeps, h->cfg.post_sweeps))) return rc;
+    } else if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.coarse_sweeps))) return rc;
     for (i--; i >= 0; --i) {
         if ((rc = do_prolong(h, i))) return rc;
         if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.post_sweeps))) return rc;
@@ -995,8 +1077,11 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
     if ((rc = do_residual(h, 0, &nrm))) return rc;
     hist[n++] = nrm;
     const double target = tol * nrm;
-    for (int it = 0; it < maxit && nrm > target; ++it) {
-        for (int l = 0; l < L - 1; ++l) {                                  // downward
+    const int T = h->lt >= 0 ? h->lt : L - 1;                              // levels T .. L-1: one launch when the tail is on
+    // one cycle: every launch, ghost exchange and the all-reduced norm of the new iterate, no host synchronisation
+    auto cycle = [&]() -> int {
+        int rc;
+        for (int l = 0; l < T; ++l) {                                      // downward
             AmgLevel &F = h->lv[l], &C = h->lv[l + 1];
             if (nu1 > 0 && (rc = do_smooth(h, l, kind, nu1))) return rc;
             if ((rc = residual_to_tmp(h, F, false))) return rc;               // r = b - A x into F.tmp (no host read-back)
@@ -1009,15 +1094,49 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
                 ACK(cudaMemsetAsync(C.x, 0, sizeof(double) * (size_t)C.A.n_rows, h->st));
                 C.x_halo_ok = true;
             }
-            ACK(cudaGetLastError());
         }
-        if ((rc = do_smooth(h, L - 1, kind, coarse))) return rc;
-        for (int l = L - 2; l >= 0; --l) {                                  // upward
+        if (h->lt >= 0) { if ((rc = launch_tail(h, 1, nu1, coarse, nu2))) return rc; }
+        else if ((rc = do_smooth(h, L - 1, kind, coarse))) return rc;
+        for (int l = T - 1; l >= 0; --l) {                                  // upward
             if ((rc = do_prolong(h, l))) return rc;
             if (nu2 > 0 && (rc = do_smooth(h, l, kind, nu2))) return rc;
         }
+        return residual_to_tmp(h, h->lv[0], true);
+    };
+    const bool graphed = h->cfg.cycle_graph >= 0 && kind != MGB_SMOOTH_JACOBI;
+    mgb_amg::CycleGraph *G = nullptr;
+    if (graphed && maxit > 0 && nrm > target) {
+        for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+            if (it->epoch != h->ptr_epoch) { cudaGraphExecDestroy(it->exec); it = h->graphs.erase(it); }
+            else ++it;
+        }
+        for (auto &g : h->graphs) if (g.nu1 == nu1 && g.nu2 == nu2 && g.coarse == coarse) G = &g;
+        if (!G) {
+            const mgb_gmg_stats before = h->stats;
+            cudaGraph_t graph = nullptr;
+            ACK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            rc = cycle();
+            const cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            ACK(ce);
+            mgb_amg::CycleGraph g{nu1, nu2, coarse, h->ptr_epoch, nullptr, h->stats.kernel_launches - before.kernel_launches,
+                                  h->stats.bytes_algorithmic - before.bytes_algorithmic};
+            ACK(cudaGraphInstantiate(&g.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->stats = before;                                                 // nothing ran yet
+            h->graphs.push_back(g);
+            G = &h->graphs.back();
+        }
+    }
+    for (int it = 0; it < maxit && nrm > target; ++it) {
+        if (G) {
+            ACK(cudaGraphLaunch(G->exec, h->st));
+            h->stats.kernel_launches += G->launches; h->stats.bytes_algorithmic += G->bytes; h->stats.graph_launches++;
+        } else if ((rc = cycle())) return rc;
         h->stats.cycles++;
-        if ((rc = do_residual(h, 0, &nrm))) return rc;
+        ACK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        ACK(cudaStreamSynchronize(h->st));
+        nrm = std::sqrt(h->h_scal[0]);
         hist[n++] = nrm;
     }
     *n_hist = n;

@@ -188,3 +188,40 @@ def test_weighted_jacobi_against_numpy():
     # a single-GPU handle reports every level as whole and unsharded
     with Amg(A.ptr, A.col, A.val, b, levels=2) as a:
         assert a.rows(0) == (0, A.n_rows, False)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("smoother", [M.GS_LEX, M.JACOBI, M.GS_MULTICOLOUR])
+def test_persistent_tail_equals_per_level_launches(fast, smoother):
+    """north_star item 3: the trailing small levels run in ONE persistent single-CTA kernel.  It calls the same row
+    functions as the per-level kernels, so the reference's pass and the correction-scheme cycles give the same
+    vectors: bit for bit in exact-order arithmetic, to rounding with the fast kernels."""
+    if fast and smoother == M.GS_LEX:
+        pytest.skip("the fast configuration reorders the sweep")
+    c = load_case("mesh1")
+    A, b = c["A"][0], c["rhs"][0]
+    out = []
+    # tail off + no CUDA graph (one launch per operator) / graph only / levels 2..4 in the tail / the whole hierarchy
+    for cap, graph in ((-1, -1), (-1, 0), (1000, 0), (20000, 0)):
+        with Amg(A.ptr, A.col, A.val, b, levels=5, fast=fast, smoother=smoother, tail_max_rows=cap, cycle_graph=graph,
+                 jacobi_omega=0.9) as a:
+            a.reset_stats()
+            res = a.apply()
+            x_pass = a.vector(0, 0)
+            launches = a.stats()["kernel_launches"]
+            a.set_vector(0, 0, np.zeros(A.n_rows))
+            hist = a.solve(tol=1e-30, maxit=3, nu1=2, nu2=1, coarse=7)
+            out.append((res, x_pass, launches, hist, a.vector(0, 0), [a.vector(l, 0) for l in range(1, 5)]))
+    ref = out[0]
+    for k, got in enumerate(out[1:]):
+        assert got[2] < ref[2] or k == 0       # fewer launches with the tail
+        if not fast:
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[4], ref[4])
+            for u, v in zip(got[5], ref[5]):
+                assert np.array_equal(u, v)
+        scale = np.abs(ref[1]).max()
+        assert np.allclose(got[1], ref[1], rtol=1e-11, atol=1e-12 * scale)
+        assert np.allclose(got[4], ref[4], rtol=1e-11, atol=1e-12 * np.abs(ref[4]).max())
+        assert abs(got[0] - ref[0]) <= 1e-10 * ref[0]
+        assert np.allclose(got[3], ref[3], rtol=1e-9)
+    assert out[3][2] <= 4                      # whole pass = the tail launch + residual + reduce

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--levels", type=int, default=10)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--cycles", type=int, default=10)
+    ap.add_argument("--tail-sweep", default="", help="comma-separated tail_max_rows values to time the cycle with (e.g. -1,3000,8000,50000)")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -146,6 +147,11 @@ def main():
 
     timed_cycles(amg, "correction-scheme V(2,2) cycle, multicolour GS")
     amg.close()
+    for cap in [int(v) for v in a.tail_sweep.split(",") if v]:
+        for graph in (0, -1):
+            t = make(tail_max_rows=cap, cycle_graph=graph)
+            timed_cycles(t, f"V(2,2) cycle, tail_max_rows={cap}, cycle_graph={graph}")
+            t.close()
     if world > 1:
         hy = make(hybrid_gs=1)
         bench(hy, "L0 hybrid multicolour GS sweep (ghosts once per sweep)", lambda: hy.smooth(0, M.GS_MULTICOLOUR, 1), units=n)
