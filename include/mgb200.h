@@ -205,7 +205,12 @@ typedef struct mgb_amg_config {
     int cycle_graph;       /* mgb_amg_solve: 0 (default) = one cycle (all launches, ghost exchanges and the norm) is captured
                               in a CUDA graph once and replayed -- the coarse levels are launch-latency bound; < 0: off.
                               (Jacobi swaps buffers every sweep and always runs uncaptured.) */
-    int reserved[2];
+    int coop_sweeps;       /* > 0: on a level that needs no ghost exchange between colours, whole multicolour sweeps run as ONE
+                              cooperative launch with a grid-wide barrier per colour.  Measured SLOWER than one launch per
+                              colour on B200 (grid.sync of a full grid costs more than a launch gap: level-0 sweep 0.207 vs
+                              0.151 ms, V(2,2) cycle 9.5 vs 5.8 ms at 4 M DoF, profiles/r01_amg_scale_1gpu_4M_coop.json), so
+                              it is off by default (0) */
+    int reserved[1];
 } mgb_amg_config;
 
 typedef struct mgb_amg *mgb_amg_t;

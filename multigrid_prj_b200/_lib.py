@@ -36,7 +36,7 @@ class AmgConfigStruct(C.Structure):
                 ("coarse_sweeps", C.c_int), ("post_sweeps", C.c_int), ("exact_order", C.c_int), ("device", C.c_int),
                 ("start_index", C.c_int64 * 16), ("hybrid_gs", C.c_int), ("shard_min_rows", C.c_int),
                 ("jacobi_omega", C.c_double), ("tail_max_rows", C.c_int), ("cycle_graph", C.c_int),
-                ("reserved", C.c_int * 2)]
+                ("coop_sweeps", C.c_int), ("reserved", C.c_int * 1)]
 
 
 # every symbol include/mgb200.h declares: name -> (restype, argtypes)

@@ -15,6 +15,7 @@
 // whose members do not depend on one another); the reordered fast smoother is multicolour
 // Gauss-Seidel from an on-device greedy (Jones-Plassmann) colouring.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -230,6 +231,35 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
             if (threadIdx.x == 0) partial[blockIdx.x] = t;
         }
     }
+}
+
+// `sweeps` whole multicolour Gauss-Seidel sweeps in ONE cooperative launch: the grid walks the colours in order with a
+// grid-wide barrier after each (the next colour reads this colour's new values).  A sweep as separate launches costs
+// one launch + ramp-up per colour -- 7 on the fine level, 13-16 on the Galerkin levels, where a colour holds only a
+// few thousand rows and the launch gap is longer than the work.  Same row arithmetic as k_amg_sell<2>.
+__global__ void __launch_bounds__(256)
+k_amg_sell_gs_sweeps(SellDev A, double *x, const double *__restrict__ b_s, const int *__restrict__ colour_slot_ptr,
+                     int n_colours, int sweeps)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int stride = gridDim.x * blockDim.x;
+    for (int sw = 0; sw < sweeps; ++sw)
+        for (int c = 0; c < n_colours; ++c) {
+            const int last = colour_slot_ptr[c + 1];
+            for (int p = colour_slot_ptr[c] + blockIdx.x * blockDim.x + threadIdx.x; p < last; p += stride) {
+                const int i = __ldcs(A.row_of_slot + p);
+                if (i < 0) continue;
+                const int s = p >> 5;
+                const int b0 = A.slice_ptr[s];
+                const int base = b0 + (p & 31);
+                const int len = (A.slice_ptr[s + 1] - b0) >> 5;
+                double sum = 0.;
+#pragma unroll 4
+                for (int k = 0; k < len; ++k) sum += __ldcs(A.val + base + 32 * k) * x[__ldcs(A.col + base + 32 * k)];
+                x[i] = (__ldcs(b_s + p) - sum) / __ldcs(A.diag_s + p);
+            }
+            grid.sync();
+        }
 }
 
 // slot-ordered copy of a level vector (keeps the SELL kernels' right-hand side in step with L.b)

@@ -287,11 +287,13 @@ struct Schedule {          // rows grouped into independent sets (wavefronts or 
 struct SellCopy {              // colour-sorted SELL-32 copy of A for the fast kernels (amg_kernels.cuh)
     int n_slots = 0;
     std::vector<int> colour_slot_ptr;      // first slot of each colour (+ end)
+    int *d_colour_slot_ptr = nullptr;      // the same on the device (cooperative whole-sweep kernel)
+    int coop_blocks = 0;                   // grid of the cooperative kernel: co-resident, at most the largest colour
     int *slice_ptr = nullptr, *col = nullptr, *row_of_slot = nullptr;
     double *val = nullptr, *diag_s = nullptr, *b_s = nullptr;
     size_t stored = 0;                     // entries incl. padding
     mgb::SellDev view() const { return mgb::SellDev{n_slots, slice_ptr, col, val, row_of_slot, diag_s, b_s}; }
-    void release() { cudaFree(slice_ptr); cudaFree(col); cudaFree(row_of_slot); cudaFree(val); cudaFree(diag_s); cudaFree(b_s); }
+    void release() { cudaFree(slice_ptr); cudaFree(col); cudaFree(row_of_slot); cudaFree(val); cudaFree(diag_s); cudaFree(b_s); cudaFree(d_colour_slot_ptr); }
 };
 
 struct AmgLevel {
@@ -324,6 +326,7 @@ struct mgb_amg {
     double *d_send = nullptr, *d_recv = nullptr;      // packed ghost entries
     double omega = 1.0;
     int lt = -1;                                      // first level of the persistent coarse tail (-1: none)
+    int coop_max_blocks = 0;                          // co-resident CTAs of k_amg_sell_gs_sweeps (0: no cooperative launch)
     // one correction-scheme cycle captured as a CUDA graph (per sweep counts); void when a buffer swap moved x / tmp
     struct CycleGraph { int nu1, nu2, coarse; uint64_t epoch; cudaGraphExec_t exec; uint64_t launches; double bytes; };
     std::vector<CycleGraph> graphs;
@@ -478,7 +481,6 @@ void sort_windows_by_length(const HostCsr &M, std::vector<int> &rows)
 // colour-sorted SELL-32 copy of A (off-diagonal entries) + slot-ordered diagonal and rhs: rows of this rank only
 int build_sell(mgb_amg *h, AmgLevel &L)
 {
-    (void)h;
     const int ncol = L.colour.n_groups;
     SellCopy &S = L.sell;
     std::vector<int> row_of_slot;
@@ -492,6 +494,11 @@ int build_sell(mgb_amg *h, AmgLevel &L)
         while (row_of_slot.size() % 32) row_of_slot.push_back(-1);        // every colour starts on a slice boundary
     }
     S.colour_slot_ptr[ncol] = (int)row_of_slot.size();
+    ACK(cudaMalloc(&S.d_colour_slot_ptr, sizeof(int) * (size_t)(ncol + 1)));
+    ACK(cudaMemcpy(S.d_colour_slot_ptr, S.colour_slot_ptr.data(), sizeof(int) * (size_t)(ncol + 1), cudaMemcpyHostToDevice));
+    int widest = 0;
+    for (int c = 0; c < ncol; ++c) widest = std::max(widest, S.colour_slot_ptr[c + 1] - S.colour_slot_ptr[c]);
+    S.coop_blocks = std::max(1, std::min((widest + 255) / 256, h->coop_max_blocks));
     return upload_sell(L.hA, row_of_slot, true, L.h_rhs.data(), S);
 }
 
@@ -601,6 +608,22 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
     } else if (kind == MGB_SMOOTH_GS_RB) {            // multicolour Gauss-Seidel
         if ((rc = need_x_halo(h, L))) return rc;
         const bool per_colour = L.sharded && !h->cfg.hybrid_gs;
+        if (!h->cfg.exact_order && !per_colour && h->coop_max_blocks > 0 && L.sell.n_slots > 0) {
+            // no ghost exchange between the colours: whole sweeps in one cooperative launch (all sweeps of the visit on
+            // an unsharded level; one sweep + one exchange at a time for the hybrid smoother of a sharded level)
+            mgb::SellDev S = L.sell.view();
+            double *xp = L.x;
+            const double *bs = L.sell.b_s;
+            const int *csp = L.sell.d_colour_slot_ptr;
+            int ncol = L.colour.n_groups, nsw = L.sharded ? 1 : sweeps;
+            void *args[] = {&S, &xp, &bs, &csp, &ncol, &nsw};
+            for (int s = 0; s < sweeps; s += nsw) {
+                ACK(cudaLaunchCooperativeKernel((const void *)mgb::k_amg_sell_gs_sweeps, dim3(L.sell.coop_blocks), dim3(256), args, 0, h->st));
+                tally(h, sweep_bytes(L) * nsw);
+                if (L.sharded && (rc = exchange_all(h, L.haloA, L.x))) return rc;
+            }
+            return MGB_OK;
+        }
         for (int s = 0; s < sweeps; ++s) {
             for (int c = 0; c < L.colour.n_groups; ++c) {
                 const int a = L.colour.h_ptr[c], b = L.colour.h_ptr[c + 1];
@@ -805,6 +828,13 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
     const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 16384;
     ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {
+        int coop = 0, sms = 0, per_sm = 0;
+        ACK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+        ACK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        ACK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgb::k_amg_sell_gs_sweeps, 256, 0));
+        h->coop_max_blocks = (coop && cfg->coop_sweeps > 0) ? sms * per_sm : 0;
+    }
     if (n_ranks > 1) {
         auto &Nc = mgb::nccl();
         if (!Nc.load()) { delete h; return mgb_set_error(MGB_ERR_NCCL, Nc.error); }

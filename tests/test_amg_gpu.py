@@ -201,10 +201,11 @@ def test_persistent_tail_equals_per_level_launches(fast, smoother):
     c = load_case("mesh1")
     A, b = c["A"][0], c["rhs"][0]
     out = []
-    # tail off + no CUDA graph (one launch per operator) / graph only / levels 2..4 in the tail / the whole hierarchy
-    for cap, graph in ((-1, -1), (-1, 0), (1000, 0), (20000, 0)):
+    # one launch per colour and operator / cooperative whole-sweep launches / + CUDA graph of the cycle / + levels 2..4 in
+    # the persistent tail / the whole hierarchy in the tail
+    for cap, graph, coop in ((-1, -1, 0), (-1, -1, 1), (-1, 0, 0), (1000, 0, 0), (20000, 0, 0)):
         with Amg(A.ptr, A.col, A.val, b, levels=5, fast=fast, smoother=smoother, tail_max_rows=cap, cycle_graph=graph,
-                 jacobi_omega=0.9) as a:
+                 coop_sweeps=coop, jacobi_omega=0.9) as a:
             a.reset_stats()
             res = a.apply()
             x_pass = a.vector(0, 0)
@@ -214,7 +215,7 @@ def test_persistent_tail_equals_per_level_launches(fast, smoother):
             out.append((res, x_pass, launches, hist, a.vector(0, 0), [a.vector(l, 0) for l in range(1, 5)]))
     ref = out[0]
     for k, got in enumerate(out[1:]):
-        assert got[2] < ref[2] or k == 0       # fewer launches with the tail
+        assert got[2] < ref[2] or (k == 0 and (not fast or smoother != M.GS_MULTICOLOUR)) or k == 1   # fewer launches
         if not fast:
             assert np.array_equal(got[1], ref[1]) and np.array_equal(got[4], ref[4])
             for u, v in zip(got[5], ref[5]):
@@ -224,4 +225,4 @@ def test_persistent_tail_equals_per_level_launches(fast, smoother):
         assert np.allclose(got[4], ref[4], rtol=1e-11, atol=1e-12 * np.abs(ref[4]).max())
         assert abs(got[0] - ref[0]) <= 1e-10 * ref[0]
         assert np.allclose(got[3], ref[3], rtol=1e-9)
-    assert out[3][2] <= 4                      # whole pass = the tail launch + residual + reduce
+    assert out[4][2] <= 4                      # whole pass = the tail launch + residual + reduce

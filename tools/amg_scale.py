@@ -152,6 +152,11 @@ def main():
             t = make(tail_max_rows=cap, cycle_graph=graph)
             timed_cycles(t, f"V(2,2) cycle, tail_max_rows={cap}, cycle_graph={graph}")
             t.close()
+    if a.tail_sweep:
+        t = make(coop_sweeps=1)
+        bench(t, "L0 multicolour GS sweep, one cooperative launch", lambda: t.smooth(0, M.GS_MULTICOLOUR, 1), units=n)
+        timed_cycles(t, "V(2,2) cycle, cooperative whole-sweep launches (coop_sweeps=1)")
+        t.close()
     if world > 1:
         hy = make(hybrid_gs=1)
         bench(hy, "L0 hybrid multicolour GS sweep (ghosts once per sweep)", lambda: hy.smooth(0, M.GS_MULTICOLOUR, 1), units=n)
