@@ -181,6 +181,34 @@ struct SellDev {
     const double *diag_s, *b_s;  // diagonal and right-hand side in slot order
 };
 
+// sum_k val_k * x[col_k] over the `len` stored entries of one slot, in storage (ascending column) order.  The entries
+// are fetched in chunks of kSellChunk: all column indices and values of a chunk are in flight together, then all the
+// gathers of x -- two dependent memory round trips per chunk.  P1 rows hold 5-8 off-diagonals, i.e. one chunk: the
+// row's lifetime is ~3 memory latencies (slice_ptr, col/val, x) instead of ~5 with a 4-wide unroll, which is what
+// bounds these kernels (ncu: long-scoreboard stalls, issue slots 13 % busy, DRAM 70 % -- latency, not bandwidth).
+constexpr int kSellChunk = 8;
+__device__ __forceinline__ double sell_row_dot(const SellDev &A, const double *x, int base, int len)
+{
+    double sum = 0.;
+    for (int k0 = 0; k0 < len; k0 += kSellChunk) {
+        int c[kSellChunk];
+        double v[kSellChunk];
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u) {
+            const bool ok = k0 + u < len;
+            c[u] = ok ? __ldcs(A.col + base + 32 * (k0 + u)) : -1;
+            v[u] = ok ? __ldcs(A.val + base + 32 * (k0 + u)) : 0.;
+        }
+        double xv[kSellChunk];
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u) xv[u] = c[u] >= 0 ? x[c[u]] : 0.;
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u)
+            if (c[u] >= 0) sum += v[u] * xv[u];
+    }
+    return sum;
+}
+
 // The operator stream (col, val, diag, rhs, row map) is read exactly once per launch: it is loaded with the streaming
 // (evict-first) hint so that it does not push the vector x -- gathered ~7 times per sweep, once from every colour --
 // out of the 126 MB L2.  ncu before the hint: 793 MB of DRAM traffic for a 447 MB (algorithmic) Jacobi sweep, L2 hit
@@ -202,9 +230,7 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
             const int b0 = A.slice_ptr[s];
             const int base = b0 + (p & 31);
             const int len = (A.slice_ptr[s + 1] - b0) >> 5;
-            double sum = 0.;
-#pragma unroll 4
-            for (int k = 0; k < len; ++k) sum += __ldcs(A.val + base + 32 * k) * x[__ldcs(A.col + base + 32 * k)];
+            const double sum = sell_row_dot(A, x, base, len);
             if (MODE == 3) out[i] = sum;
             else {
                 const double d = __ldcs(A.diag_s + p), bi = __ldcs(b_s + p);
@@ -253,9 +279,7 @@ k_amg_sell_gs_sweeps(SellDev A, double *x, const double *__restrict__ b_s, const
                 const int b0 = A.slice_ptr[s];
                 const int base = b0 + (p & 31);
                 const int len = (A.slice_ptr[s + 1] - b0) >> 5;
-                double sum = 0.;
-#pragma unroll 4
-                for (int k = 0; k < len; ++k) sum += __ldcs(A.val + base + 32 * k) * x[__ldcs(A.col + base + 32 * k)];
+                const double sum = sell_row_dot(A, x, base, len);
                 x[i] = (__ldcs(b_s + p) - sum) / __ldcs(A.diag_s + p);
             }
             grid.sync();
