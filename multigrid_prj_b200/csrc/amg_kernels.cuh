@@ -215,7 +215,11 @@ __device__ __forceinline__ double sell_row_dot(const SellDev &A, const double *x
 // rate 25 % (profiles/r01_ncu_amg_ops_4M.txt).
 // MODE 0: r = b - A x (+ sum r^2 per CTA); MODE 1: Jacobi into `out`; MODE 2: Gauss-Seidel on the slots
 // [first, last) of one colour, in place on x; MODE 3: plain product out[row] = sum (restriction, R = P^T)
-template <int MODE>
+// NAT: the copy keeps the natural row order (only permuted inside 512-row windows) and has no slot-ordered vectors:
+// diag_s / b_s are then the level's diag / b, indexed by row.  Jacobi and the residual visit every row once in any
+// order; in natural order the gathers of x stay local, while the colour-sorted copy walks the whole index range once
+// per colour (7 passes over x -- 54 % of peak instead of 77 % once x outgrows the L2, 16 M DoF).
+template <int MODE, bool NAT = false>
 __global__ void __launch_bounds__(256)
 k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *out, double *__restrict__ partial,
            int first, int last, double omega)
@@ -233,7 +237,7 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
             const double sum = sell_row_dot(A, x, base, len);
             if (MODE == 3) out[i] = sum;
             else {
-                const double d = __ldcs(A.diag_s + p), bi = __ldcs(b_s + p);
+                const double d = __ldcs(A.diag_s + (NAT ? i : p)), bi = __ldcs(b_s + (NAT ? i : p));
                 if (MODE == 0) {
                     const double ri = bi - (sum + d * x[i]);
                     if (out) out[i] = ri;

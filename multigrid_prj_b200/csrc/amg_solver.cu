@@ -302,7 +302,8 @@ struct AmgLevel {
     DevCsr A, P, R;
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
     Schedule lex, colour;
-    SellCopy sell, sellR;                      // fast-path copies of A (colour-sorted) and of this rank's rows of R
+    SellCopy sell, sellN, sellR;               // fast-path copies of A (colour-sorted / natural order) and of this rank's rows of R
+    mgb::SellDev natural() const { mgb::SellDev v = sellN.view(); v.diag_s = diag; return v; }
     // sharding: rows [own.r0, own.r1) of this level are smoothed here (the whole level when it is replicated)
     bool sharded = false;
     Block own;                                 // rows this rank works on
@@ -416,7 +417,8 @@ int build_colouring(mgb_amg *h, AmgLevel &L)
 
 // SELL-32 copy of the rows `row_of_slot` (already padded to slices, -1 = padding slot) of M; skip_diag drops a_ii.
 // diag / rhs (may be null) are copied in slot order.
-int upload_sell(const HostCsr &M, const std::vector<int> &row_of_slot, bool skip_diag, const double *rhs, SellCopy &S)
+int upload_sell(const HostCsr &M, const std::vector<int> &row_of_slot, bool skip_diag, const double *rhs, SellCopy &S,
+                bool slot_vectors = true)
 {
     S.n_slots = (int)row_of_slot.size();
     const int n_slices = S.n_slots / 32;
@@ -453,14 +455,16 @@ int upload_sell(const HostCsr &M, const std::vector<int> &row_of_slot, bool skip
     ACK(cudaMalloc(&S.col, sizeof(int) * col.size()));
     ACK(cudaMalloc(&S.val, sizeof(double) * val.size()));
     ACK(cudaMalloc(&S.row_of_slot, sizeof(int) * (size_t)std::max(S.n_slots, 1)));
-    ACK(cudaMalloc(&S.diag_s, sizeof(double) * diag_s.size()));
-    ACK(cudaMalloc(&S.b_s, sizeof(double) * b_s.size()));
+    if (slot_vectors) {
+        ACK(cudaMalloc(&S.diag_s, sizeof(double) * diag_s.size()));
+        ACK(cudaMalloc(&S.b_s, sizeof(double) * b_s.size()));
+        ACK(cudaMemcpy(S.diag_s, diag_s.data(), sizeof(double) * diag_s.size(), cudaMemcpyHostToDevice));
+        ACK(cudaMemcpy(S.b_s, b_s.data(), sizeof(double) * b_s.size(), cudaMemcpyHostToDevice));
+    }
     ACK(cudaMemcpy(S.slice_ptr, slice_ptr.data(), sizeof(int) * (size_t)(n_slices + 1), cudaMemcpyHostToDevice));
     ACK(cudaMemcpy(S.col, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice));
     ACK(cudaMemcpy(S.val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
     if (S.n_slots) ACK(cudaMemcpy(S.row_of_slot, row_of_slot.data(), sizeof(int) * (size_t)S.n_slots, cudaMemcpyHostToDevice));
-    ACK(cudaMemcpy(S.diag_s, diag_s.data(), sizeof(double) * diag_s.size(), cudaMemcpyHostToDevice));
-    ACK(cudaMemcpy(S.b_s, b_s.data(), sizeof(double) * b_s.size(), cudaMemcpyHostToDevice));
     return MGB_OK;
 }
 
@@ -502,6 +506,17 @@ int build_sell(mgb_amg *h, AmgLevel &L)
     return upload_sell(L.hA, row_of_slot, true, L.h_rhs.data(), S);
 }
 
+// SELL-32 copy of this rank's rows of A in natural order (off-diagonals; diag / rhs are read by row) for the kernels
+// that visit every row once: Jacobi and the residual
+int build_sell_natural(AmgLevel &L)
+{
+    std::vector<int> list;
+    for (int i = L.own.r0; i < L.own.r1; ++i) list.push_back(i);
+    sort_windows_by_length(L.hA, list);
+    while (list.size() % 32) list.push_back(-1);
+    return upload_sell(L.hA, list, true, nullptr, L.sellN, false);
+}
+
 // SELL-32 copy of the rows [own_c.r0, own_c.r1) of R = P^T for the fast restriction (one thread per coarse row)
 int build_sell_restriction(const HostCsr &R, Block rows, SellCopy &S)
 {
@@ -509,7 +524,7 @@ int build_sell_restriction(const HostCsr &R, Block rows, SellCopy &S)
     for (int m = rows.r0; m < rows.r1; ++m) list.push_back(m);
     sort_windows_by_length(R, list);
     while (list.size() % 32) list.push_back(-1);
-    return upload_sell(R, list, false, nullptr, S);
+    return upload_sell(R, list, false, nullptr, S, false);
 }
 
 // ---- ghost exchange -----------------------------------------------------------------------------------------------
@@ -645,8 +660,8 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
         for (int s = 0; s < sweeps; ++s) {
             if (h->cfg.exact_order) {
                 if (rows) mgb::k_amg_jacobi_vec<<<(rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp, h->omega, L.own.r0, L.own.r1);
-            } else if (L.sell.n_slots)
-                mgb::k_amg_sell<1><<<(L.sell.n_slots + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, nullptr, 0, L.sell.n_slots, h->omega);
+            } else if (L.sellN.n_slots)
+                mgb::k_amg_sell<1, true><<<(L.sellN.n_slots + 255) / 256, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, nullptr, 0, L.sellN.n_slots, h->omega);
             tally(h, sweep_bytes(L));
             std::swap(L.x, L.tmp);
             h->ptr_epoch++;                                                         // captured graphs hold the old pointers
@@ -669,8 +684,8 @@ int residual_to_tmp(mgb_amg *h, AmgLevel &L, bool want_norm)
         blocks = (rows + 255) / 256;
         if (blocks) mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial, L.own.r0, L.own.r1);
     } else {
-        blocks = (L.sell.n_slots + 255) / 256;
-        if (blocks) mgb::k_amg_sell<0><<<blocks, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.tmp, h->d_partial, 0, L.sell.n_slots, 1.0);
+        blocks = (L.sellN.n_slots + 255) / 256;
+        if (blocks) mgb::k_amg_sell<0, true><<<blocks, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, h->d_partial, 0, L.sellN.n_slots, 1.0);
     }
     tally(h, sweep_bytes(L));
     if (want_norm) {
@@ -927,6 +942,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         if ((rc = build_lex_schedule(h, L))) return rc;
         if ((rc = build_colouring(h, L))) return rc;       // on the whole graph: every rank derives the same colours
         if ((rc = build_sell(h, L))) return rc;
+        if (!cfg->exact_order && (rc = build_sell_natural(L))) return rc;
         if (L.sharded) {
             L.haloA = halo_plan(L.hA, n_ranks, rank, nullptr, 1);
             L.haloA_colour = halo_plan(L.hA, n_ranks, rank, L.colour.h_group.data(), L.colour.n_groups);
@@ -954,7 +970,7 @@ void mgb_amg_destroy(mgb_amg_t h)
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (auto &L : h->lv) {
-        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellR.release();
+        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellN.release(); L.sellR.release();
         L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
     }
