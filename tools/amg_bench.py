@@ -115,10 +115,10 @@ def main():
         print(f"{name:44s} {ms:9.4f} ms {gbs:9.1f} GB/s alg  {100 * gbs / peak:5.1f}% of peak  {s['kernel_launches'] / reps:5.1f} launches", flush=True)
 
     lib, h = amg.lib, amg.h
-    bench("L0 multicolour GS sweep (vector, 8 lanes/row)", lambda: amg.smooth(0, M.GS_MULTICOLOUR, 1))
-    bench("L0 Jacobi sweep (vector)", lambda: amg.smooth(0, M.JACOBI, 1))
-    bench("L0 residual r=b-Ax + norm (vector)", lambda: lib.mgb_amg_residual(h, 0, __import__('ctypes').byref(__import__('ctypes').c_double())))
-    bench("restrict L0->L1 (R=P^T gather SpMV)", lambda: amg.restrict(1))
+    bench("L0 multicolour GS sweep (colour-sorted SELL-32)", lambda: amg.smooth(0, M.GS_MULTICOLOUR, 1))
+    bench("L0 Jacobi sweep (natural-order SELL-32)", lambda: amg.smooth(0, M.JACOBI, 1))
+    bench("L0 residual r=b-Ax + norm (natural-order SELL-32)", lambda: lib.mgb_amg_residual(h, 0, __import__('ctypes').byref(__import__('ctypes').c_double())))
+    bench("restrict L0->L1 (R=P^T, SELL-32 gather)", lambda: amg.restrict(1))
     bench("prolong-add L1->L0", lambda: amg.prolong(0))
     amg.set_vector(0, 0, np.zeros(n))
     bench("one pass (10 pre / 200 coarse / 10 post sweeps), multicolour GS", lambda: amg.apply(False), reps=3)
