@@ -12,6 +12,8 @@ One "step" = one driver iteration of the reference (GeometricMultigrid/src/main.
   roofline = the dominant kernel (fine-level red-black GS colour pass) timed alone, live.
   cpu_baseline = the reference's own CPU classes (oracle/_ref, compiled from /root/reference) on the
            box's host cores, on a bounded sample of the same workload.
+  amg      = (N=1 only; the second half of BASELINE.json's metric, "smoother/SpMV HBM GB/s vs peak") the level-0
+           AMG kernels on a 4 M DoF synthetic unstructured triangulation: ms, algorithmic GB/s, fraction of peak.
 Workloads: N=1 -> config C3 (8193^2, L=13); N>1 -> config C4 (16385^2, L=14) in row slabs.
 """
 import argparse
@@ -109,6 +111,39 @@ def cpu_reference(n, levels, cycles, threads=None):
     return n * n * cycles / dt, threads, kind, dt
 
 
+def amg_kernels(device, peak, side=2001, reps=20):
+    """level-0 kernels of the AMG fast path (multicolour GS, weighted Jacobi, residual, R x, x += P x) timed with CUDA
+    events on the library's stream; algorithmic bytes per SURVEY.md section 8d (12 nnz + 28 n per sweep / SpMV)"""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from amg_bench import synthetic_system
+    from multigrid_prj_b200 import Amg
+    from multigrid_prj_b200 import amg as M
+    from multigrid_prj_b200.gmg import Timer
+    A, rhs = synthetic_system(side)
+    out = {"workload": f"P1 FEM Poisson on a synthetic unstructured triangulation, {A.shape[0]} DoF, {A.nnz} nnz (BASELINE config 5 "
+                       f"shape at 1/4 size), 2 levels", "peak": peak, "unit": "GB/s", "kernels": {}}
+    with Amg(A.indptr, A.indices, A.data, rhs, levels=2, fast=True, device=device) as a:
+        tm, st, nrm = Timer(), a.stream(), C.c_double()
+        ops = {"multicolour_gs_sweep": lambda: a.smooth(0, M.GS_MULTICOLOUR, 1), "jacobi_sweep": lambda: a.smooth(0, M.JACOBI, 1),
+               "residual_norm": lambda: a.lib.mgb_amg_residual(a.h, 0, C.byref(nrm)), "restrict_Rx": lambda: a.restrict(1),
+               "prolong_add_Px": lambda: a.prolong(0)}
+        launches = 0
+        for name, fn in ops.items():
+            fn(); fn(); a.sync(); a.reset_stats()
+            tm.start(st)
+            for _ in range(reps):
+                fn()
+            tm.stop(st)
+            ms = tm.elapsed_ms() / reps
+            s_ = a.stats()
+            gbs = s_["bytes_algorithmic"] / reps / (ms * 1e-3) / 1e9
+            launches += int(s_["kernel_launches"])
+            out["kernels"][name] = {"ms": ms, "achieved": gbs, "frac": gbs / peak}
+        out["gpu_launches"] = launches
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +199,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "parity-jacobi", "parity-gs"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-amg", action="store_true", help="skip the AMG kernel leg (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -331,6 +367,11 @@ def main():
                "sample": f"{cc} driver iterations of the reference's GS solver on {cn}^2, L={cl} ({dt:.1f} s); "
                          f"lexicographic GS is serial, only the residual loops use the {cores} OpenMP threads"}
 
+    # ---- AMG smoother / SpMV kernels against the HBM peak (rank 0, N=1 only) -------------------------------------
+    amg = None
+    if rank == 0 and world == 1 and not args.no_amg:
+        amg = amg_kernels(local, peak)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -340,7 +381,7 @@ def main():
                        "l2": "inputs larger than L2 (6 x 537 MB fine arrays vs 126 MB L2)",
                        "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured", "final_relres": relres},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks,
+            "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "amg": amg,
         }
         print(json.dumps(line))
     g.close()

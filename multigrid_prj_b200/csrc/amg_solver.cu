@@ -838,6 +838,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     }
     ACK(cudaSetDevice(cfg->device));
     mgb_amg *h = new mgb_amg();
+    struct Guard { mgb_amg *h; ~Guard() { if (h) mgb_amg_destroy(h); } } guard{h};     // any early return frees what exists so far
     h->cfg = *cfg;
     h->rank = rank; h->n_ranks = n_ranks;
     h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
@@ -852,7 +853,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     }
     if (n_ranks > 1) {
         auto &Nc = mgb::nccl();
-        if (!Nc.load()) { delete h; return mgb_set_error(MGB_ERR_NCCL, Nc.error); }
+        if (!Nc.load()) return mgb_set_error(MGB_ERR_NCCL, Nc.error);
         mgb::NcclUniqueId id;
         std::memcpy(&id, nccl_id, sizeof(id));
         ANK(Nc.CommInitRank(&h->comm, n_ranks, id, rank));
@@ -865,8 +866,8 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         A.ptr.assign(n + 1, 0);
         for (size_t i = 0; i < n; ++i) {
             for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
-                if (col[k] < 0 || col[k] >= (int64_t)n) { delete h; return mgb_set_error(MGB_ERR_ARG, "column index out of range"); }
-                if (k > ptr[i] && col[k] <= col[k - 1]) { delete h; return mgb_set_error(MGB_ERR_ARG, "rows must be sorted by column without duplicates"); }
+                if (col[k] < 0 || col[k] >= (int64_t)n) return mgb_set_error(MGB_ERR_ARG, "column index out of range");
+                if (k > ptr[i] && col[k] <= col[k - 1]) return mgb_set_error(MGB_ERR_ARG, "rows must be sorted by column without duplicates");
                 if (val[k] != 0) { A.col.push_back((int)col[k]); A.val.push_back(val[k]); }
             }
             A.ptr[i + 1] = (int)A.col.size();
@@ -959,6 +960,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     ACK(cudaMalloc(&h->d_partial, sizeof(double) * max_blocks));
     ACK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
     ACK(cudaMallocHost(&h->h_scal, sizeof(double) * 4));
+    guard.h = nullptr;
     *out = h;
     return MGB_OK;
 }

@@ -997,13 +997,14 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     CK(cudaSetDevice(cfg->device));
     if (int rc = prepare_kernels()) return rc;
     mgb_gmg *h = new mgb_gmg();
+    struct Guard { mgb_gmg *h; ~Guard() { if (h) mgb_gmg_destroy(h); } } guard{h};     // any early return frees what exists so far
     h->cfg = *cfg;
     h->ls = ls;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     if (cfg->n_ranks > 1) {
         auto &Nc = mgb::nccl();
-        if (!Nc.load()) { delete h; return fail(MGB_ERR_NCCL, Nc.error); }
+        if (!Nc.load()) return fail(MGB_ERR_NCCL, Nc.error);
         mgb::NcclUniqueId id;
         std::memcpy(&id, cfg->nccl_id, sizeof(id));
         NK(Nc.CommInitRank(&h->comm, cfg->n_ranks, id, cfg->rank));
@@ -1052,6 +1053,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     CK(cudaMemsetAsync(h->d_scal, 0, 16 * sizeof(double), h->st));
     CK(cudaMallocHost(&h->h_scal, 16 * sizeof(double)));
     CK(cudaStreamSynchronize(h->st));
+    guard.h = nullptr;
     *out = h;
     return MGB_OK;
 }
