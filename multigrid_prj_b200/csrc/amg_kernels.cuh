@@ -209,12 +209,35 @@ __device__ __forceinline__ double sell_row_dot(const SellDev &A, const double *x
     return sum;
 }
 
+// v + sum_k val_k * x[col_k], added term by term into v with unfused IEEE operations (the reference's prolongation)
+__device__ __forceinline__ double sell_row_add_exact(const SellDev &A, const double *x, int base, int len, double v)
+{
+    for (int k0 = 0; k0 < len; k0 += kSellChunk) {
+        int c[kSellChunk];
+        double w[kSellChunk], xv[kSellChunk];
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u) {
+            const bool ok = k0 + u < len;
+            c[u] = ok ? __ldcs(A.col + base + 32 * (k0 + u)) : -1;
+            w[u] = ok ? __ldcs(A.val + base + 32 * (k0 + u)) : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u) xv[u] = c[u] >= 0 ? x[c[u]] : 0.;
+#pragma unroll
+        for (int u = 0; u < kSellChunk; ++u)
+            if (c[u] >= 0) v = __dadd_rn(v, __dmul_rn(w[u], xv[u]));
+    }
+    return v;
+}
+
 // The operator stream (col, val, diag, rhs, row map) is read exactly once per launch: it is loaded with the streaming
 // (evict-first) hint so that it does not push the vector x -- gathered ~7 times per sweep, once from every colour --
 // out of the 126 MB L2.  ncu before the hint: 793 MB of DRAM traffic for a 447 MB (algorithmic) Jacobi sweep, L2 hit
 // rate 25 % (profiles/r01_ncu_amg_ops_4M.txt).
 // MODE 0: r = b - A x (+ sum r^2 per CTA); MODE 1: Jacobi into `out`; MODE 2: Gauss-Seidel on the slots
-// [first, last) of one colour, in place on x; MODE 3: plain product out[row] = sum (restriction, R = P^T)
+// [first, last) of one colour, in place on x; MODE 3: plain product out[row] = sum (restriction, R = P^T);
+// MODE 4: out[row] += sum with the reference's term order and unfused operations (prolongation x_f += P x_c,
+// AMG/src/AMG.cpp:218-232 -- bit-identical to k_amg_prolong_add)
 // NAT: the copy keeps the natural row order (only permuted inside 512-row windows) and has no slot-ordered vectors:
 // diag_s / b_s are then the level's diag / b, indexed by row.  Jacobi and the residual visit every row once in any
 // order; in natural order the gathers of x stay local, while the colour-sorted copy walks the whole index range once
@@ -234,6 +257,7 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
             const int b0 = A.slice_ptr[s];
             const int base = b0 + (p & 31);
             const int len = (A.slice_ptr[s + 1] - b0) >> 5;
+            if (MODE == 4) { out[i] = sell_row_add_exact(A, x, base, len, out[i]); return; }
             const double sum = sell_row_dot(A, x, base, len);
             if (MODE == 3) out[i] = sum;
             else {

@@ -302,7 +302,7 @@ struct AmgLevel {
     DevCsr A, P, R;
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
     Schedule lex, colour;
-    SellCopy sell, sellN, sellR;               // fast-path copies of A (colour-sorted / natural order) and of this rank's rows of R
+    SellCopy sell, sellN, sellR, sellP;        // fast-path copies of A (colour-sorted / natural order) and of this rank's rows of R and P
     mgb::SellDev natural() const { mgb::SellDev v = sellN.view(); v.diag_s = diag; return v; }
     // sharding: rows [own.r0, own.r1) of this level are smoothed here (the whole level when it is replicated)
     bool sharded = false;
@@ -517,7 +517,7 @@ int build_sell_natural(AmgLevel &L)
     return upload_sell(L.hA, list, true, nullptr, L.sellN, false);
 }
 
-// SELL-32 copy of the rows [own_c.r0, own_c.r1) of R = P^T for the fast restriction (one thread per coarse row)
+// SELL-32 copy of a block of rows of a transfer operator (R = P^T for the restriction, P for the prolongation)
 int build_sell_restriction(const HostCsr &R, Block rows, SellCopy &S)
 {
     std::vector<int> list;
@@ -745,7 +745,9 @@ int do_prolong(mgb_amg *h, int level)
     int rc;
     if (C.sharded && (rc = exchange_all(h, F.haloP, C.x))) return rc;        // coarse entries of other blocks my fine rows interpolate from
     const int rows = F.own.size();
-    if (rows) mgb::k_amg_prolong_add<<<(rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x, F.own.r0, F.own.r1);
+    if (rows && !h->cfg.exact_order)
+        mgb::k_amg_sell<4><<<(F.sellP.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellP.view(), C.x, nullptr, F.x, nullptr, 0, F.sellP.n_slots, 1.0);
+    else if (rows) mgb::k_amg_prolong_add<<<(rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x, F.own.r0, F.own.r1);
     tally(h, (12. * P.nnz + 20. * P.n_rows + 8. * P.n_cols) * (P.n_rows ? (double)rows / P.n_rows : 0.));
     ACK(cudaGetLastError());
     F.x_halo_ok = !F.sharded;
@@ -930,6 +932,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
             // coarse level is then completed by an all-gather), everything otherwise
             L.own_c = L.sharded ? block_of(R.n_rows, n_ranks, rank) : Block{0, R.n_rows};
             if (!cfg->exact_order && (rc = build_sell_restriction(R, L.own_c, L.sellR))) return rc;
+            if (!cfg->exact_order && (rc = build_sell_restriction(L.hP, L.own, L.sellP))) return rc;
             if (L.sharded) {
                 L.haloR = halo_plan(R, n_ranks, rank, nullptr, 1);
                 if ((rc = upload_plan(L.haloR))) return rc;
@@ -972,7 +975,7 @@ void mgb_amg_destroy(mgb_amg_t h)
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (auto &L : h->lv) {
-        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellN.release(); L.sellR.release();
+        L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellN.release(); L.sellR.release(); L.sellP.release();
         L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
     }
