@@ -195,7 +195,9 @@ typedef struct mgb_amg_config {
                               multicolour sweep equals the single-GPU sweep bit for bit; 1: once per sweep ("hybrid"
                               Gauss-Seidel: Jacobi-like across block boundaries, one exchange instead of n_colours) */
     int shard_min_rows;    /* a level is cut into row blocks while it keeps at least this many rows per rank; smaller
-                              levels are replicated on every rank (<= 0: 16384) */
+                              levels are replicated on every rank (<= 0: 262144).  A ghost exchange costs ~25 us (measured,
+                              2 B200): sharding pays only where half a sweep saves more than that, i.e. above ~0.5 M rows
+                              per rank for the hybrid smoother; the 2-GPU runs of round 1 used 16384 */
     double jacobi_omega;   /* MGB_SMOOTH_JACOBI: x <- x + omega (D^-1 (b - (A - D) x) - x); the reference is omega = 1
                               (<= 0 is read as 1) */
     int tail_max_rows;     /* north_star item 3: the trailing levels whose row count is <= this (and that are not sharded)

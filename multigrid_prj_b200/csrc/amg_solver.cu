@@ -797,7 +797,7 @@ void mgb_amg_config_default(mgb_amg_config *c)
     c->device = 0;
     for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
     c->hybrid_gs = 0;
-    c->shard_min_rows = 16384;
+    c->shard_min_rows = 262144;
     c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
     c->tail_max_rows = 4000;
 }
@@ -844,7 +844,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     h->cfg = *cfg;
     h->rank = rank; h->n_ranks = n_ranks;
     h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
-    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 16384;
+    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 262144;
     ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     {
         int coop = 0, sms = 0, per_sm = 0;

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--cycles", type=int, default=10)
     ap.add_argument("--tail-sweep", default="", help="comma-separated tail_max_rows values to time the cycle with (e.g. -1,3000,8000,50000)")
+    ap.add_argument("--min-rows", type=int, default=0, help="shard_min_rows (0: library default; the round-1 2-GPU profiles used 16384)")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -75,9 +76,11 @@ def main():
     A, rhs = synthetic_system(a.side)
     n, nnz = A.shape[0], A.nnz
     t_asm = time.time() - t0
-    out = {"n": n, "nnz": nnz, "levels": a.levels, "n_gpus": world, "peak_gbs_per_gpu": peak, "kernels": {}}
+    out = {"n": n, "nnz": nnz, "levels": a.levels, "n_gpus": world, "peak_gbs_per_gpu": peak, "shard_min_rows": a.min_rows,
+           "kernels": {}}
 
     def make(**kw):
+        kw.setdefault("shard_min_rows", a.min_rows)
         return Amg(A.indptr, A.indices, A.data, rhs, levels=a.levels, fast=True, device=local, rank=rank, n_ranks=world,
                    nccl_id=new_id(), **kw)
 
