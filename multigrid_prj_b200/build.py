@@ -16,7 +16,7 @@ LIB = os.path.join(PKG, "lib", "libmgb200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-fopenmp", "--use_fast_math=false",
 ]
 
 
@@ -68,7 +68,7 @@ def build_lib(force=False, verbose=False):
     # the image's $CC/$CXX wrappers are not usable as nvcc host compilers for shared objects
     with ThreadPoolExecutor(max(len(jobs), 1)) as ex:
         list(ex.map(_compile_one, jobs))
-    cmd = [_nvcc()] + flags[:2] + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++"]
+    cmd = [_nvcc()] + flags[:2] + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp"]
     cmd += ["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "1") == "1" else []
     subprocess.check_call(cmd)
     return LIB

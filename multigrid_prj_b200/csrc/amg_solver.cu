@@ -16,6 +16,9 @@
 #include "nccl_dyn.h"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -49,6 +52,33 @@ struct HostCsr {
         return 0.0;
     }
 };
+
+// The per-row setup loops (interpolation weights, the two products of the Galerkin operator) are independent row by
+// row: they run on the host threads in contiguous row chunks, every row with the same operations in the same order
+// as the serial loop, so the hierarchy does not depend on the thread count.  (The reference's own OpenMP loop over
+// these rows races on std::map, AMG/include/AMG.hpp:314-331.)
+inline int setup_threads(int n_rows)
+{
+#ifdef _OPENMP
+    return std::max(1, std::min(omp_get_max_threads(), n_rows / 4096 + 1));
+#else
+    (void)n_rows;
+    return 1;
+#endif
+}
+
+// out = the row chunks of `part` one after the other; out.ptr holds the row LENGTHS on entry (ptr[i + 1] = length of row i)
+void concat_chunks(HostCsr &out, std::vector<HostCsr> &part, const std::vector<int> &first_row)
+{
+    for (int i = 0; i < out.n_rows; ++i) out.ptr[i + 1] += out.ptr[i];
+    out.col.resize((size_t)out.ptr[out.n_rows]);
+    out.val.resize((size_t)out.ptr[out.n_rows]);
+    for (size_t t = 0; t < part.size(); ++t) {
+        std::copy(part[t].col.begin(), part[t].col.end(), out.col.begin() + out.ptr[first_row[t]]);
+        std::copy(part[t].val.begin(), part[t].val.end(), out.val.begin() + out.ptr[first_row[t]]);
+        HostCsr().col.swap(part[t].col); HostCsr().val.swap(part[t].val);
+    }
+}
 
 // strong couplings of a row: off-diagonal entries with |a_ij| >= eps * max_k |a_ik| (AMG.hpp:105-130)
 void strong_of_row(const HostCsr &A, int i, double eps, std::vector<int> &out)
@@ -106,24 +136,37 @@ HostCsr interpolation(const HostCsr &A, double eps, const std::vector<unsigned c
     for (int i = 0, k = 0; i < n; ++i) if (!(state[i] & 0xC0)) cidx[i] = k++;
     HostCsr P;
     P.n_rows = n; P.n_cols = nc; P.ptr.assign(n + 1, 0);
-    std::vector<int> strong;
-    for (int i = 0; i < n; ++i) {
-        if (!(state[i] & 0xC0)) { P.col.push_back(cidx[i]); P.val.push_back(1.0); P.ptr[i + 1] = (int)P.col.size(); continue; }
-        double off_sum = 0.0;
-        for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) if (A.col[k] != i) off_sum += A.val[k];
-        strong_of_row(A, i, eps, strong);
-        double coarse_sum = 0.0;
-        for (int j : strong) if (!(state[j] & 0xC0)) coarse_sum += A.at(i, j);
-        const double alpha = off_sum / coarse_sum;
-        double norm = 0.0;
-        for (int j : strong) if (!(state[j] & 0xC0)) norm += alpha * A.at(i, j);
-        for (int j : strong)
-            if (!(state[j] & 0xC0)) {
-                const double w = alpha * A.at(i, j) / norm;
-                if (w != 0) { P.col.push_back(cidx[j]); P.val.push_back(w); }     // exact zeros are dropped (CSRMatrix.cpp:13-14)
+    const int T = setup_threads(n);
+    std::vector<HostCsr> part(T);
+    std::vector<int> first(T);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+        const int r0 = (int)((long long)n * t / T), r1 = (int)((long long)n * (t + 1) / T);
+        first[t] = r0;
+        HostCsr &Q = part[t];
+        std::vector<int> strong;
+        for (int i = r0; i < r1; ++i) {
+            const size_t before = Q.col.size();
+            if (!(state[i] & 0xC0)) { Q.col.push_back(cidx[i]); Q.val.push_back(1.0); }
+            else {
+                double off_sum = 0.0;
+                for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) if (A.col[k] != i) off_sum += A.val[k];
+                strong_of_row(A, i, eps, strong);
+                double coarse_sum = 0.0;
+                for (int j : strong) if (!(state[j] & 0xC0)) coarse_sum += A.at(i, j);
+                const double alpha = off_sum / coarse_sum;
+                double norm = 0.0;
+                for (int j : strong) if (!(state[j] & 0xC0)) norm += alpha * A.at(i, j);
+                for (int j : strong)
+                    if (!(state[j] & 0xC0)) {
+                        const double w = alpha * A.at(i, j) / norm;
+                        if (w != 0) { Q.col.push_back(cidx[j]); Q.val.push_back(w); }     // exact zeros are dropped (CSRMatrix.cpp:13-14)
+                    }
             }
-        P.ptr[i + 1] = (int)P.col.size();
+            P.ptr[i + 1] = (int)(Q.col.size() - before);
+        }
     }
+    concat_chunks(P, part, first);
     return P;
 }
 
@@ -163,27 +206,36 @@ struct RowAccumulator {
     }
 };
 
+// out(i, :) = sum over the entries (k, v) of row i of M, in order, of v * B(k, :) -- every row by RowAccumulator::run
+HostCsr row_product(const HostCsr &M, const HostCsr &B)
+{
+    HostCsr out;
+    out.n_rows = M.n_rows; out.n_cols = B.n_cols; out.ptr.assign(M.n_rows + 1, 0);
+    const int T = setup_threads(M.n_rows);
+    std::vector<HostCsr> part(T);
+    std::vector<int> first(T);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+        const int r0 = (int)((long long)M.n_rows * t / T), r1 = (int)((long long)M.n_rows * (t + 1) / T);
+        first[t] = r0;
+        RowAccumulator ra(B.n_cols);
+        HostCsr &Q = part[t];
+        for (int i = r0; i < r1; ++i) {
+            const size_t before = Q.col.size();
+            ra.run(i, &M.col[M.ptr[i]], &M.val[M.ptr[i]], M.ptr[i + 1] - M.ptr[i], B, Q);
+            out.ptr[i + 1] = (int)(Q.col.size() - before);
+        }
+    }
+    concat_chunks(out, part, first);
+    return out;
+}
+
 // Galerkin operator in the reference's evaluation order (AMG.hpp:303-369):
 //   PtA(i,j) = sum_k A(j,k) P(k,i)  (k ascending; A taken as symmetric),   Ac(i,j) = sum_k PtA(i,k) P(k,j)
 HostCsr galerkin(const HostCsr &A, const HostCsr &P)
 {
-    const int n = A.n_rows, nc = P.n_cols;
-    HostCsr AP;                                  // AP(j, i) = PtA(i, j)
-    AP.n_rows = n; AP.n_cols = nc; AP.ptr.assign(n + 1, 0);
-    RowAccumulator ra(std::max(n, nc));
-    for (int j = 0; j < n; ++j) {
-        ra.run(j, &A.col[A.ptr[j]], &A.val[A.ptr[j]], A.ptr[j + 1] - A.ptr[j], P, AP);
-        AP.ptr[j + 1] = (int)AP.col.size();
-    }
-    HostCsr PtA = transpose(AP);
-    HostCsr Ac;
-    Ac.n_rows = nc; Ac.n_cols = nc; Ac.ptr.assign(nc + 1, 0);
-    RowAccumulator rb(std::max(n, nc));
-    for (int i = 0; i < nc; ++i) {
-        rb.run(i, &PtA.col[PtA.ptr[i]], &PtA.val[PtA.ptr[i]], PtA.ptr[i + 1] - PtA.ptr[i], P, Ac);
-        Ac.ptr[i + 1] = (int)Ac.col.size();
-    }
-    return Ac;
+    HostCsr PtA = transpose(row_product(A, P));      // row j of A P holds PtA(:, j)
+    return row_product(PtA, P);
 }
 
 // ---- row-block sharding ----------------------------------------------------------------------
