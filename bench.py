@@ -111,6 +111,24 @@ def cpu_reference(n, levels, cycles, threads=None):
     return n * n * cycles / dt, threads, kind, dt
 
 
+def amg_cpu_baseline(A, rhs, sweeps=2):
+    """the checker's restatement of the reference's Gauss-Seidel loop (AMG/include/Utilities.hpp:44-58) on the host,
+    one core, on the same matrix: the CPU number beside the AMG kernels.  Never fails the bench."""
+    try:
+        import oracle
+        o = oracle.amg()
+        n = A.shape[0]
+        Ao = oracle.Csr(n, n, A.indptr, A.indices, A.data)
+        x = np.zeros(n)
+        t0 = time.perf_counter()
+        o.gs(Ao, rhs, x, sweeps)
+        dt = (time.perf_counter() - t0) / sweeps
+        return {"gs_sweep_ms": dt * 1e3, "achieved": (12.0 * A.nnz + 28.0 * n) / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                "sample": f"{sweeps} lexicographic Gauss-Seidel sweeps of oracle/amg_oracle.c on the same {n}-row matrix"}
+    except Exception as e:                                   # noqa: BLE001 -- a reported baseline, not the product
+        return {"error": repr(e)}
+
+
 def amg_kernels(device, peak, side=2001, reps=20):
     """level-0 kernels of the AMG fast path (multicolour GS, weighted Jacobi, residual, R x, x += P x) timed with CUDA
     events on the library's stream; algorithmic bytes per SURVEY.md section 8d (12 nnz + 28 n per sweep / SpMV)"""
@@ -141,6 +159,7 @@ def amg_kernels(device, peak, side=2001, reps=20):
             launches += int(s_["kernel_launches"])
             out["kernels"][name] = {"ms": ms, "achieved": gbs, "frac": gbs / peak}
         out["gpu_launches"] = launches
+    out["cpu_baseline"] = amg_cpu_baseline(A, rhs)
     return out
 
 

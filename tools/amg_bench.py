@@ -7,8 +7,7 @@ diagonal chosen by a seeded hash, so connectivity and values are unstructured; P
 nodes with the reference's conventions (vertex quadrature, weights 2*area/3, Dirichlet values lifted into the
 right-hand side -- AMG/src/main.cpp:34-117), assembled vectorised on the host (caller side, not the product).
 Reports per level-0 kernel: ms, algorithmic GB/s (12*nnz + 28*n per sweep / SpMV) and fraction of
-the measured HBM peak; the one-pass cycle of the reference (AMG.cpp:277-308) with both smoothers; and the
-oracle's CPU Gauss-Seidel on the same matrix as the baseline.
+the measured HBM peak; the one-pass cycle of the reference (AMG.cpp:277-308) and correction-scheme cycles.
 """
 import argparse
 import json
@@ -141,18 +140,8 @@ def main():
     print(f"correction-scheme V(2,2), multicolour GS: {cyc} cycles to {hist[-1] / hist[0]:.1e} in {dt * 1e3:.1f} ms "
           f"({1e3 * dt / max(cyc, 1):.2f} ms/cycle, {n * cyc / dt / 1e9:.2f} GDoF*cycles/s, reduction {out['correction_scheme']['mean_reduction_per_cycle']:.3f}/cycle)")
     amg.close()
-    # CPU baseline: the oracle's restatement of the reference's Gauss-Seidel loop on the same matrix (1 core)
-    import oracle
-    o = oracle.amg()
-    Ao = oracle.Csr(n, n, A.indptr, A.indices, A.data)
-    x = np.zeros(n)
-    t0 = time.perf_counter()
-    o.gs(Ao, rhs, x, 2)
-    dt = (time.perf_counter() - t0) / 2
-    out["cpu_baseline"] = {"kind": "port", "cores": 1, "gs_sweep_ms": dt * 1e3, "ns_per_nnz": dt * 1e9 / nnz,
-                           "note": "oracle/amg_oracle.c amgo_gs_sweep; the reference's own loop copies every row to the heap "
-                                   "(CSRMatrix.cpp:42-52) and measured 7.5 ns/nnz (SURVEY 8a a13)"}
-    print(f"CPU Gauss-Seidel sweep (oracle port, 1 core): {dt * 1e3:.1f} ms = {dt * 1e9 / nnz:.2f} ns/nnz")
+    # (the CPU baseline of these kernels -- the checker's Gauss-Seidel loop on the same matrix -- is timed by bench.py,
+    #  the only bench that may execute oracle/: see the `amg.cpu_baseline` object of its JSON line)
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)
 
