@@ -14,7 +14,12 @@ One "step" = one driver iteration of the reference (GeometricMultigrid/src/main.
            box's host cores, on a bounded sample of the same workload.
   amg      = (N=1 only; the second half of BASELINE.json's metric, "smoother/SpMV HBM GB/s vs peak") the level-0
            AMG kernels on a 4 M DoF synthetic unstructured triangulation: ms, algorithmic GB/s, fraction of peak.
-Workloads: N=1 -> config C3 (8193^2, L=13); N>1 -> config C4 (16385^2, L=14) in row slabs.
+Workloads: N=1 -> config C3 (8193^2, L=13, BASELINE configs[2]); N>1 -> config C4 (16385^2, L=14, configs[3]) in row
+slabs.  The N=1 line also carries `c4_single_gpu` (the 16385^2 grid on one GPU), so scaling can be taken on ONE grid.
+  parity (N>1) = rank 0 repeats the same iterations on ONE GPU and the 64-bit checksum of u over all ranks must
+           equal the single-GPU one (bit-identical slabs); a mismatch fails the run.
+  value is timed with the residual norm all-reduced inside every iteration (as the reference's loop reads it every
+           iteration); `value_deferred_norm` is the variant with one all-reduce at the end.
 """
 import argparse
 import json
@@ -175,12 +180,14 @@ def run_reference(args):
         if i >= args.warmup:
             vals.append((v, dt))
     value = n * n * len(vals) / sum(d for _, d in vals)
-    workload = workload_name(args)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload},
+        "config": config_of(args),
+        "sample_config": {"ran": f"GMG 2D Poisson {n}x{n}, L={levels}, test {TEST}, lexicographic GS (the reference's own classes)",
+                          "why": "bounded sample of the arm's workload: the reference needs ~100 s and 16 GB per iteration at "
+                                 "8193^2; its cost per DoF does not depend on the grid size"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"each step = 1 driver iteration (2 GS + sawtooth cycle + residual) of the "
                                    f"reference's GS solver on {n}^2, L={levels}, test {TEST}; throughput per DoF is "
@@ -197,6 +204,36 @@ def workload_name(args):
     n, L = problem(args)
     return (f"GMG 2D Poisson {n}x{n} ({n * n / 1e6:.0f}M DoF), L={L}, test {TEST}, alpha={ALPHA}, W={LENGTH}, "
             f"u0=0; {args.mode} mode")
+
+
+def config_of(args):
+    """the SAME dictionary on both arms (the driver compares them); run-dependent values live outside `config`"""
+    n, L = problem(args)
+    return {"workload": workload_name(args), "grid": n, "levels": L,
+            "baseline_config": "configs[2] (8193^2 on 1 B200)" if n == 8193 else ("configs[3] (16385^2 in row slabs)" if n == 16385 else "custom"),
+            "l2": "inputs larger than L2 (fine arrays of 0.5-2 GB vs 126 MB L2)"}
+
+
+def timed_steps_single(h, timer, steps):
+    h.sync()
+    timer.start(h.stream())
+    h.run_cycles(steps, want_relres=False)
+    timer.stop(h.stream())
+    return timer.elapsed_ms()
+
+
+def ncu_traffic(kernel_regex):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the newest committed `ncu --set full` summary under
+    profiles/ that names the kernel (a TRAFFIC_BYTES line written next to the capture); None if there is none"""
+    import glob
+    import re
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*full*.txt"))):
+        txt = open(f, errors="ignore").read()
+        m = re.search(r"^TRAFFIC_BYTES\s+([0-9.eE+]+)", txt, re.M)
+        if m and re.search(kernel_regex, txt):
+            best = (float(m.group(1)), os.path.relpath(f, ROOT))
+    return best
 
 
 def problem(args):
@@ -219,6 +256,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG kernel leg (N=1 only)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the single-GPU repeat + checksum comparison")
+    ap.add_argument("--no-c4", action="store_true", help="N=1: skip the 16385^2 single-GPU line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -263,28 +302,63 @@ def main():
     g.set_u(None)
     timer = Timer()
     st = g.stream()
+
+    def timed_steps(h, steps):
+        """K driver iterations, device-timed on the library's stream, max over ranks"""
+        h.sync(); barrier()
+        h.reset_stats()
+        timer.start(h.stream())
+        h.run_cycles(steps, want_relres=False)
+        timer.stop(h.stream())
+        t_ms = timer.elapsed_ms()
+        h.sync(); barrier()
+        if dist is not None:
+            import torch
+            t = torch.tensor([t_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
     # ---- device-resident throughput ------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.wait_started()
     g.run_cycles(args.warmup)
     g.run_cycles(4)          # 4 more untimed steps: lets the library capture its CUDA graph for this buffer state
-    g.sync(); barrier()
-    g.reset_stats()
-    timer.start(st)
-    g.run_cycles(args.steps, want_relres=False)
-    timer.stop(st)
-    ms = timer.elapsed_ms()
-    g.sync(); barrier()
+    ms = timed_steps(g, args.steps)          # the norm of every iteration is all-reduced inside the loop (defer_norm = 0)
     stats = g.stats()
+    total_cycles = args.warmup + 4 + args.steps
+    u_checksum = g.checksum()
     relres = g.run_cycles(0)
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     dof = float(n) * float(n)
     value = dof * args.steps / (ms * 1e-3)
+    deferred = None
+    if world > 1:            # named extra: one all-reduce at the end instead of one per iteration
+        from multigrid_prj_b200._lib import check
+        check(g.lib.mgb_gmg_set_defer_norm(g.h, 1))
+        g.run_cycles(4)
+        ms_d = timed_steps(g, args.steps)
+        check(g.lib.mgb_gmg_set_defer_norm(g.h, 0))
+        deferred = {"value": dof * args.steps / (ms_d * 1e-3), "ms_per_step": ms_d / args.steps,
+                    "what": "same steps with mgb_gmg_config.defer_norm = 1: every rank keeps its partial sum, one all-reduce when the norm is read"}
+
+    # ---- parity of the slab decomposition: the same iterations on ONE GPU, checksums must agree ------------------
+    parity = {"u_checksum": f"{u_checksum:#018x}", "cycles": total_cycles}
+    parity_ok = True
+    if world > 1 and not args.no_parity:
+        if rank == 0:
+            c1 = GmgConfig.fast(n, L, length=LENGTH, alpha=ALPHA, device=local) if args.mode == "fast" else None
+            if c1 is not None:
+                with Gmg(c1) as g1:
+                    g1.set_rhs_test(TEST); g1.set_u(None)
+                    g1.run_cycles(args.warmup); g1.run_cycles(4); g1.run_cycles(args.steps, want_relres=False)
+                    ref_sum = g1.checksum()
+                    t1 = timed_steps_single(g1, timer, args.steps)
+                parity.update(single_gpu_checksum=f"{ref_sum:#018x}", match=bool(ref_sum == u_checksum),
+                              single_gpu_same_grid={"value": dof * args.steps / (t1 * 1e-3), "ms_per_step": t1 / args.steps,
+                                                    "what": f"the same {n}^2 grid on one GPU of this box (rank 0), for scaling on one grid"})
+                parity_ok = bool(ref_sum == u_checksum)
+        barrier()
 
     # ---- dominant kernel alone ---------------------------------------------------------------------------
     # fast path on one rank: the fused fine-level launch of the upward leg (prolongation from level 1 + nu red-black
@@ -301,9 +375,9 @@ def main():
         kname = (f"k_rb_stream<{2 * cfg.nu}, EXACT=0, MODE=1, PIN=1>: prolongation + {cfg.nu} red-black sweeps + correction + "
                  f"residual norm in one launch ({cfg.nu} x 24 + 10 + 24 + 16 B/pt algorithmic)")
         moved = 26.0 * n * rows0                      # read res 8, u 8, coarse err 2; write u 8
-        traffic, traffic_src = 1.725148e9, "profiles/r01_ncu_fine_leg_full.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch at 8193^2)"
-        if n != 8193:
-            traffic, traffic_src = None, None
+        tr = ncu_traffic(r"k_rb_stream<10, 0, 1, 1>") if n == 8193 else None
+        traffic, traffic_src = (tr[0], tr[1] + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch at 8193^2; "
+                                "read from the committed file, not measured in this run)") if tr else (None, None)
     else:
         run_k = lambda: g.smooth(0, kind, sweeps=group, sol=G.VEC_E, rhs=G.VEC_R)
         kname = {G.GS_RB: (f"k_rb_stream<{2 * group}> ({group} fused red-black sweeps per launch = {group} x 24 B/pt algorithmic)")
@@ -344,15 +418,10 @@ def main():
         import torch
         r0, rows = g.rows(0)
         f_host = torch.empty((rows, n), dtype=torch.float64).pin_memory()
-        u_host = torch.zeros((rows, n), dtype=torch.float64).pin_memory()
+        u_host = torch.empty((rows, n), dtype=torch.float64).pin_memory()
         fh, uh = f_host.numpy(), u_host.numpy()
-        gl = np.zeros((n, n)) if world == 1 else None
-        if world == 1:
-            fh[:] = g.get_level(0, G.VEC_F)
-        else:                                   # multi-rank: refill the slab from the device-resident f
-            from multigrid_prj_b200._lib import check
-            check(g.lib.mgb_gmg_get_level(g.h, 0, G.VEC_F, C.c_void_p(fh.ctypes.data - r0 * n * 8)))
-        del gl
+        from multigrid_prj_b200._lib import check
+        check(g.lib.mgb_gmg_get_level(g.h, 0, G.VEC_F, C.c_void_p(fh.ctypes.data - r0 * n * 8)))   # the slab of f, from the device
         fptr = C.c_void_p(fh.ctypes.data - r0 * n * 8)
         uptr = C.c_void_p(uh.ctypes.data - r0 * n * 8)
         from multigrid_prj_b200._lib import check
@@ -361,7 +430,7 @@ def main():
         g.sync(); barrier()
         t0 = time.perf_counter()
         check(g.lib.mgb_gmg_set_rhs(g.h, fptr))
-        check(g.lib.mgb_gmg_set_u(g.h, uptr))
+        check(g.lib.mgb_gmg_set_u(g.h, None))            # u0 = 0 (main.cpp:49): NULL = zero-fill on the device, nothing to upload
         check(g.lib.mgb_gmg_solve(g.h, 0.0, args.steps, 1, hist.ctypes.data_as(C.c_void_p), C.byref(nh)))
         check(g.lib.mgb_gmg_get_u(g.h, uptr))
         barrier()
@@ -372,8 +441,9 @@ def main():
             dt = float(t.item())
         slab_bytes = float(rows) * n * 8
         e2e = {"value": dof * args.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": 2 * slab_bytes / args.steps, "d2h_bytes_per_step": slab_bytes / args.steps + 8,
-               "what": f"per rank: mgb_gmg_set_rhs + mgb_gmg_set_u (pinned host slab -> HBM), mgb_gmg_solve with "
+               "h2d_bytes_per_step": slab_bytes / args.steps, "d2h_bytes_per_step": slab_bytes / args.steps + 8,
+               "seconds": dt, "pcie_floor_note": "the two slab copies alone take ~2 x slab_bytes / 50 GB/s; the solve is PCIe-bound below ~40 steps",
+               "what": f"per rank: mgb_gmg_set_rhs (pinned host slab -> HBM), mgb_gmg_set_u(NULL) (u0 = 0: device fill), mgb_gmg_solve with "
                        f"{args.steps} steps each reading its residual norm back, mgb_gmg_get_u (HBM -> pinned host); "
                        f"wall clock, max over ranks; bytes are per rank", "final_relres": float(hist[nh.value - 1])}
 
@@ -391,21 +461,40 @@ def main():
     if rank == 0 and world == 1 and not args.no_amg:
         amg = amg_kernels(local, peak)
 
+    g.close()
+    # ---- N=1 only: the slab runs' grid (config C4, 16385^2) on this one GPU, so that scaling can be taken on one grid -------
+    c4 = None
+    if rank == 0 and world == 1 and n == 8193 and not args.no_c4 and args.mode == "fast":
+        with Gmg(GmgConfig.fast(16385, 14, length=LENGTH, alpha=ALPHA, device=local)) as g4:
+            g4.set_rhs_test(TEST); g4.set_u(None)
+            g4.run_cycles(args.warmup); g4.run_cycles(4)
+            t4 = timed_steps_single(g4, timer, args.steps)
+            c4 = {"value": 16385.0 ** 2 * args.steps / (t4 * 1e-3), "ms_per_step": t4 / args.steps, "u_checksum": f"{g4.checksum():#018x}",
+                  "cycles": args.warmup + 4 + args.steps,
+                  "what": "GMG 2D Poisson 16385x16385, L=14 (BASELINE configs[3]) on ONE B200: the N=1 point of the slab runs' grid"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "smoother": cfg.smoother, "restriction": cfg.restriction,
-                       "l2": "inputs larger than L2 (6 x 537 MB fine arrays vs 126 MB L2)",
-                       "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured", "final_relres": relres},
+            "config": config_of(args),
+            "scaling_note": "N=1 runs BASELINE configs[2] (8193^2), N>=2 run configs[3] (16385^2 in row slabs): total work is fixed "
+                            "among N>=2 (strong); the N=1 line's c4_single_gpu and every N>1 line's parity.single_gpu_same_grid give "
+                            "the 16385^2 grid on one GPU for an efficiency on one grid",
+            "run": {"smoother": cfg.smoother, "restriction": cfg.restriction, "final_relres": relres,
+                    "norm": "all-reduced inside every iteration" if world > 1 else "single rank",
+                    "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "amg": amg,
+            "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "parity": parity,
+            "value_deferred_norm": deferred, "c4_single_gpu": c4, "amg": amg,
         }
         print(json.dumps(line))
-    g.close()
     if dist is not None:
         dist.destroy_process_group()
+    if not parity_ok:
+        print("bench.py: PARITY FAILURE: the slab-decomposed u differs from the single-GPU u (checksums above)", file=sys.stderr)
+        return 3
     return 0
 
 

@@ -85,7 +85,9 @@ typedef struct mgb_gmg_config {
     int fuse_prolong;     /* red-black fused path only: the first post-smoothing launch of a level interpolates its input
                              from the coarser level on the fly (multigrid.cpp:3-27, same arithmetic); the prolonged field
                              is never written to HBM */
-    int reserved0;
+    int defer_norm;       /* slabs (n_ranks > 1), mgb_gmg_run_cycles only: 0 (default) = the residual norm of every iteration is
+                             all-reduced inside the loop, as the reference's loop reads it every iteration (main.cpp:86-90);
+                             1 = every rank keeps its partial sum and the all-reduce happens once, when the norm is read */
     double jacobi_omega;  /* MGB_SMOOTH_JACOBI: u <- u + omega (u_jacobi - u) on interior points.  The reference is
                              omega = 1 (solvers.hpp:64-83) and that value keeps the bit-identical path; other values
                              (north_star: weighted Jacobi) run level by level without the persistent tail kernel.
@@ -141,6 +143,9 @@ int mgb_gmg_prolong(mgb_gmg_t h, int level_coarse);
  * handle keeps one hierarchy and switches the cycle's parameters instead */
 int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double coarse_tol, int coarse_maxit);
 
+/* switches mgb_gmg_config.defer_norm of a live handle (measurement: the same handle timed both ways) */
+int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer);
+
 /* replaces SawtoothMGIteration::apply_iteration_to_vec (multigrid.hpp:126-145) applied to u.
  * coarse_relres = the value the reference prints per cycle; coarse_iters = coarse-solve sweeps. */
 int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters);
@@ -157,6 +162,12 @@ int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres);
 /* the fine-level part of the upward leg (multigrid.hpp:134-144 for j = 1): E(1) -> E(0) prolongation, nu sweeps on
  * level 0 against R(0), u += err, and sum (f - A u)^2 of the new u.  One fused launch on the fast path. */
 int mgb_gmg_fine_leg(mgb_gmg_t h, double *sumsq);
+
+/* 64-bit checksum of a level vector over ALL ranks (wrap-around sum of bit pattern x (2 * global index + 1) over the
+ * points; integer addition is associative, so the value is independent of the slab partition and of the launch
+ * geometry).  Equal checksums on 1 and N ranks <=> the slab-decomposed solve is bit-identical to the single-GPU one;
+ * bench.py asserts exactly that.  Collective when n_ranks > 1. */
+int mgb_gmg_checksum(mgb_gmg_t h, int level, int which, uint64_t *out);
 
 /* measurement hooks */
 typedef struct mgb_gmg_stats {

@@ -20,7 +20,7 @@ class GmgConfigStruct(C.Structure):
                 ("coarse_tol", C.c_double), ("coarse_maxit", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
                 ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("rb_fast_arith", C.c_int),
-                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("reserved0", C.c_int),
+                ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("defer_norm", C.c_int),
                 ("jacobi_omega", C.c_double)]
 
 
@@ -62,10 +62,12 @@ SYMBOLS = {
     "mgb_gmg_restrict": (_i, [_vp]),
     "mgb_gmg_prolong": (_i, [_vp, _i]),
     "mgb_gmg_set_cycle": (_i, [_vp, _i, _i, _i, _d, _i]),
+    "mgb_gmg_set_defer_norm": (_i, [_vp, _i]),
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
     "mgb_gmg_fine_leg": (_i, [_vp, _pd]),
     "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),
     "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),
+    "mgb_gmg_checksum": (_i, [_vp, _i, _i, C.POINTER(C.c_uint64)]),
     "mgb_gmg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
     "mgb_gmg_reset_stats": (_i, [_vp]),
     "mgb_gmg_stream": (_vp, [_vp]),

@@ -69,7 +69,8 @@ def build_lib(force=False, verbose=False):
     with ThreadPoolExecutor(max(len(jobs), 1)) as ex:
         list(ex.map(_compile_one, jobs))
     cmd = [_nvcc()] + flags[:2] + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp"]
-    cmd += ["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "1") == "1" else []
+    # NCCL is bound with dlopen at run time (csrc/nccl_dyn.h): no link-time dependency unless asked for
+    cmd += ["-ldl"] + (["-lnccl"] if os.environ.get("MGB_LINK_NCCL", "0") == "1" else [])
     subprocess.check_call(cmd)
     return LIB
 

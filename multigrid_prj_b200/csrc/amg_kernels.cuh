@@ -419,6 +419,8 @@ __device__ __forceinline__ unsigned hash32(unsigned x)
 }
 // One round: an uncoloured row whose (hash, index) priority beats all its uncoloured neighbours takes the
 // smallest colour no neighbour holds.  colour[i] < 0 = uncoloured.  *remaining counts rows left.
+// The colours in use are collected 64 at a time (window base, base + 64, ...), so rows of dense Galerkin levels
+// whose neighbours already hold colours 0..63 still find one.
 __global__ void __launch_bounds__(256)
 k_amg_colour_round(CsrDev A, const int *__restrict__ colour_in, int *__restrict__ colour_out, int *remaining)
 {
@@ -427,20 +429,27 @@ k_amg_colour_round(CsrDev A, const int *__restrict__ colour_in, int *__restrict_
     int c = colour_in[i];
     if (c >= 0) { colour_out[i] = c; return; }
     const unsigned pi = hash32((unsigned)i);
-    unsigned long long used = 0ull;
+    const int k0 = A.ptr[i], k1 = A.ptr[i + 1];
     bool top = true;
-    for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+    for (int k = k0; k < k1 && top; ++k) {
         const int j = A.col[k];
-        if (j == i) continue;
-        const int cj = colour_in[j];
-        if (cj >= 0) { if (cj < 64) used |= 1ull << cj; }
-        else {
-            const unsigned pj = hash32((unsigned)j);
-            if (pj > pi || (pj == pi && j > i)) top = false;
-        }
+        if (j == i || colour_in[j] >= 0) continue;
+        const unsigned pj = hash32((unsigned)j);
+        if (pj > pi || (pj == pi && j > i)) top = false;
     }
-    if (top) c = __ffsll((long long)~used) - 1;
-    else atomicAdd(remaining, 1);
+    if (top) {
+        for (int base = 0; c < 0; base += 64) {
+            unsigned long long used = 0ull;
+            for (int k = k0; k < k1; ++k) {
+                const int j = A.col[k];
+                if (j == i) continue;
+                const int cj = colour_in[j] - base;
+                if (cj >= 0 && cj < 64) used |= 1ull << cj;
+            }
+            if (~used) c = base + __ffsll((long long)~used) - 1;
+        }
+    } else
+        atomicAdd(remaining, 1);
     colour_out[i] = c;
 }
 

@@ -711,7 +711,7 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
         if ((rc = need_x_halo(h, L))) return rc;
         for (int s = 0; s < sweeps; ++s) {
             if (h->cfg.exact_order) {
-                if (rows) mgb::k_amg_jacobi_vec<<<(rows * mgb::kLanes + 255) / 256, 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp, h->omega, L.own.r0, L.own.r1);
+                if (rows) mgb::k_amg_jacobi_vec<<<(unsigned)(((size_t)rows * mgb::kLanes + 255) / 256), 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp, h->omega, L.own.r0, L.own.r1);
             } else if (L.sellN.n_slots)
                 mgb::k_amg_sell<1, true><<<(L.sellN.n_slots + 255) / 256, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, nullptr, 0, L.sellN.n_slots, h->omega);
             tally(h, sweep_bytes(L));
@@ -1006,7 +1006,7 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
             if ((rc = upload_plan(L.haloA_colour))) return rc;
             max_halo = std::max<size_t>(max_halo, std::max(L.haloA.n_send(), L.haloA.n_recv()));
         }
-        max_blocks = std::max(max_blocks, (size_t)(nl * mgb::kLanes + 255) / 256 + 1);
+        max_blocks = std::max(max_blocks, ((size_t)nl * mgb::kLanes + 255) / 256 + 1);
     }
     if (n_ranks > 1) {
         ACK(cudaMalloc(&h->d_send, sizeof(double) * max_halo));

@@ -347,6 +347,24 @@ k_gs_lex_band(LevelGeom g, double *u, const double *__restrict__ b, int band0, i
     }
 }
 
+// ---- 64-bit checksum of a level vector: wrap-around sum of the bit patterns of the owned points -----------------
+// Integer addition is associative, so the value does not depend on the launch geometry, on the slab
+// partition or on the order of the atomics: equal checksums <=> (up to collisions) bit-identical vectors.
+__global__ void __launch_bounds__(256)
+k_checksum(LevelGeom g, const double *__restrict__ v, unsigned long long *out)
+{
+    unsigned long long acc = 0ull;
+    for (int i = blockIdx.y; i < g.rows; i += gridDim.y)
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < g.w; j += gridDim.x * blockDim.x) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[(size_t)i * g.pitch + j]);
+            // position-dependent mixing, so that a permutation of the values changes the sum
+            acc += bits * (2ull * (unsigned long long)((size_t)(g.row0 + i) * g.w + j) + 1ull);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 // ---- rhs sampling on device (linear_system.hpp:85-92 with utilities.cpp:138-147) -------------------
 __global__ void __launch_bounds__(256)
 k_sample_rhs(LevelGeom g, double *__restrict__ b, double length, int test)

@@ -124,7 +124,10 @@ struct mgb_gmg {
     int n_sm = 148;
     mgb_gmg_stats stats{};
     // CUDA graphs of `period` driver iterations, keyed by the buffer-pointer state they were captured in
-    struct IterGraph { std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; unsigned scal_local; };
+    struct IterGraph {
+        std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; unsigned scal_local;
+        int end_u_halo_valid; bool end_r0_ready, end_r1_ready;     // host-side state one replay leaves behind
+    };
     std::vector<IterGraph> graphs;
 
     double **vec(int level, int which)
@@ -725,7 +728,7 @@ int one_iteration_ca(mgb_gmg *h)
         h->u_halo_valid = ext_u;
         const int np = h->norm_partials;
         h->norm_partials = 0;
-        return reduce_partials(h, np, 1, true, true);
+        return reduce_partials(h, np, 1, true, h->cfg.defer_norm != 0);
     }
     if ((rc = finish_cycle(h))) return rc;
     // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
@@ -853,6 +856,13 @@ std::vector<const double *> pointer_state(mgb_gmg *h)
     for (auto &lv : h->lv) { k.push_back(lv.u); k.push_back(lv.tu); k.push_back(lv.e); k.push_back(lv.t); k.push_back(lv.r); }
     k.push_back((const double *)(uintptr_t)((h->cfg.smoother << 8) | (h->cfg.pre_smoother << 4) | h->cfg.restriction));
     k.push_back((const double *)(uintptr_t)((h->cfg.nu << 8) | h->cfg.n_pre));
+    // everything else the captured launches depend on: whether the leading exchange of u is skipped
+    // (one_iteration_ca), the coarse-solve parameters baked into TailParams, the norm's all-reduce placement
+    const bool halo_ok = ca_applicable(h) && h->u_halo_valid >= ca_u_depth(h, plan_depths(h));
+    k.push_back((const double *)(uintptr_t)((halo_ok ? 1u : 0u) | (h->cfg.defer_norm ? 2u : 0u) | ((unsigned)h->cfg.coarse_maxit << 2)));
+    uint64_t tol_bits;
+    std::memcpy(&tol_bits, &h->cfg.coarse_tol, sizeof(tol_bits));
+    k.push_back((const double *)(uintptr_t)tol_bits);
     return k;
 }
 
@@ -864,6 +874,13 @@ int run_iterations(mgb_gmg *h, int cycles)
     const bool graph_ok = h->cfg.use_graph && h->lt >= 0;       // the cycle must be free of host synchronisation
     while (cycles > 0) {
         if (graph_ok) {
+            // slabs: the first iteration after u was set from outside posts the leading exchange of u; every later one
+            // starts with the halo the previous iteration left.  Only the second kind is captured.
+            if (ca_applicable(h) && h->u_halo_valid < ca_u_depth(h, plan_depths(h))) {
+                if ((rc = one_iteration(h))) return rc;
+                --cycles;
+                continue;
+            }
             auto key = pointer_state(h);
             mgb_gmg::IterGraph *g = nullptr;
             for (auto &c : h->graphs) if (c.key == key) g = &c;
@@ -871,6 +888,8 @@ int run_iterations(mgb_gmg *h, int cycles)
             if (!g) {
                 const mgb_gmg_stats before = h->stats;
                 const unsigned local_before = h->scal_local;
+                const int halo_before = h->u_halo_valid;
+                const bool r0_before = h->r0_ready, r1_before = h->r1_ready;
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
                 int period = 0;
@@ -880,9 +899,11 @@ int run_iterations(mgb_gmg *h, int cycles)
                 // capturing executes nothing: restore the counters and (after an odd number of swaps) the pointers
                 mgb_gmg::IterGraph ng{key, nullptr, period, h->stats.kernel_launches - before.kernel_launches,
                                       h->stats.bytes_algorithmic - before.bytes_algorithmic,
-                                      h->stats.reserved[0] - before.reserved[0], h->scal_local & 2u};
+                                      h->stats.reserved[0] - before.reserved[0], h->scal_local & 2u,
+                                      h->u_halo_valid, h->r0_ready, h->r1_ready};
                 h->stats = before;
                 h->scal_local = local_before;
+                h->u_halo_valid = halo_before; h->r0_ready = r0_before; h->r1_ready = r1_before;
                 if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
                 if (pointer_state(h) != key) { cudaGraphDestroy(graph); return fail(MGB_ERR_STATE, "buffer rotation has no short period"); }
@@ -899,6 +920,7 @@ int run_iterations(mgb_gmg *h, int cycles)
                 h->stats.reserved[0] += g->exchanges;
                 h->stats.cycles += g->period;
                 h->scal_local = (h->scal_local & ~2u) | g->scal_local;
+                h->u_halo_valid = g->end_u_halo_valid; h->r0_ready = g->end_r0_ready; h->r1_ready = g->end_r1_ready;
                 cycles -= g->period;
                 continue;
             }
@@ -1198,6 +1220,13 @@ int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double
     return MGB_OK;
 }
 
+int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer)
+{
+    if (!h) return fail(MGB_ERR_ARG, "null handle");
+    h->cfg.defer_norm = defer ? 1 : 0;
+    return MGB_OK;
+}
+
 int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters)
 {
     if (!h) return fail(MGB_ERR_ARG, "null handle");
@@ -1284,6 +1313,29 @@ int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres)
         if ((rc = read_scalar(h, 1, &ss))) return rc;
         *final_relres = std::sqrt(ss / h->norm_f);
     }
+    return MGB_OK;
+}
+
+int mgb_gmg_checksum(mgb_gmg_t h, int level, int which, uint64_t *out)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !out) return fail(MGB_ERR_ARG, "bad level/pointer");
+    double **v = h->vec(level, which);
+    if (!v) return fail(MGB_ERR_ARG, "vector does not exist on this level");
+    CK(cudaSetDevice(h->cfg.device));
+    const Level &L = h->lv[level];
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->d_scal + 8);
+    CK(cudaMemsetAsync(d, 0, sizeof(*d), h->st));
+    LevelGeom g = L.g;
+    if (!L.sharded && h->cfg.n_ranks > 1) {          // replicated level: every rank holds all of it; rank 0's copy counts
+        if (h->cfg.rank != 0) g.rows = 0;
+    }
+    if (g.rows > 0) mgb::k_checksum<<<dim3(std::min((g.w + 255) / 256, 64), std::min(g.rows, 1024)), 256, 0, h->st>>>(g, *v, d);
+    CK(cudaGetLastError());
+    if (h->cfg.n_ranks > 1) NK(mgb::nccl().AllReduce(d, d, 1, mgb::kNcclUint64, mgb::kNcclSum, h->comm, h->st));
+    unsigned long long hv = 0;
+    CK(cudaMemcpyAsync(&hv, d, sizeof(hv), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    *out = (uint64_t)hv;
     return MGB_OK;
 }
 

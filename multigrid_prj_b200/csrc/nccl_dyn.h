@@ -14,7 +14,7 @@ namespace mgb {
 
 struct NcclUniqueId { char internal[128]; };      // NCCL_UNIQUE_ID_BYTES
 typedef struct ncclComm *NcclComm;
-enum { kNcclSuccess = 0, kNcclSum = 0, kNcclFloat64 = 8 };
+enum { kNcclSuccess = 0, kNcclSum = 0, kNcclUint8 = 1, kNcclUint64 = 5, kNcclFloat64 = 8 };
 
 struct NcclApi {
     void *lib = nullptr;
@@ -24,6 +24,7 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -47,6 +48,7 @@ struct NcclApi {
         MGB_NCCL_SYM(Send, "ncclSend")
         MGB_NCCL_SYM(Recv, "ncclRecv")
         MGB_NCCL_SYM(AllReduce, "ncclAllReduce")
+        MGB_NCCL_SYM(AllGather, "ncclAllGather")
         MGB_NCCL_SYM(GroupStart, "ncclGroupStart")
         MGB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         MGB_NCCL_SYM(GetErrorString, "ncclGetErrorString")

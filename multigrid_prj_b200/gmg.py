@@ -40,6 +40,7 @@ class GmgConfig:
     fuse_correction: int = 0
     fuse_residual: int = 0
     fuse_prolong: int = 0
+    defer_norm: int = 0
     jacobi_omega: float = 1.0
 
     @staticmethod
@@ -77,7 +78,7 @@ class Gmg:
         self.lib.mgb_gmg_config_default(C.byref(c))
         for k in ("n", "levels", "length", "alpha", "smoother", "pre_smoother", "n_pre", "nu",
                   "restriction", "coarse_tol", "coarse_maxit", "device", "rank", "n_ranks",
-                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong",
+                  "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong", "defer_norm",
                   "jacobi_omega"):
             setattr(c, k, getattr(cfg, k))
         if cfg.nccl_id:
@@ -186,6 +187,12 @@ class Gmg:
         rel = C.c_double()
         check(self.lib.mgb_gmg_run_cycles(self.h, cycles, C.byref(rel) if want_relres else None))
         return rel.value
+
+    def checksum(self, level=0, which=VEC_U):
+        """64-bit checksum over all ranks (collective when n_ranks > 1): equal <=> bit-identical vectors"""
+        v = C.c_uint64()
+        check(self.lib.mgb_gmg_checksum(self.h, level, which, C.byref(v)))
+        return v.value
 
     def sync(self):
         check(self.lib.mgb_gmg_sync(self.h))

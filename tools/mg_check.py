@@ -99,6 +99,29 @@ def main():
             rel_ref = ref.run_cycles(6)
             report(f"[{mode}] run_cycles(6): solution bit-identical", np.array_equal(got, ref.get_u()))
             report(f"[{mode}] run_cycles(6): final residual", abs(rel - rel_ref) <= 1e-9 * rel_ref, f"{rel} vs {rel_ref}")
+        # (4) cached graphs against state changes between calls (round-1 advisor finding): run_cycles(3) runs uncaptured and
+        # leaves the halo of u valid, run_cycles(4) captures a graph without the leading exchange, set_u(random) invalidates
+        # the halo, the next run_cycles must not replay that graph on stale halo rows; same for set_cycle(coarse_maxit)
+        g.set_rhs_test(1); g.set_u(None)
+        g.run_cycles(3); g.run_cycles(4)
+        g.set_u(u0)
+        g.run_cycles(6)
+        got = assemble(g, n, g.get_u)
+        cs = g.checksum()
+        if rank == 0:
+            ref.set_rhs_test(1); ref.set_u(None)
+            ref.run_cycles(3); ref.run_cycles(4)
+            ref.set_u(u0)
+            ref.run_cycles(6)
+            report(f"[{mode}] run_cycles(3); run_cycles(4); set_u(random); run_cycles(6): bit-identical", np.array_equal(got, ref.get_u()))
+            report(f"[{mode}] checksum over ranks == single-rank checksum", cs == ref.checksum(), f"{cs:#x}")
+        g.lib.mgb_gmg_set_cycle(g.h, cfg.smoother, cfg.restriction, cfg.nu, 0.5, 3)
+        g.run_cycles(4)
+        got = assemble(g, n, g.get_u)
+        if rank == 0:
+            ref.lib.mgb_gmg_set_cycle(ref.h, cfg.smoother, cfg.restriction, cfg.nu, 0.5, 3)
+            ref.run_cycles(4)
+            report(f"[{mode}] set_cycle(coarse_tol, coarse_maxit) reaches cached graphs", np.array_equal(got, ref.get_u()))
         g.close()
         if ref is not None:
             ref.close()
