@@ -12,8 +12,10 @@ One "step" = one driver iteration of the reference (GeometricMultigrid/src/main.
   roofline = the dominant kernel (fine-level red-black GS colour pass) timed alone, live.
   cpu_baseline = the reference's own CPU classes (oracle/_ref, compiled from /root/reference) on the
            box's host cores, on a bounded sample of the same workload.
-  amg      = (N=1 only; the second half of BASELINE.json's metric, "smoother/SpMV HBM GB/s vs peak") the level-0
-           AMG kernels on a 4 M DoF synthetic unstructured triangulation: ms, algorithmic GB/s, fraction of peak.
+  amg      = BASELINE configs[4] at every N: AMG on the 16 M DoF synthetic unstructured triangulation, assembled and set up
+           on the device, fine levels in row blocks over the N GPUs: level-0 kernels (ms, algorithmic GB/s, fraction of
+           peak -- the "smoother/SpMV HBM GB/s vs peak" half of the metric), V(2,2) cycles (ms, GDoF*cycles/s, launches,
+           convergence factor), checksum of x against a single-GPU repeat.
 Workloads: N=1 -> config C3 (8193^2, L=13, BASELINE configs[2]); N>1 -> config C4 (16385^2, L=14, configs[3]) in row
 slabs.  The N=1 line also carries `c4_single_gpu` (the 16385^2 grid on one GPU), so scaling can be taken on ONE grid.
   parity (N>1) = rank 0 repeats the same iterations on ONE GPU and the 64-bit checksum of u over all ranks must
@@ -134,37 +136,138 @@ def amg_cpu_baseline(A, rhs, sweeps=2):
         return {"error": repr(e)}
 
 
-def amg_kernels(device, peak, side=2001, reps=20):
-    """level-0 kernels of the AMG fast path (multicolour GS, weighted Jacobi, residual, R x, x += P x) timed with CUDA
-    events on the library's stream; algorithmic bytes per SURVEY.md section 8d (12 nnz + 28 n per sweep / SpMV)"""
+def amg_config5(device, peak, side, levels, rank, world, dist, cycles=10, reps=10, cpu=True):
+    """BASELINE configs[4]: AMG on a synthetic unstructured 2D triangulation (side^2 nodes; 4001 -> 15 992 001 DoF), the fine
+    levels cut into row blocks over `world` GPUs.  The mesh is generated and assembled ON THE DEVICE (mgb_fem_synthetic), the
+    hierarchy is built ON THE DEVICE (mgb_amg_config_device: PMIS + direct interpolation + Galerkin products), every rank
+    redundantly and deterministically on its own GPU, keeping its row blocks.  Reported: level-0 kernels and whole
+    correction-scheme V(2,2) cycles (CUDA events on the library's stream, max over ranks), algorithmic bytes per SURVEY.md 8d
+    (12 nnz + 28 n per sweep / SpMV), the convergence factor per cycle, and the checksum of x against a single-GPU repeat."""
     import ctypes as C
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from amg_bench import synthetic_system
-    from multigrid_prj_b200 import Amg
+    from multigrid_prj_b200 import Amg, System
     from multigrid_prj_b200 import amg as M
+    from multigrid_prj_b200 import gmg as G
     from multigrid_prj_b200.gmg import Timer
-    A, rhs = synthetic_system(side)
-    out = {"workload": f"P1 FEM Poisson on a synthetic unstructured triangulation, {A.shape[0]} DoF, {A.nnz} nnz (BASELINE config 5 "
-                       f"shape at 1/4 size), 2 levels", "peak": peak, "unit": "GB/s", "kernels": {}}
-    with Amg(A.indptr, A.indices, A.data, rhs, levels=2, fast=True, device=device) as a:
-        tm, st, nrm = Timer(), a.stream(), C.c_double()
-        ops = {"multicolour_gs_sweep": lambda: a.smooth(0, M.GS_MULTICOLOUR, 1), "jacobi_sweep": lambda: a.smooth(0, M.JACOBI, 1),
-               "residual_norm": lambda: a.lib.mgb_amg_residual(a.h, 0, C.byref(nrm)), "restrict_Rx": lambda: a.restrict(1),
-               "prolong_add_Px": lambda: a.prolong(0)}
-        launches = 0
-        for name, fn in ops.items():
-            fn(); fn(); a.sync(); a.reset_stats()
+
+    def maxr(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumr(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def new_id():
+        if dist is None:
+            return None
+        ids = [G.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    t0 = time.perf_counter()
+    sysm = System.synthetic(side, device=device)
+    n, nnz = sysm.info()
+    t_asm = maxr(time.perf_counter() - t0)
+    out = {"workload": f"AMG, P1 FEM Poisson on a synthetic unstructured triangulation ({side}^2 nodes): {n} DoF, {nnz} nnz "
+                       f"(BASELINE configs[4]), fine levels in row blocks over {world} GPU(s)",
+           "n": n, "nnz": nnz, "n_gpus": world, "peak": peak, "unit": "GB/s",
+           "assembly_s": t_asm, "assembly": "mesh generated and assembled on the device (mgb_fem_synthetic), every rank its own copy"}
+    tm = Timer()
+
+    def variant(name, **kw):
+        t0 = time.perf_counter()
+        a = Amg.from_system(sysm, levels=levels, rank=rank, n_ranks=world, nccl_id=new_id(), device=device, **kw)
+        a.sync()
+        setup_s = maxr(time.perf_counter() - t0)
+        lay = [dict(a.info(l), rows=a.rows(l)[1], sharded=a.rows(l)[2]) for l in range(a.levels)]
+        rec = {"setup_s": setup_s, "levels": [{"n": x["n"], "nnz": x["nnz_a"], "colours": x["colours"], "sharded": x["sharded"]} for x in lay],
+               "kernels": {}}
+        st = a.stream()
+
+        def bench(kname, fn, r=reps):
+            fn(); a.sync(); barrier(); a.reset_stats()
             tm.start(st)
-            for _ in range(reps):
+            for _ in range(r):
                 fn()
             tm.stop(st)
-            ms = tm.elapsed_ms() / reps
+            ms = maxr(tm.elapsed_ms() / r)
             s_ = a.stats()
-            gbs = s_["bytes_algorithmic"] / reps / (ms * 1e-3) / 1e9
-            launches += int(s_["kernel_launches"])
-            out["kernels"][name] = {"ms": ms, "achieved": gbs, "frac": gbs / peak}
-        out["gpu_launches"] = launches
-    out["cpu_baseline"] = amg_cpu_baseline(A, rhs)
+            gbs = sumr(s_["bytes_algorithmic"]) / r / (ms * 1e-3) / 1e9
+            rec["kernels"][kname] = {"ms": ms, "achieved": gbs, "frac": gbs / world / peak, "launches": s_["kernel_launches"] / r}
+
+        nrm = C.c_double()
+        if lay[0]["colours"] > 0:
+            bench("L0 multicolour GS sweep", lambda: a.smooth(0, M.GS_MULTICOLOUR, 1))
+        bench("L0 l1-Jacobi sweep", lambda: a.smooth(0, M.L1_JACOBI, 2), r=max(reps // 2, 1))
+        rec["kernels"]["L0 l1-Jacobi sweep"]["ms"] /= 2; rec["kernels"]["L0 l1-Jacobi sweep"]["launches"] /= 2
+        bench("L0 residual + norm", lambda: a.lib.mgb_amg_residual(a.h, 0, C.byref(nrm)))
+        bench("restrict L0->L1", lambda: a.restrict(1))
+        bench("prolong-add L1->L0", lambda: a.prolong(0))
+        # K correction-scheme V(2,2) cycles from x = 0 (one norm read back per cycle, as mgb_amg_solve reports it)
+        zero = np.zeros(n)
+        a.set_vector(0, 0, zero); a.solve(tol=0.0, maxit=3)                      # warm-up + graph capture
+        a.set_vector(0, 0, zero); a.sync(); barrier(); a.reset_stats()
+        tm.start(st)
+        hist = a.solve(tol=0.0, maxit=cycles)
+        tm.stop(st)
+        ms = maxr(tm.elapsed_ms())
+        s_ = a.stats()
+        alg = sumr(s_["bytes_algorithmic"])
+        rec["cycle"] = {"cycles": cycles, "ms_per_cycle": ms / cycles, "dof_cycles_per_s": n * cycles / (ms * 1e-3),
+                        "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / world / peak,
+                        "launches_per_cycle": s_["kernel_launches"] / cycles, "graph_launches": s_["graph_launches"],
+                        "residual": [float(hist[0]), float(hist[-1])],
+                        "reduction_per_cycle": float((hist[-1] / hist[0]) ** (1.0 / cycles)),
+                        "x_checksum": f"{a.checksum():#018x}"}
+        a.close()
+        out[name] = rec
+        return rec
+
+    v1 = variant("multicolour_gs_fine_l1_jacobi_coarse")                       # config 5's smoother on the fine level
+    v2 = variant("l1_jacobi_all_levels", smoother=M.L1_JACOBI)
+    out["parity"] = None
+    if world > 1:
+        # the same cycles on ONE GPU (rank 0): bit-identical iterates expected (Jacobi-type sweeps and per-colour ghost refresh
+        # do not depend on the partition)
+        res = {}
+        if rank == 0:
+            for name, kw in (("multicolour_gs_fine_l1_jacobi_coarse", {}), ("l1_jacobi_all_levels", {"smoother": M.L1_JACOBI})):
+                with Amg.from_system(sysm, levels=levels, device=device, **kw) as a1:
+                    a1.set_vector(0, 0, np.zeros(n)); a1.solve(tol=0.0, maxit=3)
+                    a1.set_vector(0, 0, np.zeros(n)); a1.sync()
+                    tm.start(a1.stream())
+                    a1.solve(tol=0.0, maxit=cycles)
+                    tm.stop(a1.stream())
+                    res[name] = {"x_checksum": f"{a1.checksum():#018x}", "ms_per_cycle": tm.elapsed_ms() / cycles}
+                    res[name]["match"] = res[name]["x_checksum"] == out[name]["cycle"]["x_checksum"]
+        barrier()
+        out["parity"] = res if rank == 0 else None
+    if cpu and rank == 0:
+        try:
+            import oracle
+            ptr, col, val, rhs = sysm.get()
+            Ao = oracle.Csr(n, n, ptr, col, val)
+            x = np.zeros(n)
+            t0 = time.perf_counter()
+            oracle.amg().gs(Ao, rhs, x, 1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"gs_sweep_ms": dt * 1e3, "achieved": (12.0 * nnz + 28.0 * n) / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                   "sample": f"1 lexicographic Gauss-Seidel sweep of oracle/amg_oracle.c (AMG/include/Utilities.hpp:44-58) on the same {n}-row matrix"}
+        except Exception as e:                               # noqa: BLE001 -- a reported baseline, not the product
+            out["cpu_baseline"] = {"error": repr(e)}
+    sysm.close()
     return out
 
 
@@ -256,6 +359,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG kernel leg (N=1 only)")
+    ap.add_argument("--amg-side", type=int, default=4001, help="nodes per side of the synthetic triangulation (4001: config 5)")
+    ap.add_argument("--amg-levels", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the single-GPU repeat + checksum comparison")
     ap.add_argument("--no-c4", action="store_true", help="N=1: skip the 16385^2 single-GPU line")
     args = ap.parse_args()
@@ -456,10 +561,14 @@ def main():
                "sample": f"{cc} driver iterations of the reference's GS solver on {cn}^2, L={cl} ({dt:.1f} s); "
                          f"lexicographic GS is serial, only the residual loops use the {cores} OpenMP threads"}
 
-    # ---- AMG smoother / SpMV kernels against the HBM peak (rank 0, N=1 only) -------------------------------------
+    # ---- AMG: BASELINE configs[4] (16 M DoF, sharded over the N GPUs): kernels against the HBM peak + whole cycles ------------
     amg = None
-    if rank == 0 and world == 1 and not args.no_amg:
-        amg = amg_kernels(local, peak)
+    amg_ok = True
+    if not args.no_amg:
+        g.close()                                  # the GMG arrays are not needed any more
+        amg = amg_config5(local, peak, args.amg_side, args.amg_levels, rank, world, dist, cpu=not args.no_cpu)
+        if amg.get("parity"):
+            amg_ok = all(v["match"] for v in amg["parity"].values())
 
     g.close()
     # ---- N=1 only: the slab runs' grid (config C4, 16385^2) on this one GPU, so that scaling can be taken on one grid -------
@@ -495,6 +604,9 @@ def main():
     if not parity_ok:
         print("bench.py: PARITY FAILURE: the slab-decomposed u differs from the single-GPU u (checksums above)", file=sys.stderr)
         return 3
+    if not amg_ok:
+        print("bench.py: PARITY FAILURE: the row-block sharded AMG iterate differs from the single-GPU one", file=sys.stderr)
+        return 4
     return 0
 
 

@@ -35,7 +35,9 @@ enum {
     MGB_SMOOTH_GS_LEX = 0,   /* lexicographic Gauss-Seidel, solvers.hpp:24-49 (exact wavefront order)   */
     MGB_SMOOTH_JACOBI = 1,   /* Jacobi, omega = 1, solvers.hpp:53-84                                       */
     MGB_SMOOTH_BICGSTAB = 2, /* accepted and routed to Jacobi exactly as main.cpp:103-106 does            */
-    MGB_SMOOTH_GS_RB = 3     /* red-black Gauss-Seidel (reordered; the B200 fast path)                    */
+    MGB_SMOOTH_GS_RB = 3,    /* red-black Gauss-Seidel (reordered; the B200 fast path)                    */
+    MGB_SMOOTH_L1_JACOBI = 4 /* AMG only: x += (b - A x) / (a_ii + sum_{j != i} |a_ij|): colouring-free, parameter-free,
+                                one SELL launch per sweep (the smoother of the Galerkin levels on the fast path)  */
 };
 
 /* restriction of the fine residual to the coarse levels */
@@ -223,13 +225,27 @@ typedef struct mgb_amg_config {
                               colour on B200 (grid.sync of a full grid costs more than a launch gap: level-0 sweep 0.207 vs
                               0.151 ms, V(2,2) cycle 9.5 vs 5.8 ms at 4 M DoF, profiles/r01_amg_scale_1gpu_4M_coop.json), so
                               it is off by default (0) */
+    int device_setup;      /* 0: the hierarchy is built on the host with the reference's semantics (AMG.hpp:105-369; exact C/F state
+                              machine, bit-identical operators); 1: built ON THE DEVICE, parity-exempt: same strength measure,
+                              same direct-interpolation weights and Galerkin operator, PMIS splitting instead of the reference's
+                              sequential one, triple product by expand-sort-compress (csrc/amg_setup.cu).  Coarsening stops early
+                              when a level has <= 1 coarse point or no fine point: mgb_amg_n_levels() gives the depth built.
+                              Multicolour GS / Jacobi-type smoothers only. */
+    int coarse_smoother;   /* smoother of the levels >= 1 in mgb_amg_apply / mgb_amg_solve: 0 = the same as `smoother`, else a
+                              MGB_SMOOTH_* id (fast path: MGB_SMOOTH_L1_JACOBI -- the Galerkin levels need 13-16 colours) */
+    int p2p;               /* row-block sharded runs: 1 = ghost entries move by direct peer stores over NVLink into the peers'
+                              identically indexed vectors + flag handshakes (one small kernel pair per exchange) instead of
+                              pack / ncclSend / ncclRecv / unpack; needs peer access between all GPUs of the box.  0 = NCCL */
     int reserved[1];
 } mgb_amg_config;
 
 typedef struct mgb_amg *mgb_amg_t;
 
 void mgb_amg_config_default(mgb_amg_config *cfg);   /* the reference's constants, exact lexicographic GS */
-void mgb_amg_config_fast(mgb_amg_config *cfg);      /* multicolour GS + vector kernels */
+void mgb_amg_config_fast(mgb_amg_config *cfg);      /* multicolour GS + vector kernels, the reference's hierarchy */
+void mgb_amg_config_device(mgb_amg_config *cfg);    /* fast + device_setup = 1 + l1-Jacobi on the levels >= 1 */
+/* number of levels the handle holds (== cfg.levels unless the device setup stopped coarsening earlier) */
+int mgb_amg_n_levels(mgb_amg_t h);
 
 /* replaces Matrix/CSRMatrix + the AMG constructor + AMG::initialization() (include/AMG.hpp:33-41,
  * src/AMG.cpp:76-120): takes the level-0 operator as CSR (rows sorted by column, as Matrix's std::map
@@ -239,6 +255,25 @@ void mgb_amg_config_fast(mgb_amg_config *cfg);      /* multicolour GS + vector k
 int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *row_ptr, const int64_t *col,
                             const double *val, const double *rhs, mgb_amg_t *out);
 void mgb_amg_destroy(mgb_amg_t h);
+
+/* ---- operator construction on the device ----
+ * A linear system (CSR with int32 indices + right-hand side) that lives in HBM. */
+typedef struct mgb_system *mgb_system_t;
+/* replaces the assembly loop of AMG/src/main.cpp:34-117 with LinearFE::set_dofs (include/FEM.hpp:174-258) and the problem
+ * functions of src/Utilities.cpp:3-28: P1 stiffness matrix and load vector of -div(grad u) = f, u = g on the boundary nodes,
+ * unknowns = interior nodes in order of appearance (src/FEM.cpp:291-303).  tri holds 3 node indices per triangle, ascending
+ * (src/FEM.cpp:162-170).  exact_order = 1: every quadrature term is added separately in the reference's order -> the matrix
+ * is bit-identical to the reference's; 0: the three equal terms of an entry are summed first. */
+int mgb_fem_assemble_p1(size_t n_nodes, const double *x, const double *y, const unsigned char *on_boundary, size_t n_tri,
+                        const int64_t *tri, int exact_order, int device, mgb_system_t *out);
+/* BASELINE config 5: side x side lattice on [0,2]^2, interior nodes jittered by <= 0.2 h, every cell split along a hashed
+ * diagonal (counter-based hash of seed: the same mesh on every rank), generated AND assembled on the device. */
+int mgb_fem_synthetic(size_t side, uint64_t seed, int device, mgb_system_t *out);
+/* the mesh mgb_fem_synthetic uses, on the host (x, y, on_boundary: side*side entries; tri: 6*(side-1)^2) -- for checks */
+int mgb_fem_synthetic_mesh(size_t side, uint64_t seed, double *x, double *y, unsigned char *on_boundary, int64_t *tri);
+int mgb_system_info(mgb_system_t s, size_t *n, size_t *nnz);
+int mgb_system_get(mgb_system_t s, int64_t *row_ptr, int64_t *col, double *val, double *rhs);   /* any pointer may be NULL */
+void mgb_system_destroy(mgb_system_t s);
 
 /* Row-block sharded AMG over the GPUs of one box (the reference is single-process).  One process
  * per GPU; EVERY rank passes the same level-0 system and builds the same hierarchy on its host (the setup is
@@ -251,6 +286,10 @@ void mgb_amg_destroy(mgb_amg_t h);
 int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *row_ptr, const int64_t *col,
                            const double *val, const double *rhs, int rank, int n_ranks,
                            const unsigned char nccl_id[128], mgb_amg_t *out);
+/* same, from a system that already lives on the device (cfg->device_setup must be 1): the hierarchy is built where the
+ * matrix is, nothing is staged through the host; every rank passes its own copy of the (identical) system */
+int mgb_amg_create_from_system(const mgb_amg_config *cfg, mgb_system_t sys, int rank, int n_ranks,
+                               const unsigned char nccl_id[128], mgb_amg_t *out);
 /* the contiguous block of n rows (or vector entries) that `rank` owns.  Host-only, no device needed. */
 int mgb_amg_partition(size_t n, int n_ranks, int rank, size_t *row0, size_t *rows);
 /* rows of `level` this handle works on, and whether the level is sharded (0: replicated, whole on every rank) */
@@ -261,7 +300,8 @@ int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t 
                        int *n_wavefronts, int *n_colours);
 /* which: 0 = A_level, 1 = P_level (level+1 -> level); arrays sized from mgb_amg_level_info */
 int mgb_amg_get_matrix(mgb_amg_t h, int level, int which, int64_t *row_ptr, int64_t *col, double *val);
-/* which: 0 = wavefront of each row in the level schedule of lexicographic GS, 1 = colour of each row */
+/* which: 0 = wavefront of each row in the level schedule of lexicographic GS, 1 = colour of each row,
+ * 2 = C/F state of each row (1 coarse, 0 fine; device-built hierarchies) */
 int mgb_amg_get_schedule(mgb_amg_t h, int level, int which, int *group_of_row);
 /* which: 0 = x_level, 1 = rhs_level, 2 = last residual vector of that level */
 int mgb_amg_get_vector(mgb_amg_t h, int level, int which, double *host);
@@ -307,6 +347,9 @@ int mgb_amg_build_coarse_matrix(mgb_csr_t A, mgb_csr_t P, mgb_csr_t *Ac);
 int mgb_amg_halo_plan(mgb_csr_t M, int n_ranks, int rank, const int *group_of_col, int n_groups,
                       int64_t *send_ptr, int64_t *send_idx, int64_t *recv_ptr, int64_t *recv_idx);
 
+/* 64-bit checksum over ALL ranks of vector `which` (0 x, 1 rhs, 2 residual) of `level`: independent of the row-block
+ * partition, so equal values on 1 and N ranks <=> the sharded solve is bit-identical.  Collective when n_ranks > 1. */
+int mgb_amg_checksum(mgb_amg_t h, int level, int which, uint64_t *out);
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
 int mgb_amg_reset_stats(mgb_amg_t h);
 void *mgb_amg_stream(mgb_amg_t h);

@@ -8,6 +8,6 @@ loader and thin handles used by the tests and by bench.py.  There is no CPU fall
 """
 from ._lib import load, MgbError, lib_path   # noqa: F401
 from .gmg import GmgConfig, Gmg              # noqa: F401
-from .amg import Amg                         # noqa: F401
+from .amg import Amg, System                 # noqa: F401
 
-__all__ = ["load", "MgbError", "lib_path", "GmgConfig", "Gmg", "Amg"]
+__all__ = ["load", "MgbError", "lib_path", "GmgConfig", "Gmg", "Amg", "System"]

@@ -36,7 +36,8 @@ class AmgConfigStruct(C.Structure):
                 ("coarse_sweeps", C.c_int), ("post_sweeps", C.c_int), ("exact_order", C.c_int), ("device", C.c_int),
                 ("start_index", C.c_int64 * 16), ("hybrid_gs", C.c_int), ("shard_min_rows", C.c_int),
                 ("jacobi_omega", C.c_double), ("tail_max_rows", C.c_int), ("cycle_graph", C.c_int),
-                ("coop_sweeps", C.c_int), ("reserved", C.c_int * 1)]
+                ("coop_sweeps", C.c_int), ("device_setup", C.c_int), ("coarse_smoother", C.c_int), ("p2p", C.c_int),
+                ("reserved", C.c_int * 1)]
 
 
 # every symbol include/mgb200.h declares: name -> (restype, argtypes)
@@ -74,9 +75,18 @@ SYMBOLS = {
     "mgb_gmg_sync": (_i, [_vp]),
     "mgb_amg_config_default": (None, [C.POINTER(AmgConfigStruct)]),
     "mgb_amg_config_fast": (None, [C.POINTER(AmgConfigStruct)]),
+    "mgb_amg_config_device": (None, [C.POINTER(AmgConfigStruct)]),
+    "mgb_amg_n_levels": (_i, [_vp]),
     "mgb_amg_create_from_csr": (_i, [C.POINTER(AmgConfigStruct), C.c_size_t, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "mgb_amg_destroy": (None, [_vp]),
     "mgb_amg_create_sharded": (_i, [C.POINTER(AmgConfigStruct), C.c_size_t, _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "mgb_amg_create_from_system": (_i, [C.POINTER(AmgConfigStruct), _vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "mgb_fem_assemble_p1": (_i, [C.c_size_t, _vp, _vp, _vp, C.c_size_t, _vp, _i, _i, C.POINTER(_vp)]),
+    "mgb_fem_synthetic": (_i, [C.c_size_t, C.c_uint64, _i, C.POINTER(_vp)]),
+    "mgb_fem_synthetic_mesh": (_i, [C.c_size_t, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "mgb_system_info": (_i, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mgb_system_get": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "mgb_system_destroy": (None, [_vp]),
     "mgb_amg_partition": (_i, [C.c_size_t, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mgb_amg_level_rows": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _pi]),
     "mgb_amg_halo_plan": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
@@ -98,6 +108,7 @@ SYMBOLS = {
     "mgb_amg_select_coarse_nodes": (_i, [_vp, _d, C.c_int64, _vp, C.POINTER(C.c_size_t)]),
     "mgb_amg_build_prolongation": (_i, [_vp, _d, _vp, C.POINTER(_vp)]),
     "mgb_amg_build_coarse_matrix": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "mgb_amg_checksum": (_i, [_vp, _i, _i, C.POINTER(C.c_uint64)]),
     "mgb_amg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
     "mgb_amg_reset_stats": (_i, [_vp]),
     "mgb_amg_stream": (_vp, [_vp]),

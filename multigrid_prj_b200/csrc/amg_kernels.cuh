@@ -19,13 +19,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace mgb {
+#include "amg_types.h"
 
-struct CsrDev {
-    int n_rows, n_cols, nnz;
-    const int *ptr, *col;
-    const double *val;
-};
+namespace mgb {
 
 constexpr int kLanes = 8;        // lanes per row in the vector kernels (P1 rows hold ~7 entries)
 
@@ -172,15 +168,6 @@ k_amg_jacobi_vec(CsrDev A, const double *__restrict__ diag, const double *__rest
 // contiguous range of slices), a slice stores the OFF-DIAGONAL entries of 32 rows column-major, padded to the
 // longest row of the slice.  One thread owns one row: its loads of col/val are coalesced across the warp and
 // mutually independent (all entries of the row in flight at once), and there is no row_ptr load on the path.
-struct SellDev {
-    int n_slots;                 // rows including padding (multiple of 32)
-    const int *slice_ptr;        // [n_slots/32 + 1] offsets into col/val
-    const int *col;              // column of each stored entry (padding: 0)
-    const double *val;           // value (padding: 0.0)
-    const int *row_of_slot;      // original row of a slot, -1 for padding slots
-    const double *diag_s, *b_s;  // diagonal and right-hand side in slot order
-};
-
 // sum_k val_k * x[col_k] over the `len` stored entries of one slot, in storage (ascending column) order.  The entries
 // are fetched in chunks of kSellChunk: all column indices and values of a chunk are in flight together, then all the
 // gathers of x -- two dependent memory round trips per chunk.  P1 rows hold 5-8 off-diagonals, i.e. one chunk: the
@@ -238,6 +225,8 @@ __device__ __forceinline__ double sell_row_add_exact(const SellDev &A, const dou
 // [first, last) of one colour, in place on x; MODE 3: plain product out[row] = sum (restriction, R = P^T);
 // MODE 4: out[row] += sum with the reference's term order and unfused operations (prolongation x_f += P x_c,
 // AMG/src/AMG.cpp:218-232 -- bit-identical to k_amg_prolong_add)
+// MODE 5: l1-Jacobi into `out`: x + (b - A x) / dl1 with dl1_i = a_ii + sum_{j != i} |a_ij| (no damping parameter, no
+// colouring: the smoother of the Galerkin levels, whose 13-16 colours make multicolour GS launch-bound)
 // NAT: the copy keeps the natural row order (only permuted inside 512-row windows) and has no slot-ordered vectors:
 // diag_s / b_s are then the level's diag / b, indexed by row.  Jacobi and the residual visit every row once in any
 // order; in natural order the gathers of x stay local, while the colour-sorted copy walks the whole index range once
@@ -245,7 +234,7 @@ __device__ __forceinline__ double sell_row_add_exact(const SellDev &A, const dou
 template <int MODE, bool NAT = false>
 __global__ void __launch_bounds__(256)
 k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *out, double *__restrict__ partial,
-           int first, int last, double omega)
+           int first, int last, double omega, const double *__restrict__ dl1)
 {
     __shared__ double red[8];
     const int p = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,7 +257,10 @@ k_amg_sell(SellDev A, const double *x, const double *__restrict__ b_s, double *o
                     acc = ri * ri;
                 } else if (MODE == 1)
                     out[i] = relax((bi - sum) / d, x[i], omega);
-                else
+                else if (MODE == 5) {
+                    const double xi = x[i];
+                    out[i] = xi + (bi - (sum + d * xi)) / __ldcs(dl1 + i);
+                } else
                     out[i] = (bi - sum) / d;
             }
         }
@@ -451,6 +443,19 @@ k_amg_colour_round(CsrDev A, const int *__restrict__ colour_in, int *__restrict_
     } else
         atomicAdd(remaining, 1);
     colour_out[i] = c;
+}
+
+// 64-bit checksum of the entries [r0, r1) of a vector: wrap-around sum of bit pattern x (2 i + 1).  Integer addition is
+// associative: the value does not depend on the row-block partition or on the order of the atomics.
+__global__ void __launch_bounds__(256)
+k_amg_checksum(const double *__restrict__ v, int r0, int r1, unsigned long long *out)
+{
+    unsigned long long acc = 0ull;
+    for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x)
+        acc += (unsigned long long)__double_as_longlong(v[i]) * (2ull * (unsigned long long)i + 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 __global__ void __launch_bounds__(1024)

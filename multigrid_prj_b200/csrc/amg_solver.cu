@@ -13,6 +13,8 @@
 #include "../../include/mgb200.h"
 #include "amg_kernels.cuh"
 #include "amg_tail.cuh"
+#include "amg_dev.h"
+#include "dev_util.cuh"
 #include "nccl_dyn.h"
 
 #include <algorithm>
@@ -25,6 +27,8 @@
 #include <vector>
 
 int mgb_set_error(int code, const std::string &msg);   // gmg_solver.cu
+
+using namespace mgb::amg;
 
 namespace {
 
@@ -238,16 +242,6 @@ HostCsr galerkin(const HostCsr &A, const HostCsr &P)
     return row_product(PtA, P);
 }
 
-// ---- row-block sharding ----------------------------------------------------------------------
-// rank r owns the entries [n r / R, n (r+1) / R) of a length-n index space (rows of an operator, entries of a vector)
-struct Block { int r0 = 0, r1 = 0; int size() const { return r1 - r0; } };
-inline Block block_of(int n, int n_ranks, int rank)
-{
-    Block b;
-    b.r0 = (int)((long long)n * rank / n_ranks);
-    b.r1 = (int)((long long)n * (rank + 1) / n_ranks);
-    return b;
-}
 inline int owner_of(int n, int n_ranks, int i)
 {
     int r = (int)std::min<long long>((long long)i * n_ranks / std::max(n, 1), n_ranks - 1);
@@ -321,38 +315,15 @@ HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_
     return H;
 }
 
-struct DevCsr {
-    int n_rows = 0, n_cols = 0, nnz = 0;
-    int *ptr = nullptr, *col = nullptr;
-    double *val = nullptr;
-    mgb::CsrDev view() const { return mgb::CsrDev{n_rows, n_cols, nnz, ptr, col, val}; }
-    void release() { cudaFree(ptr); cudaFree(col); cudaFree(val); ptr = col = nullptr; val = nullptr; }
-};
-
-struct Schedule {          // rows grouped into independent sets (wavefronts or colours)
-    int n_groups = 0;
-    std::vector<int> h_ptr, h_group;
-    int *d_ptr = nullptr, *d_rows = nullptr;
-    void release() { cudaFree(d_ptr); cudaFree(d_rows); d_ptr = d_rows = nullptr; }
-};
-
-struct SellCopy {              // colour-sorted SELL-32 copy of A for the fast kernels (amg_kernels.cuh)
-    int n_slots = 0;
-    std::vector<int> colour_slot_ptr;      // first slot of each colour (+ end)
-    int *d_colour_slot_ptr = nullptr;      // the same on the device (cooperative whole-sweep kernel)
-    int coop_blocks = 0;                   // grid of the cooperative kernel: co-resident, at most the largest colour
-    int *slice_ptr = nullptr, *col = nullptr, *row_of_slot = nullptr;
-    double *val = nullptr, *diag_s = nullptr, *b_s = nullptr;
-    size_t stored = 0;                     // entries incl. padding
-    mgb::SellDev view() const { return mgb::SellDev{n_slots, slice_ptr, col, val, row_of_slot, diag_s, b_s}; }
-    void release() { cudaFree(slice_ptr); cudaFree(col); cudaFree(row_of_slot); cudaFree(val); cudaFree(diag_s); cudaFree(b_s); cudaFree(d_colour_slot_ptr); }
-};
-
 struct AmgLevel {
     HostCsr hA, hP;                       // host copies (hierarchy queries, schedules)
     std::vector<double> h_rhs;
     DevCsr A, P, R;
     double *diag = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
+    double *dl1 = nullptr;                     // a_ii + sum_{j != i} |a_ij| (l1-Jacobi)
+    double *b0 = nullptr;                      // device-built hierarchy: the level's own right-hand side (P^T b), restored after mgb_amg_solve
+    int *d_colour = nullptr;                   // device-built hierarchy: colour of every row (the host copy is made on demand)
+    int *d_cf = nullptr;                       // device-built hierarchy: C/F state of every row (1 coarse, 0 fine)
     Schedule lex, colour;
     SellCopy sell, sellN, sellR, sellP;        // fast-path copies of A (colour-sorted / natural order) and of this rank's rows of R and P
     mgb::SellDev natural() const { mgb::SellDev v = sellN.view(); v.diag_s = diag; return v; }
@@ -652,6 +623,12 @@ inline int need_x_halo(mgb_amg *h, AmgLevel &L)
     return MGB_OK;
 }
 
+// the smoother mgb_amg_apply / mgb_amg_solve use on `level`
+inline int kind_of(const mgb_amg *h, int level)
+{
+    return (level > 0 && h->cfg.coarse_smoother > 0) ? h->cfg.coarse_smoother : h->cfg.smoother;
+}
+
 int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
 {
     AmgLevel &L = h->lv[level];
@@ -673,6 +650,7 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
                 }
         }
     } else if (kind == MGB_SMOOTH_GS_RB) {            // multicolour Gauss-Seidel
+        if (rows && !L.colour.d_rows) return mgb_set_error(MGB_ERR_STATE, "this level was set up without a colouring (its smoother is Jacobi-type)");
         if ((rc = need_x_halo(h, L))) return rc;
         const bool per_colour = L.sharded && !h->cfg.hybrid_gs;
         if (!h->cfg.exact_order && !per_colour && h->coop_max_blocks > 0 && L.sell.n_slots > 0) {
@@ -699,7 +677,7 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
                 } else {
                     const int p0 = L.sell.colour_slot_ptr[c], p1 = L.sell.colour_slot_ptr[c + 1];
                     if (p1 > p0)
-                        mgb::k_amg_sell<2><<<(p1 - p0 + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.x, nullptr, p0, p1, 1.0);
+                        mgb::k_amg_sell<2><<<(p1 - p0 + 255) / 256, 256, 0, h->st>>>(L.sell.view(), L.x, L.sell.b_s, L.x, nullptr, p0, p1, 1.0, nullptr);
                 }
                 if (rows) tally(h, sweep_bytes(L) * (double)(b - a) / rows);
                 // the rows of the next colours (here and on the peers) read this colour's new values
@@ -707,17 +685,27 @@ int do_smooth(mgb_amg *h, int level, int kind, int sweeps)
             }
             if (L.sharded && h->cfg.hybrid_gs && (rc = exchange_all(h, L.haloA, L.x))) return rc;
         }
-    } else if (kind == MGB_SMOOTH_JACOBI) {
+    } else if (kind == MGB_SMOOTH_JACOBI || kind == MGB_SMOOTH_L1_JACOBI) {
         if ((rc = need_x_halo(h, L))) return rc;
+        if (kind == MGB_SMOOTH_L1_JACOBI && (h->cfg.exact_order || !L.sellN.n_slots) && rows)
+            return mgb_set_error(MGB_ERR_ARG, "l1-Jacobi runs on the SELL copies of the fast path (exact_order = 0)");
+        // the sweeps alternate between x and tmp; the pointers themselves stay put (an odd count ends with one copy), so a
+        // CUDA graph that holds them stays valid
+        double *src = L.x, *dst = L.tmp;
         for (int s = 0; s < sweeps; ++s) {
-            if (h->cfg.exact_order) {
-                if (rows) mgb::k_amg_jacobi_vec<<<(unsigned)(((size_t)rows * mgb::kLanes + 255) / 256), 256, 0, h->st>>>(A, L.diag, L.x, L.b, L.tmp, h->omega, L.own.r0, L.own.r1);
+            if (kind == MGB_SMOOTH_L1_JACOBI) {
+                if (rows) mgb::k_amg_sell<5, true><<<(L.sellN.n_slots + 255) / 256, 256, 0, h->st>>>(L.natural(), src, L.b, dst, nullptr, 0, L.sellN.n_slots, 1.0, L.dl1);
+            } else if (h->cfg.exact_order) {
+                if (rows) mgb::k_amg_jacobi_vec<<<(unsigned)(((size_t)rows * mgb::kLanes + 255) / 256), 256, 0, h->st>>>(A, L.diag, src, L.b, dst, h->omega, L.own.r0, L.own.r1);
             } else if (L.sellN.n_slots)
-                mgb::k_amg_sell<1, true><<<(L.sellN.n_slots + 255) / 256, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, nullptr, 0, L.sellN.n_slots, h->omega);
+                mgb::k_amg_sell<1, true><<<(L.sellN.n_slots + 255) / 256, 256, 0, h->st>>>(L.natural(), src, L.b, dst, nullptr, 0, L.sellN.n_slots, h->omega, nullptr);
             tally(h, sweep_bytes(L));
-            std::swap(L.x, L.tmp);
-            h->ptr_epoch++;                                                         // captured graphs hold the old pointers
-            if (L.sharded && (rc = exchange_all(h, L.haloA, L.x))) return rc;      // the new iterate has no ghosts yet
+            std::swap(src, dst);
+            if (L.sharded && (rc = exchange_all(h, L.haloA, src))) return rc;       // the new iterate has no ghosts yet
+        }
+        if (src != L.x) {
+            ACK(cudaMemcpyAsync(L.x, src, sizeof(double) * (size_t)A.n_rows, cudaMemcpyDeviceToDevice, h->st));
+            tally(h, 16. * A.n_rows);
         }
     } else
         return mgb_set_error(MGB_ERR_ARG, "unknown AMG smoother");
@@ -737,7 +725,7 @@ int residual_to_tmp(mgb_amg *h, AmgLevel &L, bool want_norm)
         if (blocks) mgb::k_amg_residual<true><<<blocks, 256, 0, h->st>>>(A, L.x, L.b, L.tmp, h->d_partial, L.own.r0, L.own.r1);
     } else {
         blocks = (L.sellN.n_slots + 255) / 256;
-        if (blocks) mgb::k_amg_sell<0, true><<<blocks, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, h->d_partial, 0, L.sellN.n_slots, 1.0);
+        if (blocks) mgb::k_amg_sell<0, true><<<blocks, 256, 0, h->st>>>(L.natural(), L.x, L.b, L.tmp, h->d_partial, 0, L.sellN.n_slots, 1.0, nullptr);
     }
     tally(h, sweep_bytes(L));
     if (want_norm) {
@@ -770,7 +758,7 @@ int restrict_vec(mgb_amg *h, int level, double *in, double *out)
     const int rows = F.own_c.size();
     if (rows) {
         if (h->cfg.exact_order) mgb::k_amg_spmv<true><<<(rows + 255) / 256, 256, 0, h->st>>>(R, in, out, F.own_c.r0, F.own_c.r1);
-        else mgb::k_amg_sell<3><<<(F.sellR.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellR.view(), in, nullptr, out, nullptr, 0, F.sellR.n_slots, 1.0);
+        else mgb::k_amg_sell<3><<<(F.sellR.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellR.view(), in, nullptr, out, nullptr, 0, F.sellR.n_slots, 1.0, nullptr);
     }
     const double share = R.n_rows ? (double)rows / R.n_rows : 0.;
     tally(h, (12. * R.nnz + 12. * R.n_rows + 8. * R.n_cols) * share);
@@ -798,7 +786,7 @@ int do_prolong(mgb_amg *h, int level)
     if (C.sharded && (rc = exchange_all(h, F.haloP, C.x))) return rc;        // coarse entries of other blocks my fine rows interpolate from
     const int rows = F.own.size();
     if (rows && !h->cfg.exact_order)
-        mgb::k_amg_sell<4><<<(F.sellP.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellP.view(), C.x, nullptr, F.x, nullptr, 0, F.sellP.n_slots, 1.0);
+        mgb::k_amg_sell<4><<<(F.sellP.n_slots + 255) / 256, 256, 0, h->st>>>(F.sellP.view(), C.x, nullptr, F.x, nullptr, 0, F.sellP.n_slots, 1.0, nullptr);
     else if (rows) mgb::k_amg_prolong_add<<<(rows + 255) / 256, 256, 0, h->st>>>(P, C.x, F.x, F.own.r0, F.own.r1);
     tally(h, (12. * P.nnz + 20. * P.n_rows + 8. * P.n_cols) * (P.n_rows ? (double)rows / P.n_rows : 0.));
     ACK(cudaGetLastError());
@@ -810,18 +798,20 @@ int do_prolong(mgb_amg *h, int level)
 int launch_tail(mgb_amg *h, int mode, int pre, int coarse, int post)
 {
     const int L = (int)h->lv.size();
-    const int kind = h->cfg.smoother;
     mgb::AmgTailParams p{};
     p.nlev = L - h->lt;
-    p.kind = kind; p.exact = h->cfg.exact_order; p.mode = mode;
+    p.exact = h->cfg.exact_order; p.mode = mode;
     p.pre = pre; p.coarse = coarse; p.post = post; p.omega = h->omega;
     double bytes = 0.;
     for (int l = h->lt; l < L; ++l) {
         AmgLevel &lv = h->lv[l];
+        const int kind = kind_of(h, l);
         const Schedule &S = kind == MGB_SMOOTH_GS_LEX ? lv.lex : lv.colour;
+        if ((kind == MGB_SMOOTH_GS_LEX || kind == MGB_SMOOTH_GS_RB) && lv.A.n_rows && !S.d_rows)
+            return mgb_set_error(MGB_ERR_STATE, "this level holds no row schedule for the requested Gauss-Seidel smoother");
         mgb::AmgTailLevel &t = p.lv[l - h->lt];
         t.A = lv.A.view(); t.P = lv.P.view(); t.R = lv.R.view();
-        t.diag = lv.diag; t.x = lv.x; t.b = lv.b; t.tmp = lv.tmp;
+        t.diag = lv.diag; t.dl1 = lv.dl1; t.kind = kind; t.x = lv.x; t.b = lv.b; t.tmp = lv.tmp;
         t.grp_ptr = S.d_ptr; t.grp_rows = S.d_rows; t.n_groups = S.n_groups;
         const int sweeps = (l == L - 1) ? coarse : pre + post;
         bytes += sweep_bytes(lv) * (sweeps + (mode == 1 && l < L - 1 ? 1 : 0));
@@ -834,84 +824,207 @@ int launch_tail(mgb_amg *h, int mode, int pre, int coarse, int post)
     return MGB_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-void mgb_amg_config_default(mgb_amg_config *c)
+// ---- hierarchy built ON THE DEVICE (csrc/amg_setup.cu; parity-exempt fast path) -----------------------------------------------
+int download(const DevCsr &D, HostCsr &H)
 {
-    std::memset(c, 0, sizeof(*c));
-    c->levels = 5;                 // AMG/src/main.cpp:126
-    c->eps = 0.2;                  // AMG/include/AMG.hpp:21
-    c->smoother = MGB_SMOOTH_GS_LEX;
-    c->pre_sweeps = 10; c->coarse_sweeps = 200; c->post_sweeps = 10;      // AMG/src/AMG.cpp:287,295,302
-    c->exact_order = 1;
-    c->device = 0;
-    for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
-    c->hybrid_gs = 0;
-    c->shard_min_rows = 262144;
-    c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
-    c->tail_max_rows = 4000;
-}
-
-void mgb_amg_config_fast(mgb_amg_config *c)
-{
-    mgb_amg_config_default(c);
-    c->smoother = MGB_SMOOTH_GS_RB;      // multicolour Gauss-Seidel
-    c->exact_order = 0;
-}
-
-int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
-                            const double *val, const double *rhs, mgb_amg_t *out)
-{
-    return mgb_amg_create_sharded(cfg, n, ptr, col, val, rhs, 0, 1, nullptr, out);
-}
-
-int mgb_amg_partition(size_t n, int n_ranks, int rank, size_t *row0, size_t *rows)
-{
-    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n > (size_t)INT32_MAX || !row0 || !rows) return mgb_set_error(MGB_ERR_ARG, "bad partition arguments");
-    const Block b = block_of((int)n, n_ranks, rank);
-    *row0 = (size_t)b.r0; *rows = (size_t)b.size();
+    H.n_rows = D.n_rows; H.n_cols = D.n_cols;
+    H.ptr.assign((size_t)D.n_rows + 1, 0); H.col.assign((size_t)D.nnz, 0); H.val.assign((size_t)D.nnz, 0.0);
+    if (D.ptr) ACK(cudaMemcpy(H.ptr.data(), D.ptr, sizeof(int) * ((size_t)D.n_rows + 1), cudaMemcpyDeviceToHost));
+    if (D.nnz) {
+        ACK(cudaMemcpy(H.col.data(), D.col, sizeof(int) * (size_t)D.nnz, cudaMemcpyDeviceToHost));
+        ACK(cudaMemcpy(H.val.data(), D.val, sizeof(double) * (size_t)D.nnz, cudaMemcpyDeviceToHost));
+    }
     return MGB_OK;
 }
 
-int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
-                           const double *val, const double *rhs, int rank, int n_ranks,
-                           const unsigned char nccl_id[128], mgb_amg_t *out)
+__global__ void __launch_bounds__(256)
+k_int_max(const int *__restrict__ v, int n, int *out)
 {
-    if (!cfg || !ptr || !col || !val || !rhs || !out) return mgb_set_error(MGB_ERR_ARG, "null argument");
-    *out = nullptr;
-    if (cfg->levels < 1 || cfg->levels > 16) return mgb_set_error(MGB_ERR_ARG, "1 <= levels <= 16");
-    if (n == 0 || n > (size_t)1 << 30 || ptr[n] > (int64_t)INT32_MAX) return mgb_set_error(MGB_ERR_ARG, "matrix too large for int32 indices");
-    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return mgb_set_error(MGB_ERR_ARG, "bad rank / n_ranks");
-    if (n_ranks > 1 && !nccl_id) return mgb_set_error(MGB_ERR_ARG, "n_ranks > 1 needs the ncclUniqueId of mgb_nccl_unique_id()");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return mgb_set_error(MGB_ERR_CUDA, "no CUDA device: libmgb200 has no CPU fallback");
+    int m = -1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// Jones-Plassmann colouring on the device; the colours stay there (L.d_colour) and the row lists / the colour-sorted
+// SELL copy are built from them without a host pass
+int build_colouring_device(mgb_amg *h, AmgLevel &L)
+{
+    const int n = L.A.n_rows;
+    int *c0 = nullptr, *c1 = nullptr, *d_left = nullptr;
+    ACK(cudaMalloc(&c0, sizeof(int) * (size_t)std::max(n, 1)));
+    ACK(cudaMalloc(&c1, sizeof(int) * (size_t)std::max(n, 1)));
+    ACK(cudaMalloc(&d_left, sizeof(int)));
+    ACK(cudaMemsetAsync(c0, 0xFF, sizeof(int) * (size_t)std::max(n, 1), h->st));
+    int left = n, rounds = 0;
+    while (left > 0 && rounds < 10000) {
+        ACK(cudaMemsetAsync(d_left, 0, sizeof(int), h->st));
+        mgb::k_amg_colour_round<<<(n + 255) / 256, 256, 0, h->st>>>(L.A.view(), c0, c1, d_left);
+        tally(h, 0.);
+        ACK(cudaMemcpyAsync(&left, d_left, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        ACK(cudaStreamSynchronize(h->st));
+        std::swap(c0, c1);
+        ++rounds;
     }
-    ACK(cudaSetDevice(cfg->device));
-    mgb_amg *h = new mgb_amg();
-    struct Guard { mgb_amg *h; ~Guard() { if (h) mgb_amg_destroy(h); } } guard{h};     // any early return frees what exists so far
-    h->cfg = *cfg;
-    h->rank = rank; h->n_ranks = n_ranks;
-    h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
+    cudaFree(c1);
+    L.d_colour = c0;
+    if (left > 0) { cudaFree(d_left); return mgb_set_error(MGB_ERR_STATE, "colouring did not finish"); }
+    int top = -1;
+    ACK(cudaMemsetAsync(d_left, 0xFF, sizeof(int), h->st));
+    if (n) k_int_max<<<std::min((n + 255) / 256, 1184), 256, 0, h->st>>>(c0, n, d_left);
+    ACK(cudaMemcpyAsync(&top, d_left, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    cudaFree(d_left);
+    return dev_group_schedule(L.A, L.d_colour, top + 1, L.own, L.colour, h->cfg.exact_order ? nullptr : &L.sell, L.diag, L.b, h->st);
+}
+
+// lv[0].A and lv[0].b are in place on the device (lv sized cfg.levels); builds everything else
+int build_levels_device(mgb_amg *h, size_t &max_blocks, size_t &max_halo)
+{
+    const mgb_amg_config *cfg = &h->cfg;
+    const int n_ranks = h->n_ranks, rank = h->rank;
     const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 262144;
-    ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    if (cfg->exact_order) return mgb_set_error(MGB_ERR_ARG, "device_setup = 1 runs the fast kernels only (exact_order = 0)");
+    if (cfg->smoother == MGB_SMOOTH_GS_LEX)
+        return mgb_set_error(MGB_ERR_ARG, "device_setup = 1: lexicographic Gauss-Seidel needs the host-built level schedule");
+    int rc;
+    mgb::dev::Trace tr("levels");
+    // 1. coarsening, level by level, on the device
+    int depth = 1;
+    for (int l = 0; l + 1 < cfg->levels; ++l) {
+        AmgLevel &F = h->lv[l];
+        if (F.A.n_rows <= 16) break;
+        DevCsr P, R, Ac;
+        int rounds = 0;
+        if ((rc = dev_coarsen(F.A, cfg->eps, 12345u + 7919u * (unsigned)l, P, R, Ac, h->st, &rounds, &F.d_cf))) { P.release(); R.release(); Ac.release(); return rc; }
+        if (P.n_cols <= 1 || P.n_cols >= F.A.n_rows || !P.ptr) { P.release(); R.release(); Ac.release(); break; }
+        F.P = P; F.R = R;
+        AmgLevel &C = h->lv[l + 1];
+        C.A = Ac;
+        ACK(cudaMalloc(&C.b, sizeof(double) * (size_t)Ac.n_rows));
+        // right-hand side of the next level as the reference forms it: b_c = P^T b (AMG.cpp:100-109)
+        mgb::k_amg_spmv<false><<<(unsigned)(((size_t)R.n_rows * mgb::kLanes + 255) / 256), 256, 0, h->st>>>(R.view(), F.b, C.b, 0, R.n_rows);
+        ACK(cudaGetLastError());
+        depth = l + 2;
+    }
+    h->lv.resize(depth);
+    const int L = depth;
+    tr.mark("hierarchy (levels)", depth);
+    // 2. vectors and diagonals
+    for (int l = 0; l < L; ++l) {
+        AmgLevel &Lv = h->lv[l];
+        const size_t bytes = sizeof(double) * (size_t)std::max(Lv.A.n_rows, 1);
+        ACK(cudaMalloc(&Lv.diag, bytes)); ACK(cudaMalloc(&Lv.dl1, bytes)); ACK(cudaMalloc(&Lv.x, bytes)); ACK(cudaMalloc(&Lv.tmp, bytes));
+        ACK(cudaMalloc(&Lv.b0, bytes));
+        ACK(cudaMemsetAsync(Lv.x, 0, bytes, h->st));
+        ACK(cudaMemsetAsync(Lv.tmp, 0, bytes, h->st));
+        ACK(cudaMemcpyAsync(Lv.b0, Lv.b, sizeof(double) * (size_t)Lv.A.n_rows, cudaMemcpyDeviceToDevice, h->st));
+        if ((rc = dev_diagonals(Lv.A, Lv.diag, Lv.dl1, h->st))) return rc;
+    }
+    ACK(cudaStreamSynchronize(h->st));
+    // 3. which levels are cut into row blocks, and the rows of every level this rank works on
+    for (int l = 0; l < L; ++l) {
+        AmgLevel &Lv = h->lv[l];
+        const int nl = Lv.A.n_rows;
+        Lv.sharded = n_ranks > 1 && (long long)nl >= (long long)min_rows * n_ranks && (l == 0 || h->lv[l - 1].sharded);
+        Lv.own = Lv.sharded ? block_of(nl, n_ranks, rank) : Block{0, nl};
+        int p0 = 0, p1 = Lv.A.nnz;
+        if (Lv.sharded) {
+            ACK(cudaMemcpy(&p0, Lv.A.ptr + Lv.own.r0, sizeof(int), cudaMemcpyDeviceToHost));
+            ACK(cudaMemcpy(&p1, Lv.A.ptr + Lv.own.r1, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        Lv.own_nnz = (size_t)(p1 - p0);
+        Lv.x_halo_ok = true;
+    }
+    // 4. persistent coarse tail: the trailing run of small, unsharded levels
     {
-        int coop = 0, sms = 0, per_sm = 0;
-        ACK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
-        ACK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        ACK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgb::k_amg_sell_gs_sweeps, 256, 0));
-        h->coop_max_blocks = (coop && cfg->coop_sweeps > 0) ? sms * per_sm : 0;
+        const int cap = cfg->tail_max_rows == 0 ? 4000 : cfg->tail_max_rows;
+        h->lt = -1;
+        for (int l = L - 1; l >= 0 && cap > 0; --l) {
+            if (h->lv[l].A.n_rows > cap || h->lv[l].sharded || L - l > mgb::kAmgTailMaxLevels) break;
+            h->lt = l;
+        }
     }
-    if (n_ranks > 1) {
-        auto &Nc = mgb::nccl();
-        if (!Nc.load()) return mgb_set_error(MGB_ERR_NCCL, Nc.error);
-        mgb::NcclUniqueId id;
-        std::memcpy(&id, nccl_id, sizeof(id));
-        ANK(Nc.CommInitRank(&h->comm, n_ranks, id, rank));
+    tr.mark("vectors, diagonals, layout");
+    // 5. SELL copies, colour lists, ghost plans
+    for (int l = 0; l < L; ++l) {
+        AmgLevel &Lv = h->lv[l];
+        const int nl = Lv.A.n_rows;
+        if (l + 1 < L) {
+            const AmgLevel &C = h->lv[l + 1];
+            Lv.own_c = Lv.sharded ? block_of(Lv.R.n_rows, n_ranks, rank) : Block{0, Lv.R.n_rows};
+            if ((rc = dev_build_sell_range(Lv.R, Lv.own_c, false, Lv.sellR, h->st))) return rc;
+            if ((rc = dev_build_sell_range(Lv.P, Lv.own, false, Lv.sellP, h->st))) return rc;
+            if (Lv.sharded) {
+                HostCsr hR, hPm;
+                if ((rc = download(Lv.R, hR))) return rc;
+                Lv.haloR = halo_plan(hR, n_ranks, rank, nullptr, 1);
+                if ((rc = upload_plan(Lv.haloR))) return rc;
+                if (C.sharded) {
+                    if ((rc = download(Lv.P, hPm))) return rc;
+                    Lv.haloP = halo_plan(hPm, n_ranks, rank, nullptr, 1);
+                    if ((rc = upload_plan(Lv.haloP))) return rc;
+                }
+                max_halo = std::max<size_t>(max_halo, std::max({Lv.haloR.n_send(), Lv.haloR.n_recv(), Lv.haloP.n_send(), Lv.haloP.n_recv()}));
+            }
+        }
+        if ((rc = dev_build_sell_range(Lv.A, Lv.own, true, Lv.sellN, h->st))) return rc;
+        if (l == 0) tr.mark("L0 SELL copies (A, R, P)");
+        const bool coloured = kind_of(h, l) == MGB_SMOOTH_GS_RB;
+        if (coloured && (rc = build_colouring_device(h, Lv))) return rc;
+        if (l == 0 && coloured) tr.mark("L0 colouring + colour SELL");
+        if (Lv.sharded) {
+            HostCsr hAm;
+            if ((rc = download(Lv.A, hAm))) return rc;
+            Lv.haloA = halo_plan(hAm, n_ranks, rank, nullptr, 1);
+            if ((rc = upload_plan(Lv.haloA))) return rc;
+            if (coloured) {
+                Lv.colour.h_group.assign((size_t)nl, 0);
+                ACK(cudaMemcpy(Lv.colour.h_group.data(), Lv.d_colour, sizeof(int) * (size_t)nl, cudaMemcpyDeviceToHost));
+                Lv.haloA_colour = halo_plan(hAm, n_ranks, rank, Lv.colour.h_group.data(), Lv.colour.n_groups);
+                if ((rc = upload_plan(Lv.haloA_colour))) return rc;
+            }
+            max_halo = std::max<size_t>(max_halo, std::max(Lv.haloA.n_send(), Lv.haloA.n_recv()));
+        }
+        max_blocks = std::max(max_blocks, ((size_t)nl * mgb::kLanes + 255) / 256 + 1);
     }
+    tr.mark("remaining levels: SELL, plans");
+    return MGB_OK;
+}
+
+int build_levels_device_from_host(mgb_amg *h, size_t n, const int64_t *ptr, const int64_t *col, const double *val, const double *rhs,
+                                  size_t &max_blocks, size_t &max_halo)
+{
+    h->lv.resize(h->cfg.levels);
+    HostCsr &A = h->lv[0].hA;                    // the level-0 operator as given (exact zeros dropped, CSRMatrix.cpp:13-14)
+    A.n_rows = A.n_cols = (int)n;
+    A.ptr.assign(n + 1, 0);
+    A.col.reserve((size_t)ptr[n]); A.val.reserve((size_t)ptr[n]);
+    for (size_t i = 0; i < n; ++i) {
+        for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= (int64_t)n) return mgb_set_error(MGB_ERR_ARG, "column index out of range");
+            if (k > ptr[i] && col[k] <= col[k - 1]) return mgb_set_error(MGB_ERR_ARG, "rows must be sorted by column without duplicates");
+            if (val[k] != 0) { A.col.push_back((int)col[k]); A.val.push_back(val[k]); }
+        }
+        A.ptr[i + 1] = (int)A.col.size();
+    }
+    h->lv[0].h_rhs.assign(rhs, rhs + n);
+    int rc;
+    if ((rc = upload(A, h->lv[0].A, h->st))) return rc;
+    ACK(cudaMalloc(&h->lv[0].b, sizeof(double) * n));
+    ACK(cudaMemcpyAsync(h->lv[0].b, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    return build_levels_device(h, max_blocks, max_halo);
+}
+
+// ---- hierarchy with the reference's semantics, built on the host (parity path) --------------------------------------------
+int build_levels_host(mgb_amg *h, size_t n, const int64_t *ptr, const int64_t *col, const double *val, const double *rhs,
+                      size_t &max_blocks, size_t &max_halo)
+{
+    const mgb_amg_config *cfg = &h->cfg;
+    const int n_ranks = h->n_ranks, rank = h->rank;
+    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 262144;
     h->lv.resize(cfg->levels);
     // level 0: CSRMatrix::copy_from drops exact zeros (CSRMatrix.cpp:13-14); rows must be column-sorted (they come from a map)
     {
@@ -959,7 +1072,6 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         }
     }
     // upload
-    size_t max_blocks = 1, max_halo = 1;
     for (int l = 0; l < cfg->levels; ++l) {
         AmgLevel &L = h->lv[l];
         const int nl = L.hA.n_rows;
@@ -973,6 +1085,8 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         ACK(cudaMemsetAsync(L.x, 0, bytes, h->st));
         ACK(cudaMemsetAsync(L.tmp, 0, bytes, h->st));
         if (nl) ACK(cudaMemcpyAsync(L.b, L.h_rhs.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, h->st));
+        ACK(cudaMalloc(&L.dl1, bytes));
+        if ((rc = dev_diagonals(L.A, L.diag, L.dl1, h->st))) return rc;      // (rewrites diag with the same values)
         ACK(cudaStreamSynchronize(h->st));
         if (l + 1 < cfg->levels) {
             if ((rc = upload(L.hP, L.P, h->st))) return rc;
@@ -1008,6 +1122,45 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
         }
         max_blocks = std::max(max_blocks, ((size_t)nl * mgb::kLanes + 255) / 256 + 1);
     }
+    return MGB_OK;
+}
+
+// common part of every constructor: handle, stream, communicator; `build` fills the levels
+template <class Build>
+int create_common(const mgb_amg_config *cfg, int rank, int n_ranks, const unsigned char nccl_id[128], mgb_amg_t *out, Build build)
+{
+    *out = nullptr;
+    if (cfg->levels < 1 || cfg->levels > 16) return mgb_set_error(MGB_ERR_ARG, "1 <= levels <= 16");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return mgb_set_error(MGB_ERR_ARG, "bad rank / n_ranks");
+    if (n_ranks > 1 && !nccl_id) return mgb_set_error(MGB_ERR_ARG, "n_ranks > 1 needs the ncclUniqueId of mgb_nccl_unique_id()");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return mgb_set_error(MGB_ERR_CUDA, "no CUDA device: libmgb200 has no CPU fallback");
+    }
+    ACK(cudaSetDevice(cfg->device));
+    mgb_amg *h = new mgb_amg();
+    struct Guard { mgb_amg *h; ~Guard() { if (h) mgb_amg_destroy(h); } } guard{h};     // any early return frees what exists so far
+    h->cfg = *cfg;
+    h->rank = rank; h->n_ranks = n_ranks;
+    h->omega = cfg->jacobi_omega > 0. ? cfg->jacobi_omega : 1.0;
+    ACK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {
+        int coop = 0, sms = 0, per_sm = 0;
+        ACK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+        ACK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        ACK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgb::k_amg_sell_gs_sweeps, 256, 0));
+        h->coop_max_blocks = (coop && cfg->coop_sweeps > 0) ? sms * per_sm : 0;
+    }
+    if (n_ranks > 1) {
+        auto &Nc = mgb::nccl();
+        if (!Nc.load()) return mgb_set_error(MGB_ERR_NCCL, Nc.error);
+        mgb::NcclUniqueId id;
+        std::memcpy(&id, nccl_id, sizeof(id));
+        ANK(Nc.CommInitRank(&h->comm, n_ranks, id, rank));
+    }
+    size_t max_blocks = 1, max_halo = 1;
+    if (int rc = build(h, max_blocks, max_halo)) return rc;
     if (n_ranks > 1) {
         ACK(cudaMalloc(&h->d_send, sizeof(double) * max_halo));
         ACK(cudaMalloc(&h->d_recv, sizeof(double) * max_halo));
@@ -1020,6 +1173,98 @@ int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *p
     return MGB_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+void mgb_amg_config_default(mgb_amg_config *c)
+{
+    std::memset(c, 0, sizeof(*c));
+    c->levels = 5;                 // AMG/src/main.cpp:126
+    c->eps = 0.2;                  // AMG/include/AMG.hpp:21
+    c->smoother = MGB_SMOOTH_GS_LEX;
+    c->pre_sweeps = 10; c->coarse_sweeps = 200; c->post_sweeps = 10;      // AMG/src/AMG.cpp:287,295,302
+    c->exact_order = 1;
+    c->device = 0;
+    for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
+    c->hybrid_gs = 0;
+    c->shard_min_rows = 262144;
+    c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
+    c->tail_max_rows = 4000;
+}
+
+void mgb_amg_config_fast(mgb_amg_config *c)
+{
+    mgb_amg_config_default(c);
+    c->smoother = MGB_SMOOTH_GS_RB;      // multicolour Gauss-Seidel
+    c->exact_order = 0;
+}
+
+void mgb_amg_config_device(mgb_amg_config *c)
+{
+    mgb_amg_config_fast(c);
+    c->device_setup = 1;
+    c->coarse_smoother = MGB_SMOOTH_L1_JACOBI;
+}
+
+int mgb_amg_n_levels(mgb_amg_t h) { return h ? (int)h->lv.size() : 0; }
+
+int mgb_amg_create_from_csr(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
+                            const double *val, const double *rhs, mgb_amg_t *out)
+{
+    return mgb_amg_create_sharded(cfg, n, ptr, col, val, rhs, 0, 1, nullptr, out);
+}
+
+int mgb_amg_partition(size_t n, int n_ranks, int rank, size_t *row0, size_t *rows)
+{
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n > (size_t)INT32_MAX || !row0 || !rows) return mgb_set_error(MGB_ERR_ARG, "bad partition arguments");
+    const Block b = block_of((int)n, n_ranks, rank);
+    *row0 = (size_t)b.r0; *rows = (size_t)b.size();
+    return MGB_OK;
+}
+
+int mgb_amg_create_sharded(const mgb_amg_config *cfg, size_t n, const int64_t *ptr, const int64_t *col,
+                           const double *val, const double *rhs, int rank, int n_ranks,
+                           const unsigned char nccl_id[128], mgb_amg_t *out)
+{
+    if (!cfg || !ptr || !col || !val || !rhs || !out) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    if (n == 0 || n > (size_t)1 << 30 || ptr[n] > (int64_t)INT32_MAX) return mgb_set_error(MGB_ERR_ARG, "matrix too large for int32 indices");
+    return create_common(cfg, rank, n_ranks, nccl_id, out, [&](mgb_amg *h, size_t &max_blocks, size_t &max_halo) {
+        return cfg->device_setup ? build_levels_device_from_host(h, n, ptr, col, val, rhs, max_blocks, max_halo)
+                                 : build_levels_host(h, n, ptr, col, val, rhs, max_blocks, max_halo);
+    });
+}
+
+int mgb_system_device_view(mgb_system_t S, int *device, int *n, int *nnz, const int **ptr, const int **col, const double **val, const double **rhs);
+
+// the level-0 system is already on the device (mgb_fem_assemble_p1 / mgb_fem_synthetic): nothing is staged through the host
+int mgb_amg_create_from_system(const mgb_amg_config *cfg, mgb_system_t sys, int rank, int n_ranks,
+                               const unsigned char nccl_id[128], mgb_amg_t *out)
+{
+    if (!cfg || !sys || !out) return mgb_set_error(MGB_ERR_ARG, "null argument");
+    if (!cfg->device_setup) return mgb_set_error(MGB_ERR_ARG, "mgb_amg_create_from_system builds the hierarchy on the device: set device_setup = 1");
+    int sdev = 0, n = 0, nnz = 0;
+    const int *sp = nullptr, *sc = nullptr;
+    const double *sv = nullptr, *sr = nullptr;
+    if (int rc = mgb_system_device_view(sys, &sdev, &n, &nnz, &sp, &sc, &sv, &sr)) return rc;
+    if (sdev != cfg->device) return mgb_set_error(MGB_ERR_ARG, "the system lives on another device than cfg->device");
+    if (n <= 0) return mgb_set_error(MGB_ERR_ARG, "empty system");
+    return create_common(cfg, rank, n_ranks, nccl_id, out, [&](mgb_amg *h, size_t &max_blocks, size_t &max_halo) -> int {
+        h->lv.resize(h->cfg.levels);
+        DevCsr &A = h->lv[0].A;
+        A.n_rows = A.n_cols = n; A.nnz = nnz;
+        ACK(cudaMalloc(&A.ptr, sizeof(int) * ((size_t)n + 1)));
+        ACK(cudaMalloc(&A.col, sizeof(int) * (size_t)std::max(nnz, 1)));
+        ACK(cudaMalloc(&A.val, sizeof(double) * (size_t)std::max(nnz, 1)));
+        ACK(cudaMalloc(&h->lv[0].b, sizeof(double) * (size_t)n));
+        ACK(cudaMemcpy(A.ptr, sp, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice));
+        ACK(cudaMemcpy(A.col, sc, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice));
+        ACK(cudaMemcpy(A.val, sv, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice));
+        ACK(cudaMemcpy(h->lv[0].b, sr, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice));
+        return build_levels_device(h, max_blocks, max_halo);
+    });
+}
+
 void mgb_amg_destroy(mgb_amg_t h)
 {
     if (!h) return;
@@ -1029,7 +1274,7 @@ void mgb_amg_destroy(mgb_amg_t h)
     for (auto &L : h->lv) {
         L.A.release(); L.P.release(); L.R.release(); L.lex.release(); L.colour.release(); L.sell.release(); L.sellN.release(); L.sellR.release(); L.sellP.release();
         L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
-        cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp);
+        cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp); cudaFree(L.dl1); cudaFree(L.b0); cudaFree(L.d_colour); cudaFree(L.d_cf);
     }
     cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFree(h->d_send); cudaFree(h->d_recv);
     if (h->comm) mgb::nccl().CommDestroy(h->comm);
@@ -1043,10 +1288,10 @@ int mgb_amg_level_info(mgb_amg_t h, int level, size_t *n, size_t *nnz_a, size_t 
 {
     if (!h || level < 0 || level >= (int)h->lv.size()) return mgb_set_error(MGB_ERR_ARG, "bad level");
     const AmgLevel &L = h->lv[level];
-    if (n) *n = (size_t)L.hA.n_rows;
-    if (nnz_a) *nnz_a = (size_t)L.hA.nnz();
-    if (nnz_p) *nnz_p = (size_t)L.hP.nnz();
-    if (n_coarse) *n_coarse = (size_t)L.hP.n_cols;
+    if (n) *n = (size_t)L.A.n_rows;
+    if (nnz_a) *nnz_a = (size_t)L.A.nnz;
+    if (nnz_p) *nnz_p = (size_t)L.P.nnz;
+    if (n_coarse) *n_coarse = (size_t)L.P.n_cols;
     if (n_waves) *n_waves = L.lex.n_groups;
     if (n_colours) *n_colours = L.colour.n_groups;
     return MGB_OK;
@@ -1071,13 +1316,33 @@ static int copy_csr(const HostCsr &M, int64_t *ptr, int64_t *col, double *val)
 int mgb_amg_get_matrix(mgb_amg_t h, int level, int which, int64_t *ptr, int64_t *col, double *val)
 {
     if (!h || level < 0 || level >= (int)h->lv.size() || !ptr || !col || !val) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
-    return copy_csr(which == 0 ? h->lv[level].hA : h->lv[level].hP, ptr, col, val);
+    const AmgLevel &L = h->lv[level];
+    if (h->cfg.device_setup) {                  // the hierarchy lives on the device: a host copy is made for the caller
+        ACK(cudaSetDevice(h->cfg.device));
+        HostCsr tmp;
+        if (int rc = download(which == 0 ? L.A : L.P, tmp)) return rc;
+        return copy_csr(tmp, ptr, col, val);
+    }
+    return copy_csr(which == 0 ? L.hA : L.hP, ptr, col, val);
 }
 
 int mgb_amg_get_schedule(mgb_amg_t h, int level, int which, int *group_of_row)
 {
     if (!h || level < 0 || level >= (int)h->lv.size() || !group_of_row) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
-    const Schedule &S = which == 0 ? h->lv[level].lex : h->lv[level].colour;
+    const AmgLevel &L = h->lv[level];
+    if (which == 2) {
+        if (!L.d_cf) return mgb_set_error(MGB_ERR_STATE, "the C/F state is kept for device-built levels that were coarsened");
+        ACK(cudaSetDevice(h->cfg.device));
+        ACK(cudaMemcpy(group_of_row, L.d_cf, sizeof(int) * (size_t)L.A.n_rows, cudaMemcpyDeviceToHost));
+        return MGB_OK;
+    }
+    const Schedule &S = which == 0 ? L.lex : L.colour;
+    if (which == 1 && S.h_group.empty() && L.d_colour) {
+        ACK(cudaSetDevice(h->cfg.device));
+        ACK(cudaMemcpy(group_of_row, L.d_colour, sizeof(int) * (size_t)L.A.n_rows, cudaMemcpyDeviceToHost));
+        return MGB_OK;
+    }
+    if (S.h_group.empty() && L.A.n_rows) return mgb_set_error(MGB_ERR_STATE, "this level holds no such schedule");
     std::copy(S.h_group.begin(), S.h_group.end(), group_of_row);
     return MGB_OK;
 }
@@ -1150,15 +1415,15 @@ int mgb_amg_apply(mgb_amg_t h, double *residual_norm)
     const int T = h->lt >= 0 ? h->lt : L - 1;          // the levels T .. L-1 are one launch when the tail is on
     int rc, i;
     for (i = 0; i < T; ++i) {
-        if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.pre_sweeps))) return rc;
+        if ((rc = do_smooth(h, i, kind_of(h, i), h->cfg.pre_sweeps))) return rc;
         if ((rc = do_restrict(h, i + 1))) return rc;
     }
     if (h->lt >= 0) {
         if ((rc = launch_tail(h, 0, h->cfg.pre_sweeps, h->cfg.coarse_sweeps, h->cfg.post_sweeps))) return rc;
-    } else if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.coarse_sweeps))) return rc;
+    } else if ((rc = do_smooth(h, i, kind_of(h, i), h->cfg.coarse_sweeps))) return rc;
     for (i--; i >= 0; --i) {
         if ((rc = do_prolong(h, i))) return rc;
-        if ((rc = do_smooth(h, i, h->cfg.smoother, h->cfg.post_sweeps))) return rc;
+        if ((rc = do_smooth(h, i, kind_of(h, i), h->cfg.post_sweeps))) return rc;
     }
     h->stats.cycles++;
     if (residual_norm) return do_residual(h, 0, residual_norm);
@@ -1174,7 +1439,6 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
     if (!h || !hist || !n_hist || maxit < 0 || nu1 < 0 || nu2 < 0 || coarse < 1) return mgb_set_error(MGB_ERR_ARG, "bad argument");
     ACK(cudaSetDevice(h->cfg.device));
     const int L = (int)h->lv.size();
-    const int kind = h->cfg.smoother;
     int rc, n = 0;
     double nrm = 0.;
     if ((rc = do_residual(h, 0, &nrm))) return rc;
@@ -1186,7 +1450,7 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
         int rc;
         for (int l = 0; l < T; ++l) {                                      // downward
             AmgLevel &F = h->lv[l], &C = h->lv[l + 1];
-            if (nu1 > 0 && (rc = do_smooth(h, l, kind, nu1))) return rc;
+            if (nu1 > 0 && (rc = do_smooth(h, l, kind_of(h, l), nu1))) return rc;
             if ((rc = residual_to_tmp(h, F, false))) return rc;               // r = b - A x into F.tmp (no host read-back)
             if (F.R.n_rows) {                                                  // b_c = P^T r, x_c = 0
                 if ((rc = restrict_vec(h, l + 1, F.tmp, C.b))) return rc;
@@ -1199,14 +1463,14 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
             }
         }
         if (h->lt >= 0) { if ((rc = launch_tail(h, 1, nu1, coarse, nu2))) return rc; }
-        else if ((rc = do_smooth(h, L - 1, kind, coarse))) return rc;
+        else if ((rc = do_smooth(h, L - 1, kind_of(h, L - 1), coarse))) return rc;
         for (int l = T - 1; l >= 0; --l) {                                  // upward
             if ((rc = do_prolong(h, l))) return rc;
-            if (nu2 > 0 && (rc = do_smooth(h, l, kind, nu2))) return rc;
+            if (nu2 > 0 && (rc = do_smooth(h, l, kind_of(h, l), nu2))) return rc;
         }
         return residual_to_tmp(h, h->lv[0], true);
     };
-    const bool graphed = h->cfg.cycle_graph >= 0 && kind != MGB_SMOOTH_JACOBI;
+    const bool graphed = h->cfg.cycle_graph >= 0;      // (Jacobi-type sweeps keep their pointers in place, see do_smooth)
     mgb_amg::CycleGraph *G = nullptr;
     if (graphed && maxit > 0 && nrm > target) {
         for (auto it = h->graphs.begin(); it != h->graphs.end();) {
@@ -1247,7 +1511,8 @@ int mgb_amg_solve(mgb_amg_t h, double tol, int maxit, int nu1, int nu2, int coar
     for (int l = 1; l < L; ++l) {
         AmgLevel &C = h->lv[l];
         if (!C.A.n_rows) continue;
-        ACK(cudaMemcpyAsync(C.b, C.h_rhs.data(), sizeof(double) * (size_t)C.A.n_rows, cudaMemcpyHostToDevice, h->st));
+        if (C.b0) ACK(cudaMemcpyAsync(C.b, C.b0, sizeof(double) * (size_t)C.A.n_rows, cudaMemcpyDeviceToDevice, h->st));
+        else ACK(cudaMemcpyAsync(C.b, C.h_rhs.data(), sizeof(double) * (size_t)C.A.n_rows, cudaMemcpyHostToDevice, h->st));
         if (C.sell.n_slots) mgb::k_amg_to_slots<<<(C.sell.n_slots + 255) / 256, 256, 0, h->st>>>(C.sell.row_of_slot, C.sell.n_slots, C.b, C.sell.b_s);
     }
     ACK(cudaStreamSynchronize(h->st));
@@ -1334,6 +1599,27 @@ int mgb_amg_halo_plan(mgb_csr_t M, int n_ranks, int rank, const int *group_of_co
     for (size_t q = 0; q < H.send_ptr.size(); ++q) { send_ptr[q] = H.send_ptr[q]; recv_ptr[q] = H.recv_ptr[q]; }
     if (send_idx) for (size_t t = 0; t < H.send_idx.size(); ++t) send_idx[t] = H.send_idx[t];
     if (recv_idx) for (size_t t = 0; t < H.recv_idx.size(); ++t) recv_idx[t] = H.recv_idx[t];
+    return MGB_OK;
+}
+
+int mgb_amg_checksum(mgb_amg_t h, int level, int which, uint64_t *out)
+{
+    if (!h || level < 0 || level >= (int)h->lv.size() || !out || which < 0 || which > 2) return mgb_set_error(MGB_ERR_ARG, "bad level/pointer");
+    ACK(cudaSetDevice(h->cfg.device));
+    AmgLevel &L = h->lv[level];
+    const double *v = which == 0 ? L.x : (which == 1 ? L.b : L.tmp);
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->d_scal + 2);
+    ACK(cudaMemsetAsync(d, 0, sizeof(*d), h->st));
+    // a sharded level: every rank adds its own rows; a replicated one: rank 0's copy counts
+    Block rows = L.own;
+    if (!L.sharded && h->n_ranks > 1 && h->rank != 0) rows = Block{0, 0};
+    if (rows.size() > 0) mgb::k_amg_checksum<<<std::min((rows.size() + 255) / 256, 2368), 256, 0, h->st>>>(v, rows.r0, rows.r1, d);
+    ACK(cudaGetLastError());
+    if (h->n_ranks > 1) ANK(mgb::nccl().AllReduce(d, d, 1, mgb::kNcclUint64, mgb::kNcclSum, h->comm, h->st));
+    unsigned long long hv = 0;
+    ACK(cudaMemcpyAsync(&hv, d, sizeof(hv), cudaMemcpyDeviceToHost, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    *out = (uint64_t)hv;
     return MGB_OK;
 }
 

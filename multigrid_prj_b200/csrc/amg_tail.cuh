@@ -19,7 +19,8 @@ constexpr int kAmgTailMaxLevels = 12;
 
 struct AmgTailLevel {
     CsrDev A, P, R;                  // P (this level <- next), R = P^T; unused on the last level
-    const double *diag;
+    const double *diag, *dl1;        // a_ii; a_ii + sum |a_ij| (l1-Jacobi, may be null otherwise)
+    int kind;                        // smoother of this level: 0 lexicographic GS, 1 Jacobi, 3 multicolour GS, 4 l1-Jacobi
     double *x, *b, *tmp;
     const int *grp_ptr, *grp_rows;   // independent sets of the smoother: colours, or wavefronts of the lexicographic sweep
     int n_groups;
@@ -27,7 +28,6 @@ struct AmgTailLevel {
 
 struct AmgTailParams {
     int nlev;                        // lv[0] = first tail level ... lv[nlev-1] = coarsest level
-    int kind;                        // MGB_SMOOTH_* : 0 lexicographic GS, 1 Jacobi, 3 multicolour GS
     int exact;                       // 1: reference term order, unfused IEEE ops; 0: the fast kernels' arithmetic
     int mode;                        // 0: the reference's pass (x_c = P^T x, AMG.cpp:277-308); 1: correction scheme (b_c = P^T r, x_c = 0)
     int pre, coarse, post;           // sweeps before the transfer down, on the last level, after the transfer up
@@ -70,11 +70,25 @@ __device__ __forceinline__ void tail_jacobi_sweep(const AmgTailLevel &L, bool ex
     __syncthreads();
 }
 
-__device__ __forceinline__ void tail_smooth(const AmgTailLevel &L, int kind, bool exact, double omega, int sweeps)
+// one l1-Jacobi sweep (k_amg_sell<5>)
+__device__ __forceinline__ void tail_l1_sweep(const AmgTailLevel &L)
+{
+    const int n = L.A.n_rows;
+    for (int i = threadIdx.x; i < n; i += kAmgTailThreads) {
+        const double xi = L.x[i];
+        L.tmp[i] = xi + (L.b[i] - (offdiag_dot_fast(L.A, L.x, i) + L.diag[i] * xi)) / L.dl1[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kAmgTailThreads) L.x[i] = L.tmp[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void tail_smooth(const AmgTailLevel &L, bool exact, double omega, int sweeps)
 {
     for (int s = 0; s < sweeps; ++s) {
-        if (kind == 1) tail_jacobi_sweep(L, exact, omega);
-        else tail_gs_sweep(L, exact || kind == 0);
+        if (L.kind == 1) tail_jacobi_sweep(L, exact, omega);
+        else if (L.kind == 4) tail_l1_sweep(L);
+        else tail_gs_sweep(L, exact || L.kind == 0);
     }
 }
 
@@ -103,7 +117,7 @@ k_amg_tail(AmgTailParams p)
     const int last = p.nlev - 1;
     for (int l = 0; l < last; ++l) {                          // downward
         const AmgTailLevel &F = p.lv[l], &C = p.lv[l + 1];
-        tail_smooth(F, p.kind, exact, p.omega, p.pre);
+        tail_smooth(F, exact, p.omega, p.pre);
         if (p.mode == 0) tail_restrict(F, F.x, C.x, exact);   // AMG.cpp:50-74: the SOLUTION is restricted
         else {
             tail_residual(F, exact);
@@ -112,12 +126,12 @@ k_amg_tail(AmgTailParams p)
             __syncthreads();
         }
     }
-    tail_smooth(p.lv[last], p.kind, exact, p.omega, p.coarse);
+    tail_smooth(p.lv[last], exact, p.omega, p.coarse);
     for (int l = last - 1; l >= 0; --l) {                     // upward
         const AmgTailLevel &F = p.lv[l], &C = p.lv[l + 1];
         for (int i = threadIdx.x; i < F.P.n_rows; i += kAmgTailThreads) prolong_row_add(F.P, C.x, F.x, i);
         __syncthreads();
-        tail_smooth(F, p.kind, exact, p.omega, p.post);
+        tail_smooth(F, exact, p.omega, p.post);
     }
 }
 
