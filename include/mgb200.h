@@ -148,6 +148,12 @@ int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double
 /* switches mgb_gmg_config.defer_norm of a live handle (measurement: the same handle timed both ways) */
 int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer);
 
+/* generation of the streaming red-black kernel behind the fused launches: 2 (default) = bulk-copy fed kernel with statically
+ * addressed rings (csrc/gmg_stream2.cuh) wherever it is instantiated, 1 = first-generation kernel everywhere.  Results are
+ * bit-identical; the switch exists for A/B measurement and for the parity test of one against the other.
+ * The environment variable MGB_STREAM_IMPL sets the default of new handles. */
+int mgb_gmg_set_stream_impl(mgb_gmg_t h, int impl);
+
 /* replaces SawtoothMGIteration::apply_iteration_to_vec (multigrid.hpp:126-145) applied to u.
  * coarse_relres = the value the reference prints per cycle; coarse_iters = coarse-solve sweeps. */
 int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "mgb_gmg_prolong": (_i, [_vp, _i]),
     "mgb_gmg_set_cycle": (_i, [_vp, _i, _i, _i, _d, _i]),
     "mgb_gmg_set_defer_norm": (_i, [_vp, _i]),
+    "mgb_gmg_set_stream_impl": (_i, [_vp, _i]),
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
     "mgb_gmg_fine_leg": (_i, [_vp, _pd]),
     "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),

@@ -17,12 +17,14 @@
 // needs ONE exchange of k... 2k rows instead of one per colour pass.  Norms: ncclAllReduce of one fp64.
 #include "../../include/mgb200.h"
 #include "gmg_kernels.cuh"
+#include "gmg_stream2.h"
 #include "gmg_tail.cuh"
 #include "nccl_dyn.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -122,6 +124,8 @@ struct mgb_gmg {
     double norm_f = 0.;               // sum f^2 on the fine grid (Residual ctor, solvers.hpp:237-242)
     bool have_rhs = false;
     int n_sm = 148;
+    int stream2_min_rows = 128;       // shortest row chunk the second-generation streaming kernel is used for
+    int stream_impl = 2;              // generation of the streaming red-black kernel (gmg_stream2.cuh where instantiated; 1 = gmg_kernels.cuh only)
     mgb_gmg_stats stats{};
     // CUDA graphs of `period` driver iterations, keyed by the buffer-pointer state they were captured in
     struct IterGraph {
@@ -253,34 +257,54 @@ int prepare_kernels()
     return MGB_OK;
 }
 
+// rows per chunk of a streaming launch: a CTA needs (rc + 2S) row steps and the grid needs ceil(nx*ny/slots) waves; pick the
+// even rc that minimises their product (small levels: many short chunks, the recomputed rows cost nothing there; large
+// levels: one wave of long chunks, 2S/rc redundant rows)
+void pick_chunks(int rows, int nx, int slots, int S, int *rc_out, int *ny_out)
+{
+    int rc = rows + (rows & 1), ny = 1;
+    double best = 1e300;
+    for (int n0 = 1; n0 <= std::max(1, rows / 8); ++n0) {
+        int c = (rows + n0 - 1) / n0;
+        c += c & 1;
+        const int n = (rows + c - 1) / c;
+        const int waves = (nx * n + slots - 1) / slots;
+        const double t = (double)(c + 2 * S) * waves;
+        if (t < best) { best = t; rc = c; ny = n; }
+    }
+    *rc_out = rc; *ny_out = ny;
+}
+
 template <int S, bool EXACT, int MODE, bool PIN>
 int launch_rb_stream_t(mgb_gmg *h, const LevelGeom &g, const double *in, const double *rhs, double *out, double *ucorr,
                        const LevelGeom &gc, double *coarse_out = nullptr, int restr = 0, double rscale = 1.0)
 {
-    int occ = 1;
-    constexpr int smem = mgb::stream_smem_bytes<S>();
-    if (int rc = stream_occupancy<S, EXACT, MODE, PIN>(&occ)) return rc;
     const int OW = mgb::kStreamTW - 2 * (S + 2 * (MODE != 0));    // owned columns per CTA (kernel: HC)
     double *aux = (MODE == 3) ? coarse_out : h->d_partial;
     const int nx = (g.w + OW - 1) / OW;
-    const int slots = h->n_sm * occ;
-    // rows per chunk: a CTA needs (rc + 2S) steps and the grid needs ceil(nx*ny/slots) waves; pick the
-    // even rc that minimises their product (small levels: many short chunks, the recomputed rows cost nothing
-    // there; large levels: one wave of long chunks, 2S/rc redundant rows)
-    int rc = g.rows + (g.rows & 1), ny = 1;
-    {
-        double best = 1e300;
-        for (int n0 = 1; n0 <= std::max(1, g.rows / 8); ++n0) {
-            int c = (g.rows + n0 - 1) / n0;
-            c += c & 1;
-            const int n = (g.rows + c - 1) / c;
-            const int waves = (nx * n + slots - 1) / slots;
-            const double t = (double)(c + 2 * S) * waves;
-            if (t < best) { best = t; rc = c; ny = n; }
-        }
+    int rc = 0, ny = 1;
+    bool gen2 = h->stream_impl >= 2 && mgb::stream2_has(S, EXACT, MODE, PIN);
+    if (gen2) {
+        // second-generation kernel (bulk-copy fed, statically addressed rings, rhs ring in tensor memory): same tiling, same
+        // results.  Its unrolled steady loop pays off on long row chunks; short chunks (small levels, cut into many chunks
+        // to fill the SMs) are mostly guarded steps and stay on the first-generation kernel.
+        int occ = 1;
+        CK(mgb::stream2_occupancy(S, EXACT, MODE, PIN, &occ));
+        pick_chunks(g.rows, nx, h->n_sm * occ, S, &rc, &ny);
+        gen2 = rc >= h->stream2_min_rows;
     }
-    if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
-    mgb::k_rb_stream<S, EXACT, MODE, PIN><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, aux, gc, restr, rscale);
+    if (gen2) {
+        if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
+        mgb::Stream2Args a{g, gc, in, rhs, out, ucorr, aux, rc, restr, rscale};
+        CK(mgb::stream2_launch(S, EXACT, MODE, PIN, dim3(nx, ny), h->st, a));
+    } else {
+        int occ = 1;
+        constexpr int smem = mgb::stream_smem_bytes<S>();
+        if (int rc0 = stream_occupancy<S, EXACT, MODE, PIN>(&occ)) return rc0;
+        pick_chunks(g.rows, nx, h->n_sm * occ, S, &rc, &ny);
+        if ((size_t)nx * ny > h->n_partial) return fail(MGB_ERR_STATE, "partial-sum buffer too small");
+        mgb::k_rb_stream<S, EXACT, MODE, PIN><<<dim3(nx, ny), mgb::kStreamNT, smem, h->st>>>(g, in, rhs, out, rc, ucorr, aux, gc, restr, rscale);
+    }
     // 24 B per point per sweep, S/2 sweeps per launch (+ correction 24 + norm-only residual 16 when fused)
     count(h, (24. * (S / 2) + (MODE == 1 ? 40. : (MODE >= 2 ? 24. : 0.))) * npts(g) + ((PIN || MODE == 3) ? 8. * (npts(g) + npts(gc)) : 0.));
     if (MODE == 1) h->norm_partials = nx * ny;
@@ -855,7 +879,7 @@ std::vector<const double *> pointer_state(mgb_gmg *h)
     std::vector<const double *> k;
     for (auto &lv : h->lv) { k.push_back(lv.u); k.push_back(lv.tu); k.push_back(lv.e); k.push_back(lv.t); k.push_back(lv.r); }
     k.push_back((const double *)(uintptr_t)((h->cfg.smoother << 8) | (h->cfg.pre_smoother << 4) | h->cfg.restriction));
-    k.push_back((const double *)(uintptr_t)((h->cfg.nu << 8) | h->cfg.n_pre));
+    k.push_back((const double *)(uintptr_t)((h->stream_impl << 16) | (h->cfg.nu << 8) | h->cfg.n_pre));
     // everything else the captured launches depend on: whether the leading exchange of u is skipped
     // (one_iteration_ca), the coarse-solve parameters baked into TailParams, the norm's all-reduce placement
     const bool halo_ok = ca_applicable(h) && h->u_halo_valid >= ca_u_depth(h, plan_depths(h));
@@ -1024,6 +1048,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     h->ls = ls;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    if (const char *e = std::getenv("MGB_STREAM_IMPL")) h->stream_impl = (std::atoi(e) == 1) ? 1 : 2;
+    if (const char *e = std::getenv("MGB_STREAM2_MIN_ROWS")) h->stream2_min_rows = std::max(0, std::atoi(e));
     if (cfg->n_ranks > 1) {
         auto &Nc = mgb::nccl();
         if (!Nc.load()) return fail(MGB_ERR_NCCL, Nc.error);
@@ -1224,6 +1250,14 @@ int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer)
 {
     if (!h) return fail(MGB_ERR_ARG, "null handle");
     h->cfg.defer_norm = defer ? 1 : 0;
+    return MGB_OK;
+}
+
+int mgb_gmg_set_stream_impl(mgb_gmg_t h, int impl)
+{
+    if (!h) return fail(MGB_ERR_ARG, "null handle");
+    if (impl != 1 && impl != 2) return fail(MGB_ERR_ARG, "stream_impl must be 1 or 2");
+    h->stream_impl = impl;            // cached iteration graphs are keyed on it
     return MGB_OK;
 }
 

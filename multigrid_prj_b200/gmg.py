@@ -188,6 +188,10 @@ class Gmg:
         check(self.lib.mgb_gmg_run_cycles(self.h, cycles, C.byref(rel) if want_relres else None))
         return rel.value
 
+    def set_stream_impl(self, impl):
+        """1 = first-generation streaming kernel everywhere, 2 = bulk-copy fed kernel where instantiated (default)"""
+        check(self.lib.mgb_gmg_set_stream_impl(self.h, impl))
+
     def checksum(self, level=0, which=VEC_U):
         """64-bit checksum over all ranks (collective when n_ranks > 1): equal <=> bit-identical vectors"""
         v = C.c_uint64()
