@@ -30,7 +30,7 @@ struct Inst {
             const int smem_cta = smem + (int)fa.sharedSizeBytes + 1024;
             int o = std::min(regs_sm / regs_cta, smem_sm / smem_cta);
             if (kS2TmemB) o = std::min(o, 512 / (int)kS2TmemCols);
-            o = std::min(o, kS2TmemB ? 3 : 2);           // __launch_bounds__ of the kernel
+            o = std::min(o, s2_min_ctas<S>());           // __launch_bounds__ of the kernel
             cached = o > 0 ? o : 1;
             if (getenv("MGB_DEBUG")) fprintf(stderr, "k_rb_stream2<%d,%d,%d,%d>: smem %d B, occupancy %d\n", S, (int)EXACT, MODE, (int)PIN, smem, o);
         }
@@ -48,7 +48,7 @@ struct Inst {
 
 // the combinations the fused fast path launches (everything else stays on the first-generation kernel)
 #define MGB_S2_LIST(F) \
-    F(10, false, 1, true) F(10, false, 0, true)
+    F(10, false, 1, true) F(10, false, 0, true) F(4, false, 3, false) F(4, false, 2, false)
 
 }  // namespace
 

@@ -28,12 +28,17 @@ constexpr int kS2RB = 24;             // rows of the right-hand side ring (>= 2S
 constexpr int kS2NS = 3;              // publication slots per half-sweep stage
 constexpr int kS2CR = 6;              // coarse-row slots (PIN)
 constexpr int kS2CW = 136;            // doubles per coarse-row slot (129 used, start rounded down to an even column)
+constexpr bool kS2TmemBConst = true;  // rhs ring in tensor memory (see kS2TmemB below)
 constexpr int kS2HP = kS2NT + 2;      // doubles per published half row: [pad][128 values][pad]
 
 // row steps per unrolled period of the steady loop: every ring period divides it (the rhs ring of 24 rows is reached
 // through two base addresses that swap every period)
 template <int S>
 constexpr int s2_period() { return 12; }
+
+// resident CTAs per SM the kernel is compiled for (register budget): 3 for the 23-row window of 10 half-sweeps
+template <int S>
+constexpr int s2_min_ctas() { return kS2TmemBConst ? (S <= 4 ? 4 : 3) : 2; }
 
 template <int S, int MODE, bool PIN>
 struct S2Layout {
@@ -95,7 +100,7 @@ __device__ __forceinline__ void s2_bulk_g2s(uint32_t dst, const void *src, uint3
 // registers it costs 88 registers (2 CTAs per SM, spills); kept in shared memory it costs 48 KB per CTA and a third of
 // the shared-memory bandwidth of a step.  TMEM (256 KB per SM, idle in a kernel without tensor-core work) holds it at no
 // cost to either: 4 columns per row, ring slot = immediate offset in the unrolled loop.
-constexpr bool kS2TmemB = true;
+constexpr bool kS2TmemB = kS2TmemBConst;
 constexpr uint32_t kS2TmemCols = 128;             // >= 4 * R, power of two
 __device__ __forceinline__ void s2_tm_st4(uint32_t taddr, double a, double b)
 {
@@ -119,7 +124,7 @@ __device__ __forceinline__ double s2_tm_value(uint32_t lo, uint32_t hi)
 // per-thread / per-CTA constants of one launch (all members live in registers or uniform registers)
 struct S2Ctx {
     LevelGeom g, gc;
-    int t, j0, i0, i1, ifirst, ilast, glast, koff, ksteps;
+    int t, warp, j0, i0, i1, ifirst, ilast, glast, koff, ksteps;
     bool first_is_bdry, last_is_bdry, own, bc0, bc1;
     double inv_diag, q0, q1, m0, m1;
     const double *b, *uin;
@@ -135,6 +140,13 @@ struct S2Ctx {
     int restr;
     double rscale;
 };
+
+__device__ __forceinline__ bool s2_elect()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ int s2_wrap(int x, int n) { return x < 0 ? x + n : (x >= n ? x - n : x); }
 
@@ -226,11 +238,12 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
         const int s0 = s2_wrap(kb - d, kS2RB);
         return (s0 < R ? tA : tB) + 4u * (uint32_t)s0;
     };
-    if ((kb % kS2G) == 0 && t == 32 * ((kb / kS2G) & 3)) {      // the requesting thread rotates over the four warps
-#pragma unroll
-        for (int j = kS2G; j < 2 * kS2G; ++j) {
-            if (GUARD) s2_issue<S, MODE, PIN>(c, k + j, s2_wrap(kb + j, R), false);
-            else s2_issue_steady<S, MODE, PIN>(c, k + j, s2_wrap(kb + j, R));
+    // the row kS2D-1 steps ahead is requested by one elected lane; the requesting warp rotates over the four warps and
+    // everything the request needs is warp-uniform (no per-lane address arithmetic)
+    if (c.warp == (kb & 3)) {
+        if (s2_elect()) {
+            if (GUARD) s2_issue<S, MODE, PIN>(c, k + kS2D - 1, s2_wrap(kb + kS2D - 1, R), false);
+            else s2_issue_steady<S, MODE, PIN>(c, k + kS2D - 1, s2_wrap(kb + kS2D - 1, R));
         }
     }
 
@@ -453,7 +466,7 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
 }
 
 template <int S, bool EXACT, int MODE, bool PIN>
-__global__ void __launch_bounds__(kS2NT, kS2TmemB ? 3 : 2)
+__global__ void __launch_bounds__(kS2NT, s2_min_ctas<S>())
 k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restrict__ b, double *__restrict__ uout,
              int rows_per_chunk, double *ucorr, double *__restrict__ partial, LevelGeom gc, int restr, double rscale)
 {
@@ -469,6 +482,7 @@ k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restri
     c.sm = s2_smem; c.sbase = s2_smem_u32(s2_smem);
     const int t = threadIdx.x;
     c.t = t;
+    c.warp = __shfl_sync(0xffffffffu, t >> 5, 0);      // warp-uniform copy of the warp index
     const int jbase = blockIdx.x * OW - HC;           // global column of tile column 0 (even)
     c.j0 = jbase + 2 * t;
     c.i0 = blockIdx.y * rows_per_chunk;               // rows_per_chunk is even (host)
@@ -519,9 +533,8 @@ k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (t == 0) {      // rows up to the end of the request group that the first step with (k + koff) mod kS2G == 0 completes
-        const int g0 = (kS2G - c.koff % kS2G) % kS2G;
-        for (int kp = 0; kp < g0 + kS2G; ++kp) s2_issue<S, MODE, PIN>(c, kp, (kp + c.koff) % R, kp == 0);
+    if (t == 0) {
+        for (int kp = 0; kp < kS2D - 1; ++kp) s2_issue<S, MODE, PIN>(c, kp, (kp + c.koff) % R, kp == 0);
     }
     c.tb = 0;
     if (kS2TmemB) {
