@@ -477,10 +477,12 @@ def main():
     group = cfg.nu if (kind == G.GS_RB and cfg.rb_fused) else 1
     if fused_leg:
         run_k = lambda: g.fine_leg()
-        kname = (f"k_rb_stream<{2 * cfg.nu}, EXACT=0, MODE=1, PIN=1>: prolongation + {cfg.nu} red-black sweeps + correction + "
-                 f"residual norm in one launch ({cfg.nu} x 24 + 10 + 24 + 16 B/pt algorithmic)")
+        gen2 = os.environ.get("MGB_STREAM_IMPL", "2") != "1" and cfg.nu == 5
+        kname = (f"k_rb_stream{'2' if gen2 else ''}<{2 * cfg.nu}, EXACT=0, MODE=1, PIN=1>: prolongation + {cfg.nu} red-black sweeps + "
+                 f"correction + residual norm in one launch ({cfg.nu} x 24 + 10 + 24 + 16 B/pt algorithmic)"
+                 + ("; rows fed by cp.async.bulk on mbarriers, right-hand-side ring in tensor memory, 3 CTAs per SM" if gen2 else ""))
         moved = 26.0 * n * rows0                      # read res 8, u 8, coarse err 2; write u 8
-        tr = ncu_traffic(r"k_rb_stream<10, 0, 1, 1>") if n == 8193 else None
+        tr = ncu_traffic(r"k_rb_stream2<10, 0, 1, 1>" if gen2 else r"k_rb_stream<10, 0, 1, 1>") if n == 8193 else None
         traffic, traffic_src = (tr[0], tr[1] + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch at 8193^2; "
                                 "read from the committed file, not measured in this run)") if tr else (None, None)
     else:
@@ -508,7 +510,7 @@ def main():
                 "note": "achieved counts SURVEY 8d algorithmic bytes of every operation the launch performs (no credit for "
                         "fusion); the launch is temporally blocked and moves each array through HBM once, so frac > 1 measures "
                         "what fusion saved and hbm_frac_actual is the fraction of HBM bandwidth the launch really uses "
-                        "(it is bound by issue/shared-memory latency at 8 warps per SM, see DESIGN.md section 5)",
+                        "(it is bound by issue slots and shared-memory bandwidth at 12 warps per SM, see DESIGN.md section 5)",
                 "kernel": kname, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kms / launches,
                 "step_algorithmic_gbs": stats["bytes_algorithmic"] / (ms * 1e-3) / 1e9,
