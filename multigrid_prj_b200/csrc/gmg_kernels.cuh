@@ -181,6 +181,15 @@ k_reduce_partials(const double *__restrict__ partial, int n, double *__restrict_
     if (threadIdx.x == 0) out[0] = t;
 }
 
+// out = sum over ranks p = 0..n-1 of (p == rank ? *local : parts[p]), added in rank order: every rank forms the same bits
+__global__ void k_sum_ranks(const double *__restrict__ parts, const double *__restrict__ local, int n, int rank, double *__restrict__ out)
+{
+    if (threadIdx.x != 0) return;
+    double acc = 0.;
+    for (int p = 0; p < n; ++p) acc += (p == rank) ? local[0] : parts[p];
+    out[0] = acc;
+}
+
 // ---- restriction of the residual to the next coarser level ------------------------------------------
 // MODE 0: injection (what the reference's mask() read amounts to), scale = 1 or 0.5 on interior
 //         points (half injection); boundary points are copied unscaled.

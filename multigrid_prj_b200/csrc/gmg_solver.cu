@@ -50,6 +50,7 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 using mgb::LevelGeom;
 
 constexpr int kHalo = 44;            // halo rows kept above and below every slab (deepest need: see plan_depths)
+constexpr int kMaxShardedLevel = 4;  // levels 0..4 may be sharded (see last_sharded_level)
 constexpr int kMinSlabRows = 256;    // a level is sharded while every rank keeps at least this many rows;
                                      // smaller levels are replicated (cheaper than a latency-bound exchange per operator)
 
@@ -76,7 +77,9 @@ int last_sharded_level(size_t n, int levels, int n_ranks)
         if ((w - 1) / (size_t)n_ranks >= (size_t)kMinSlabRows) ls = l; else break;
         w = (w + 1) / 2;
     }
-    return ls;
+    // the communication-avoiding schedule recomputes 2^(ls+1) - 1 halo rows of the fine residual for the restriction
+    // cascade: at most 5 sharded levels keep that (and the halo of u it needs) inside the kHalo rows every vector carries
+    return std::min(ls, kMaxShardedLevel);
 }
 
 Part partition(size_t n, int levels, int n_ranks, int rank, int level)
@@ -127,6 +130,13 @@ struct mgb_gmg {
     int stream2_min_rows = 128;       // shortest row chunk the second-generation streaming kernel is used for
     int stream_impl = 2;              // generation of the streaming red-black kernel (gmg_stream2.cuh where instantiated; 1 = gmg_kernels.cuh only)
     mgb_gmg_stats stats{};
+    // MGB_TRACE=1: CUDA events between the phases of the slab iteration (uncaptured runs only), printed by rank 0
+    struct Trace {
+        bool on = false;
+        std::vector<std::pair<const char *, cudaEvent_t>> ev;
+        std::vector<cudaEvent_t> pool;
+        size_t used = 0;
+    } trace;
     // CUDA graphs of `period` driver iterations, keyed by the buffer-pointer state they were captured in
     struct IterGraph {
         std::vector<const double *> key; cudaGraphExec_t exec; int period; uint64_t launches; double bytes; int exchanges; unsigned scal_local;
@@ -169,7 +179,10 @@ View extended(const Level &L, int ext)
 }
 
 // exchange `depth` halo rows of a sharded level vector with the slab neighbours
-int halo_exchange(mgb_gmg *h, int level, double *v, int depth)
+// `norm_local` (optional): this rank's part of a sum rides in the same NCCL group -- every rank sends its part to every
+// other rank (parts[p] receives rank p's) and the caller adds them up in rank order, which replaces a separate all-reduce
+// launch by a few 8-byte messages inside a group that is posted anyway
+int halo_exchange(mgb_gmg *h, int level, double *v, int depth, const double *norm_local = nullptr, double *parts = nullptr)
 {
     Level &L = h->lv[level];
     if (!L.sharded || h->cfg.n_ranks <= 1) return MGB_OK;
@@ -186,6 +199,13 @@ int halo_exchange(mgb_gmg *h, int level, double *v, int depth)
     if (r < n - 1) {
         NK(N.Send(v + (size_t)(L.g.rows - depth) * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st)); // my bottom rows
         NK(N.Recv(v + (size_t)L.g.rows * P, cnt, mgb::kNcclFloat64, r + 1, h->comm, h->st));           // halo below
+    }
+    if (norm_local) {
+        for (int p = 0; p < n; ++p) {
+            if (p == r) continue;
+            NK(N.Send(norm_local, 1, mgb::kNcclFloat64, p, h->comm, h->st));
+            NK(N.Recv(parts + p, 1, mgb::kNcclFloat64, p, h->comm, h->st));
+        }
     }
     NK(N.GroupEnd());
     h->stats.reserved[0]++;           // exchanges
@@ -589,9 +609,12 @@ Depths plan_depths(mgb_gmg *h)
 
 // halo rows of the fine residual the cycle reads, and of u the pre-sweep launch reads to produce them
 int ca_resid_depth(mgb_gmg *, const Depths &d) { return std::max(d.din[0], d.ext_r[0]); }
+// slabs: the fused pre-sweep launch also restricts its residual to level 1 (kernel MODE 3) when level 1 is sharded too
+bool ca_fuse_restrict1(mgb_gmg *h) { return fuse_resid(h) && h->ls >= 1; }
 int ca_u_depth(mgb_gmg *h, const Depths &d)
 {
-    return 2 * h->cfg.n_pre + 1 + (fuse_resid(h) ? ca_resid_depth(h, d) : 0);
+    // MODE 3 forms the residual one row beyond its output rows (the stencil of the restriction): one more row of u
+    return 2 * h->cfg.n_pre + 1 + (fuse_resid(h) ? ca_resid_depth(h, d) : 0) + (ca_fuse_restrict1(h) ? 1 : 0);
 }
 
 bool ca_applicable(mgb_gmg *h)
@@ -605,6 +628,34 @@ bool ca_applicable(mgb_gmg *h)
     int need = std::max(d.ext_r[0], ca_u_depth(h, d));
     for (int l = 0; l <= h->ls; ++l) need = std::max(need, d.din[l]);
     return need + 2 <= kHalo && need <= h->lv[h->ls].g.rows / 2;
+}
+
+void trace_mark(mgb_gmg *h, const char *what)
+{
+    if (!h->trace.on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return;
+    if (h->trace.used == h->trace.pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->trace.pool.push_back(e); }
+    cudaEvent_t e = h->trace.pool[h->trace.used++];
+    cudaEventRecord(e, h->st);
+    h->trace.ev.emplace_back(what, e);
+}
+
+void trace_flush(mgb_gmg *h)
+{
+    if (!h->trace.on || h->trace.ev.size() < 2) { h->trace.ev.clear(); h->trace.used = 0; return; }
+    cudaStreamSynchronize(h->st);
+    if (h->cfg.rank == 0) {
+        std::fprintf(stderr, "[mgb trace]");
+        for (size_t i = 1; i < h->trace.ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->trace.ev[i - 1].second, h->trace.ev[i].second);
+            std::fprintf(stderr, " %s=%.1fus", h->trace.ev[i].first, ms * 1e3);
+        }
+        std::fprintf(stderr, "\n");
+    }
+    h->trace.ev.clear(); h->trace.used = 0;
 }
 
 // fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
@@ -640,10 +691,17 @@ int one_iteration_ca(mgb_gmg *h)
     // which removes the exchange of the residual altogether.
     const int dr = ca_resid_depth(h, d);
     const int ext_u = ca_u_depth(h, d);
+    trace_mark(h, "start");
     if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
     h->u_halo_valid = 0;
+    const bool fuse_r1 = ca_fuse_restrict1(h);
     if (fuse_resid(h)) {
-        if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, dr, nullptr, F.r))) return rc;
+        // the launch covers dr >= 2 ext_r[1] + 1 halo rows of the residual, so the coarse rows it restricts include the
+        // ext_r[1] halo rows of level 1 the cascade below reads (same term order as k_restrict: bit-identical)
+        h->restrict_into = fuse_r1 ? &h->lv[1] : nullptr;
+        rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, dr, nullptr, F.r);
+        h->restrict_into = nullptr;
+        if (rc) return rc;
     } else {
         // (2) unfused: fine residual on the owned rows, then ONE deep exchange of it
         if ((rc = smooth_ca(h, 0, h->cfg.n_pre, &F.u, F.f, F.tu, 1))) return rc;
@@ -653,9 +711,10 @@ int one_iteration_ca(mgb_gmg *h)
         CK(cudaGetLastError());
         if ((rc = halo_exchange(h, 0, F.r, dr))) return rc;
     }
+    trace_mark(h, "pre-sweeps+residual");
     // (3) restriction down the sharded levels, halo rows recomputed; then the first replicated level's slab
     const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
-    for (int l = 1; l <= std::min(ls + 1, h->lt); ++l) {
+    for (int l = fuse_r1 ? 2 : 1; l <= std::min(ls + 1, h->lt); ++l) {
         Level &Fl = h->lv[l - 1], &C = h->lv[l];
         LevelGeom gc;
         double *out;
@@ -675,6 +734,7 @@ int one_iteration_ca(mgb_gmg *h)
         count(h, fw ? 8. * npts(Fl.g) + 8. * npts(gc) : 16. * npts(gc));
         CK(cudaGetLastError());
     }
+    trace_mark(h, "restrict-sharded");
     // one NCCL group: halo rows of every restricted residual (the smoothers' rhs) + gather of the replicated slab rows
     {
         const int r = h->cfg.rank, n = h->cfg.n_ranks;
@@ -712,6 +772,7 @@ int one_iteration_ca(mgb_gmg *h)
         NK(N.GroupEnd());
         h->stats.reserved[0]++;
     }
+    trace_mark(h, "exchange-r+gather");
     // (4) replicated levels down to the tail, the tail itself, and back up to the first replicated level
     for (int l = ls + 2; l <= h->lt; ++l) {
         Level &Fl = h->lv[l - 1], &C = h->lv[l];
@@ -730,12 +791,15 @@ int one_iteration_ca(mgb_gmg *h)
         if ((rc = do_prolong(h, j))) return rc;
         if ((rc = do_smooth(h, j - 1, MGB_SMOOTH_GS_RB, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r))) return rc;
     }
+    trace_mark(h, "replicated-part");
     // (5) upward through the sharded levels without any exchange
     for (int j = ls + 1; j > 0; --j) {
         Level &C = h->lv[j], &Fl = h->lv[j - 1];
         double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
         if (fuse_prolong(h)) {
             if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc, nullptr, &C))) return rc;
+            static const char *const names[] = {"up-L0", "up-L1", "up-L2", "up-L3", "up-L4", "up-L5", "up-L6", "up-L7"};
+            if (j - 1 < 8) trace_mark(h, names[j - 1]);
             continue;
         }
         const View vf = extended(Fl, d.din[j - 1]);
@@ -745,14 +809,34 @@ int one_iteration_ca(mgb_gmg *h)
         CK(cudaGetLastError());
         if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc))) return rc;
     }
+    trace_mark(h, "upward-sharded");
     if (fuse_corr(h)) {
         h->u_halo_valid = 0;
         h->stats.cycles++;
-        if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;          // for the next iteration's pre-sweeps
-        h->u_halo_valid = ext_u;
         const int np = h->norm_partials;
         h->norm_partials = 0;
-        return reduce_partials(h, np, 1, true, h->cfg.defer_norm != 0);
+        if (h->cfg.defer_norm) {
+            if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;      // for the next iteration's pre-sweeps
+            h->u_halo_valid = ext_u;
+            trace_mark(h, "exchange-u");
+            rc = reduce_partials(h, np, 1, true, true);
+        } else {
+            // the norm of every iteration, summed over the ranks (main.cpp:86-90 reads it every iteration): this rank's part
+            // travels inside the exchange of u, the parts are added in rank order (the same bits on every rank)
+            double *local = h->d_scal + 15, *parts = h->d_scal + 16;
+            mgb::k_reduce_partials<<<1, 1024, 0, h->st>>>(h->d_partial, np, local);
+            count(h, 0.);
+            if ((rc = halo_exchange(h, 0, F.u, ext_u, local, parts))) return rc;
+            h->u_halo_valid = ext_u;
+            trace_mark(h, "exchange-u+norm");
+            mgb::k_sum_ranks<<<1, 32, 0, h->st>>>(parts, local, h->cfg.n_ranks, h->cfg.rank, h->d_scal + 1);
+            count(h, 0.);
+            CK(cudaGetLastError());
+            h->scal_local &= ~(1u << 1);
+        }
+        trace_mark(h, "norm");
+        trace_flush(h);
+        return rc;
     }
     if ((rc = finish_cycle(h))) return rc;
     // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
@@ -1031,7 +1115,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     // not boundary nodes and neighbour indices run out of range
     if ((N - 1) % ((size_t)1 << (L - 1)) != 0 || ((N - 1) >> (L - 1)) < 1)
         return fail(MGB_ERR_ARG, "(n-1) must be divisible by 2^(levels-1)");
-    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail(MGB_ERR_ARG, "bad rank / n_ranks");
+    if (cfg->n_ranks < 1 || cfg->n_ranks > 64 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail(MGB_ERR_ARG, "bad rank / n_ranks");
     const int ls = last_sharded_level(N, L, cfg->n_ranks);
     if (cfg->n_ranks > 1 && ls < 0)
         return fail(MGB_ERR_ARG, "grid too small to be cut into row slabs for this many ranks");
@@ -1048,6 +1132,7 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     h->ls = ls;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    if (const char *e = std::getenv("MGB_TRACE")) h->trace.on = std::atoi(e) != 0;
     if (const char *e = std::getenv("MGB_STREAM_IMPL")) h->stream_impl = (std::atoi(e) == 1) ? 1 : 2;
     if (const char *e = std::getenv("MGB_STREAM2_MIN_ROWS")) h->stream2_min_rows = std::max(0, std::atoi(e));
     if (cfg->n_ranks > 1) {
@@ -1097,8 +1182,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     }
     h->n_partial = std::max<size_t>(max_partial, 1 << 16);
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));
-    CK(cudaMalloc(&h->d_scal, 16 * sizeof(double)));
-    CK(cudaMemsetAsync(h->d_scal, 0, 16 * sizeof(double), h->st));
+    CK(cudaMalloc(&h->d_scal, 80 * sizeof(double)));      // 16 scalars + one part per rank of a sum that rides in an exchange
+    CK(cudaMemsetAsync(h->d_scal, 0, 80 * sizeof(double), h->st));
     CK(cudaMallocHost(&h->h_scal, 16 * sizeof(double)));
     CK(cudaStreamSynchronize(h->st));
     guard.h = nullptr;
