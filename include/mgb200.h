@@ -94,7 +94,20 @@ typedef struct mgb_gmg_config {
                              omega = 1 (solvers.hpp:64-83) and that value keeps the bit-identical path; other values
                              (north_star: weighted Jacobi) run level by level without the persistent tail kernel.
                              <= 0 is read as 1 */
+    /* --- textbook cycle options (NOT in the reference, whose only cycle is the sawtooth) --- */
+    int cycle_type;       /* MGB_CYCLE_*: 0 = the reference's sawtooth (multigrid.hpp:126-145); V / W / F = correction-scheme cycles
+                             with nu_pre pre-sweeps, the residual of the level's own equation restricted to the next level,
+                             prolongation ADDED to the level's iterate and nu post-sweeps.  Levels inside the persistent coarse
+                             tail (tail_max_width) are the coarse solver of these cycles: one sawtooth pass of that kernel */
+    int nu_pre;           /* pre-sweeps per level of a V / W / F cycle (nu is the number of post-sweeps) */
+    int fmg;              /* 1: mgb_gmg_solve starts with one full-multigrid pass (mgb_gmg_fmg) */
+    int reserved_cycle;
 } mgb_gmg_config;
+
+enum { MGB_CYCLE_SAWTOOTH = 0, MGB_CYCLE_V = 1, MGB_CYCLE_W = 2, MGB_CYCLE_F = 3 };
+/* Krylov methods of mgb_gmg_krylov and their preconditioners */
+enum { MGB_KRYLOV_CG = 0, MGB_KRYLOV_BICGSTAB = 1 };
+enum { MGB_PRECOND_NONE = 0, MGB_PRECOND_MG = 1 };
 
 typedef struct mgb_gmg *mgb_gmg_t;
 
@@ -145,6 +158,9 @@ int mgb_gmg_prolong(mgb_gmg_t h, int level_coarse);
  * handle keeps one hierarchy and switches the cycle's parameters instead */
 int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double coarse_tol, int coarse_maxit);
 
+/* switches the cycle shape of a live handle (mgb_gmg_config.cycle_type / nu_pre / fmg) */
+int mgb_gmg_set_cycle_type(mgb_gmg_t h, int cycle_type, int nu_pre, int fmg);
+
 /* switches mgb_gmg_config.defer_norm of a live handle (measurement: the same handle timed both ways) */
 int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer);
 
@@ -163,6 +179,21 @@ int mgb_gmg_cycle(mgb_gmg_t h, double *coarse_relres, int *coarse_iters);
  * hist must hold maxiter+1 doubles. check_every: read the norm back (one double, one sync) every
  * k-th cycle only (1 = the reference's behaviour). */
 int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double *hist, int *n_hist);
+/* One full-multigrid pass on the residual equation (nested iteration): r = f - A u restricted to
+ * every level, coarse solve, then per level upward: bilinear prolongation of the coarser correction as the initial guess
+ * and one V(nu_pre, nu) cycle of that level's equation; finally u += e.  No extra storage: the V cycle of level l only
+ * overwrites arrays of levels > l, which the pass has already left behind. */
+int mgb_gmg_fmg(mgb_gmg_t h);
+
+/* A real Krylov solver on the fine level, replacing the reference's never-executed BiCGSTAB (solvers.hpp:86-216; SURVEY.md
+ * section 8 row a11 and 8f item 4): conjugate gradients or BiCGSTAB on A u = f, optionally right-preconditioned by ONE
+ * multigrid cycle of the handle's configuration applied to the residual (zero initial guess).  The boundary rows of A are
+ * identity rows: u is first set to f there, after which every residual and search direction vanishes on the boundary and
+ * A acts as the symmetric interior operator.  CG needs a symmetric preconditioner: use MGB_SMOOTH_JACOBI cycles with full
+ * weighting (or MGB_PRECOND_NONE); BiCGSTAB takes any cycle (red-black GS, sawtooth ...).
+ * hist[0] = ||f - A u|| / ||f|| on entry, then one entry per iteration (maxit + 1 doubles); stops at hist <= tol. */
+int mgb_gmg_krylov(mgb_gmg_t h, int method, int precond, double tol, int maxit, double *hist, int *n_hist);
+
 /* runs exactly `cycles` driver iterations without any host readback; writes the final relative
  * residual.  This is the timed region of bench.py. */
 int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres);

@@ -21,7 +21,8 @@ class GmgConfigStruct(C.Structure):
                 ("rank", C.c_int), ("n_ranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
                 ("tail_max_width", C.c_int), ("use_graph", C.c_int), ("rb_fast_arith", C.c_int),
                 ("rb_fused", C.c_int), ("fuse_correction", C.c_int), ("fuse_residual", C.c_int), ("fuse_prolong", C.c_int), ("defer_norm", C.c_int),
-                ("jacobi_omega", C.c_double)]
+                ("jacobi_omega", C.c_double),
+                ("cycle_type", C.c_int), ("nu_pre", C.c_int), ("fmg", C.c_int), ("reserved_cycle", C.c_int)]
 
 
 class GmgStatsStruct(C.Structure):
@@ -63,6 +64,9 @@ SYMBOLS = {
     "mgb_gmg_restrict": (_i, [_vp]),
     "mgb_gmg_prolong": (_i, [_vp, _i]),
     "mgb_gmg_set_cycle": (_i, [_vp, _i, _i, _i, _d, _i]),
+    "mgb_gmg_set_cycle_type": (_i, [_vp, _i, _i, _i]),
+    "mgb_gmg_fmg": (_i, [_vp]),
+    "mgb_gmg_krylov": (_i, [_vp, _i, _i, _d, _i, _vp, _pi]),
     "mgb_gmg_set_defer_norm": (_i, [_vp, _i]),
     "mgb_gmg_set_stream_impl": (_i, [_vp, _i]),
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),

@@ -221,6 +221,8 @@ k_restrict(LevelGeom gf, LevelGeom gc, const double *__restrict__ rf, double *__
 // even row, even col: copy; odd row, even col: 0.5*(N+S); even row, odd col: 0.5*(W+E) of the
 // copied values; odd row, odd col: 0.5*(vm_W + vm_E) with vm = the vertical midpoints -- the same
 // two-stage order as the reference's in-place loops, hence bit-identical.
+// ADD: ef += P ec instead (the coarse-grid correction of the textbook cycles; not in the reference).
+template <bool ADD>
 __global__ void __launch_bounds__(kTPB)
 k_prolong(LevelGeom gc, LevelGeom gf, const double *__restrict__ ec, double *__restrict__ ef)
 {
@@ -243,8 +245,14 @@ k_prolong(LevelGeom gc, LevelGeom gf, const double *__restrict__ ec, double *__r
             c = has1 ? __dmul_rn(0.5, __dadd_rn(cn[1], cs[1])) : 0.;
         }
         double *o = ef + (size_t)i * gf.pitch + j0;
-        if (has1) st2(o, make_double2(a, __dmul_rn(0.5, __dadd_rn(a, c))));
-        else o[0] = a;
+        const double m = has1 ? __dmul_rn(0.5, __dadd_rn(a, c)) : 0.;
+        if (ADD) {
+            if (has1) { const double2 old = ld2(o); st2(o, make_double2(__dadd_rn(old.x, a), __dadd_rn(old.y, m))); }
+            else o[0] = __dadd_rn(o[0], a);
+        } else {
+            if (has1) st2(o, make_double2(a, m));
+            else o[0] = a;
+        }
     }
 }
 

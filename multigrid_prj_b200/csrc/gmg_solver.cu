@@ -17,6 +17,7 @@
 // needs ONE exchange of k... 2k rows instead of one per colour pass.  Norms: ncclAllReduce of one fp64.
 #include "../../include/mgb200.h"
 #include "gmg_kernels.cuh"
+#include "gmg_krylov.cuh"
 #include "gmg_stream2.h"
 #include "gmg_tail.cuh"
 #include "nccl_dyn.h"
@@ -128,6 +129,8 @@ struct mgb_gmg {
     bool have_rhs = false;
     int n_sm = 148;
     int stream2_min_rows = 128;       // shortest row chunk the second-generation streaming kernel is used for
+    bool no_fused_correction = false; // set while the cycle serves as a preconditioner (its output is e, not u += e)
+    double *kry[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fine-level work vectors of mgb_gmg_krylov (allocated on first use)
     int stream_impl = 2;              // generation of the streaming red-black kernel (gmg_stream2.cuh where instantiated; 1 = gmg_kernels.cuh only)
     mgb_gmg_stats stats{};
     // MGB_TRACE=1: CUDA events between the phases of the slab iteration (uncaptured runs only), printed by rank 0
@@ -517,13 +520,14 @@ int do_restrict(mgb_gmg *h)
     return MGB_OK;
 }
 
-int do_prolong(mgb_gmg *h, int lc)
+int do_prolong(mgb_gmg *h, int lc, bool add = false)
 {
     Level &C = h->lv[lc], &F = h->lv[lc - 1];
     if (int rc = halo_exchange(h, lc, C.e, 1)) return rc;
     dim3 grid((F.g.w + 2 * mgb::kTPB - 1) / (2 * mgb::kTPB), (F.g.rows + 3) / 4);
-    mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, F.g, C.e, F.e);
-    count(h, 8. * (npts(F.g) + npts(C.g)));
+    if (add) mgb::k_prolong<true><<<grid, mgb::kTPB, 0, h->st>>>(C.g, F.g, C.e, F.e);
+    else mgb::k_prolong<false><<<grid, mgb::kTPB, 0, h->st>>>(C.g, F.g, C.e, F.e);
+    count(h, 8. * (npts(F.g) + npts(C.g)) + (add ? 8. * npts(F.g) : 0.));
     CK(cudaGetLastError());
     return MGB_OK;
 }
@@ -587,8 +591,11 @@ bool fuse_resid(mgb_gmg *h)
 }
 
 // the correction u += e and the new iterate's residual norm ride on the last fine post-smoothing launch
+bool textbook(mgb_gmg *h) { return h->cfg.cycle_type != MGB_CYCLE_SAWTOOTH; }
+
 bool fuse_corr(mgb_gmg *h)
 {
+    if (textbook(h) || h->no_fused_correction) return false;
     return h->cfg.fuse_correction && h->cfg.smoother == MGB_SMOOTH_GS_RB && h->cfg.rb_fused && h->cfg.nu > 0 &&
            h->lv.size() > 1 && h->lt != 0;
 }
@@ -619,6 +626,7 @@ int ca_u_depth(mgb_gmg *h, const Depths &d)
 
 bool ca_applicable(mgb_gmg *h)
 {
+    if (textbook(h)) return false;                       // the V / W / F cycles run operator by operator
     if (h->cfg.n_ranks <= 1 || !h->cfg.rb_fused || h->cfg.smoother != MGB_SMOOTH_GS_RB || h->cfg.pre_smoother != MGB_SMOOTH_GS_RB)
         return false;
     if (h->cfg.restriction != MGB_RESTRICT_FULL_WEIGHTING && h->cfg.restriction != MGB_RESTRICT_HALF_INJECTION &&
@@ -804,7 +812,7 @@ int one_iteration_ca(mgb_gmg *h)
         }
         const View vf = extended(Fl, d.din[j - 1]);
         dim3 grid((vf.g.w + 2 * mgb::kTPB - 1) / (2 * mgb::kTPB), (vf.g.rows + 3) / 4);
-        mgb::k_prolong<<<grid, mgb::kTPB, 0, h->st>>>(C.g, vf.g, C.e, Fl.e + vf.off);
+        mgb::k_prolong<false><<<grid, mgb::kTPB, 0, h->st>>>(C.g, vf.g, C.e, Fl.e + vf.off);
         count(h, 8. * (npts(vf.g) + npts(C.g)));
         CK(cudaGetLastError());
         if ((rc = smooth_ca(h, j - 1, h->cfg.nu, &Fl.e, Fl.r, Fl.t, d.dout[j - 1], uc))) return rc;
@@ -850,44 +858,13 @@ int one_iteration_ca(mgb_gmg *h)
     return reduce_partials(h, grid.x * grid.y, 1, true);
 }
 
-// multigrid.hpp:126-145
-int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
+// the coarse "solve" of multigrid.hpp:128-131 driven from the host (no persistent tail): Solver::Solve, solvers.hpp:324-342
+int host_coarse_solve(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
 {
     const int L = (int)h->lv.size();
-    Level &F = h->lv[0], &C = h->lv[L - 1];
+    Level &C = h->lv[L - 1];
     const int kind = h->cfg.smoother;
     int rc;
-    h->norm_partials = 0;
-    // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
-    const bool skip_first_restriction = h->r0_ready && h->r1_ready;
-    if (h->r0_ready) h->r0_ready = false;
-    else if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
-    h->r1_ready = false;
-    h->skip_restrict_l1 = skip_first_restriction;
-    if ((rc = do_restrict(h))) return rc;
-    if (h->lt >= 0) {
-        // restriction below lt, coarse solve and the upward leg up to level lt: one persistent CTA
-        if ((rc = launch_tail(h))) return rc;
-        if (coarse_relres || coarse_iters) {
-            double rel = 0., its = 0.;
-            if ((rc = read_scalar(h, 4, &rel))) return rc;
-            if ((rc = read_scalar(h, 5, &its))) return rc;
-            if (coarse_relres) *coarse_relres = rel;
-            if (coarse_iters) *coarse_iters = (int)its;
-            h->stats.coarse_iters_total += (uint64_t)its;
-        }
-        for (int j = h->lt; j > 0; --j) {
-            double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
-            if (fuse_prolong(h)) {
-                if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc, nullptr, &h->lv[j]))) return rc;
-                continue;
-            }
-            if ((rc = do_prolong(h, j))) return rc;
-            if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
-        }
-        if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
-        return finish_cycle(h);
-    }
     // :128 COARSE_RES->refresh_normalization_constant()
     if ((rc = do_sumsq(h, L - 1, C.r, 2))) return rc;
     double nb = 0., norm = 0.;
@@ -906,9 +883,36 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
     if (coarse_relres) *coarse_relres = std::sqrt(norm / nb);       // :131 (the printed value)
     if (coarse_iters) *coarse_iters = its;
     h->stats.coarse_iters_total += its;
+    return MGB_OK;
+}
+
+// multigrid.hpp:128-139: everything between the fine residual (already in r of level 0) and the correction: restriction
+// to every level, coarse solve, upward leg.  Leaves the correction in e of level 0 -- or, with `fused`, already added to u
+// by the last fine launch (then norm_partials > 0).
+int sawtooth_core(mgb_gmg *h, double *coarse_relres, int *coarse_iters, bool fused)
+{
+    const int L = (int)h->lv.size();
+    Level &F = h->lv[0];
+    const int kind = h->cfg.smoother;
+    int rc;
+    if ((rc = do_restrict(h))) return rc;
+    int top = L - 1;
+    if (h->lt >= 0) {
+        // restriction below lt, coarse solve and the upward leg up to level lt: one persistent CTA
+        if ((rc = launch_tail(h))) return rc;
+        if (coarse_relres || coarse_iters) {
+            double rel = 0., its = 0.;
+            if ((rc = read_scalar(h, 4, &rel))) return rc;
+            if ((rc = read_scalar(h, 5, &its))) return rc;
+            if (coarse_relres) *coarse_relres = rel;
+            if (coarse_iters) *coarse_iters = (int)its;
+            h->stats.coarse_iters_total += (uint64_t)its;
+        }
+        top = h->lt;
+    } else if ((rc = host_coarse_solve(h, coarse_relres, coarse_iters))) return rc;
     // :134-139
-    for (int j = L - 1; j > 0; --j) {
-        double *uc = (j == 1 && fuse_corr(h)) ? F.u : nullptr;
+    for (int j = top; j > 0; --j) {
+        double *uc = (j == 1 && fused) ? F.u : nullptr;
         if (fuse_prolong(h)) {
             if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc, nullptr, &h->lv[j]))) return rc;
             continue;
@@ -916,7 +920,111 @@ int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
         if ((rc = do_prolong(h, j))) return rc;
         if ((rc = do_smooth(h, j - 1, kind, h->cfg.nu, &h->lv[j - 1].e, h->lv[j - 1].r, uc))) return rc;
     }
+    return MGB_OK;
+}
+
+// ---- textbook cycles (the reference only has the sawtooth) ---------------------------------
+// restriction of `src`, a vector of level l-1, into r of level l (the right-hand side of that level's equation)
+int restrict_one(mgb_gmg *h, int l, double *src)
+{
+    Level &F = h->lv[l - 1], &C = h->lv[l];
+    int rc;
+    const bool fw = h->cfg.restriction == MGB_RESTRICT_FULL_WEIGHTING;
+    if (fw && (rc = halo_exchange(h, l - 1, src, 1))) return rc;
+    LevelGeom gc = C.g;
+    double *rc_ptr = C.r;
+    if (F.sharded && !C.sharded) {             // this rank produces the coarse rows whose coincident fine row it owns
+        gc.row0 = (F.g.row0 + 1) / 2;
+        gc.rows = (F.g.row0 + F.g.rows - 1) / 2 - gc.row0 + 1;
+        rc_ptr = C.r + (size_t)gc.row0 * gc.pitch;
+    }
+    dim3 grid((gc.w + 255) / 256, gc.rows);
+    if (fw) {
+        mgb::k_restrict<2><<<grid, 256, 0, h->st>>>(F.g, gc, src, rc_ptr, 1.0);
+        count(h, 8. * npts(F.g) + 8. * npts(gc));
+    } else {
+        // half injection: the residual a red-black sweep leaves is zero on one colour and doubled on the other ON EVERY LEVEL
+        const double scale = h->cfg.restriction == MGB_RESTRICT_HALF_INJECTION ? 0.5 : 1.0;
+        mgb::k_restrict<0><<<grid, 256, 0, h->st>>>(F.g, gc, src, rc_ptr, scale);
+        count(h, 16. * npts(gc));
+    }
+    CK(cudaGetLastError());
+    if (F.sharded && !C.sharded) return allgather_rows(h, l, C.r);
+    return halo_exchange(h, l, C.r, kHalo);
+}
+
+// One correction-scheme cycle for A_l e_l = r_l (e and r of level l), improving the current e_l (`zero`: e_l = 0 on entry):
+//   nu_pre sweeps; d = r_l - A_l e_l; r_{l+1} = R d; cycle(s) on level l+1 from zero; e_l += P e_{l+1}; nu sweeps.
+// V visits the next level once, W twice (the second visit improves the first one's e_{l+1}), F = an F cycle followed by a
+// V cycle.  The levels of the persistent tail are the coarse solver: one launch = one sawtooth pass from r of its first level.
+int mu_cycle(mgb_gmg *h, int l, int type, bool zero)
+{
+    const int L = (int)h->lv.size();
+    const int bottom = h->lt >= 0 ? h->lt : L - 1;
+    Level &X = h->lv[l];
+    int rc;
+    if (l >= bottom) return h->lt >= 0 ? launch_tail(h) : host_coarse_solve(h, nullptr, nullptr);
+    const int kind = h->cfg.smoother;
+    if (zero) CK(cudaMemsetAsync(X.e - (size_t)kHalo * X.g.pitch, 0, X.elems * sizeof(double), h->st));
+    if (h->cfg.nu_pre > 0 && (rc = do_smooth(h, l, kind, h->cfg.nu_pre, &X.e, X.r))) return rc;
+    if ((rc = do_residual(h, l, X.e, X.r, X.t, 6))) return rc;          // X.t: the ping-pong partner of e is free between sweeps
+    if ((rc = restrict_one(h, l + 1, X.t))) return rc;
+    if (type == MGB_CYCLE_F) {
+        if ((rc = mu_cycle(h, l + 1, MGB_CYCLE_F, true))) return rc;
+        if (l + 1 < bottom && (rc = mu_cycle(h, l + 1, MGB_CYCLE_V, false))) return rc;
+    } else {
+        const int visits = (type == MGB_CYCLE_W && l + 1 < bottom) ? 2 : 1;
+        for (int v = 0; v < visits; ++v)
+            if ((rc = mu_cycle(h, l + 1, type, v == 0))) return rc;
+    }
+    if ((rc = do_prolong(h, l + 1, true))) return rc;
+    return do_smooth(h, l, kind, h->cfg.nu, &X.e, X.r);
+}
+
+// the configured cycle as an operator on the fine residual: e (level 0) ~= A^-1 r (level 0), r is left untouched
+int cycle_core(mgb_gmg *h, double *coarse_relres, int *coarse_iters, bool fused)
+{
+    if (textbook(h)) return mu_cycle(h, 0, h->cfg.cycle_type, true);
+    return sawtooth_core(h, coarse_relres, coarse_iters, fused);
+}
+
+// multigrid.hpp:126-145
+int do_cycle(mgb_gmg *h, double *coarse_relres, int *coarse_iters)
+{
+    Level &F = h->lv[0];
+    int rc;
+    h->norm_partials = 0;
+    // :127 sol * RES  -> r0 = f - A u on the fine grid (the norm of this residual is never read)
+    const bool skip_first_restriction = h->r0_ready && h->r1_ready && !textbook(h);
+    if (h->r0_ready) h->r0_ready = false;
+    else if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
+    h->r1_ready = false;
+    h->skip_restrict_l1 = skip_first_restriction;
+    if ((rc = cycle_core(h, coarse_relres, coarse_iters, fuse_corr(h)))) return rc;
     if (fuse_corr(h)) { h->u_halo_valid = 0; h->stats.cycles++; return MGB_OK; }
+    return finish_cycle(h);
+}
+
+// One full-multigrid pass on the residual equation A e = f - A u (nested iteration): the residual is restricted to every
+// level, the coarsest levels are solved, and on the way up the prolonged coarser correction is the initial guess of one
+// V(nu_pre, nu) cycle of each level's own equation.  The V cycle of level l overwrites only e, r of the levels below it,
+// which the pass has already left behind, so no storage beyond the cycle's is needed.
+int do_fmg(mgb_gmg *h)
+{
+    const int L = (int)h->lv.size();
+    const int bottom = h->lt >= 0 ? h->lt : L - 1;
+    Level &F = h->lv[0];
+    int rc;
+    h->norm_partials = 0;
+    h->r0_ready = h->r1_ready = false;
+    h->skip_restrict_l1 = false;
+    if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;
+    if ((rc = do_restrict(h))) return rc;
+    if ((rc = (h->lt >= 0 ? launch_tail(h) : host_coarse_solve(h, nullptr, nullptr)))) return rc;
+    for (int l = bottom - 1; l >= 0; --l) {
+        if ((rc = do_prolong(h, l + 1))) return rc;                    // e_l = P e_{l+1} (multigrid.cpp:3-27)
+        if ((rc = mu_cycle(h, l, MGB_CYCLE_V, false))) return rc;
+    }
     return finish_cycle(h);
 }
 
@@ -941,7 +1049,7 @@ int one_iteration(mgb_gmg *h)
     Level &F = h->lv[0];
     int rc;
     if (fuse_resid(h)) {
-        const bool with_restriction = h->cfg.n_ranks == 1 && h->lv.size() > 1;
+        const bool with_restriction = h->cfg.n_ranks == 1 && h->lv.size() > 1 && !textbook(h);
         h->restrict_into = with_restriction ? &h->lv[1] : nullptr;
         rc = do_smooth(h, 0, h->cfg.pre_smoother, h->cfg.n_pre, &F.u, F.f, nullptr, F.r);
         h->restrict_into = nullptr;
@@ -963,7 +1071,7 @@ std::vector<const double *> pointer_state(mgb_gmg *h)
     std::vector<const double *> k;
     for (auto &lv : h->lv) { k.push_back(lv.u); k.push_back(lv.tu); k.push_back(lv.e); k.push_back(lv.t); k.push_back(lv.r); }
     k.push_back((const double *)(uintptr_t)((h->cfg.smoother << 8) | (h->cfg.pre_smoother << 4) | h->cfg.restriction));
-    k.push_back((const double *)(uintptr_t)((h->stream_impl << 16) | (h->cfg.nu << 8) | h->cfg.n_pre));
+    k.push_back((const double *)(uintptr_t)(((uintptr_t)h->cfg.cycle_type << 32) | ((uintptr_t)h->cfg.nu_pre << 24) | (h->stream_impl << 16) | (h->cfg.nu << 8) | h->cfg.n_pre));
     // everything else the captured launches depend on: whether the leading exchange of u is skipped
     // (one_iteration_ca), the coarse-solve parameters baked into TailParams, the norm's all-reduce placement
     const bool halo_ok = ca_applicable(h) && h->u_halo_valid >= ca_u_depth(h, plan_depths(h));
@@ -1036,6 +1144,183 @@ int run_iterations(mgb_gmg *h, int cycles)
         if ((rc = one_iteration(h))) return rc;
         --cycles;
     }
+    return MGB_OK;
+}
+
+// ---- Krylov solvers on the fine level (mgb_gmg_krylov) ------------------------------------------------------------------
+// Device scalars of an iteration live in d_scal[kKs ...]; the host reads back only the residual norm (slot 1).
+constexpr int kKs = 80;
+enum { KS_RHO = kKs, KS_DEN, KS_RHO_NEW, KS_TS, KS_TT, KS_ALPHA, KS_OMEGA, KS_BETA };
+
+__global__ void k_scal_div(double *s, int dst, int a, int b) { if (threadIdx.x == 0) s[dst] = s[a] / s[b]; }
+// BiCGSTAB: beta = (rho_new / rho) * (alpha / omega)
+__global__ void k_scal_beta(double *s, int dst, int rho_new, int rho, int alpha, int omega)
+{
+    if (threadIdx.x == 0) s[dst] = (s[rho_new] / s[rho]) * (s[alpha] / s[omega]);
+}
+
+// second stage of a dot product into d_scal[slot], summed over the ranks of a sharded fine level
+int reduce_to(mgb_gmg *h, int n, int slot)
+{
+    mgb::k_reduce_partials<<<1, 1024, 0, h->st>>>(h->d_partial, n, h->d_scal + slot);
+    count(h, 0.);
+    CK(cudaGetLastError());
+    if (h->lv[0].sharded && h->cfg.n_ranks > 1)
+        NK(mgb::nccl().AllReduce(h->d_scal + slot, h->d_scal + slot, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+    return MGB_OK;
+}
+
+int kry_dot(mgb_gmg *h, const double *a, const double *b, int slot)
+{
+    const LevelGeom &g = h->lv[0].g;
+    dim3 grid = march_grid(g);
+    mgb::k_dot<<<grid, mgb::kTPB, 0, h->st>>>(g, a, b, h->d_partial);
+    count(h, 16. * npts(g));
+    return reduce_to(h, grid.x * grid.y, slot);
+}
+
+// q = A p and p.q -> d_scal[slot]
+int kry_apply(mgb_gmg *h, double *p, double *q, int slot)
+{
+    const LevelGeom &g = h->lv[0].g;
+    int rc;
+    if ((rc = halo_exchange(h, 0, p, 1))) return rc;
+    dim3 grid = march_grid(g);
+    mgb::k_apply_dot<<<grid, mgb::kTPB, 0, h->st>>>(g, p, q, h->d_partial);
+    count(h, 16. * npts(g));
+    return reduce_to(h, grid.x * grid.y, slot);
+}
+
+// y += ca x (+ cb z); sum y^2 -> d_scal[slot] when slot >= 0
+int kry_axpy(mgb_gmg *h, double *y, const double *x, mgb::Coef ca, const double *z, mgb::Coef cb, int slot)
+{
+    const LevelGeom &g = h->lv[0].g;
+    dim3 grid = march_grid(g);
+    mgb::k_axpy_dot<<<grid, mgb::kTPB, 0, h->st>>>(g, h->d_scal, y, x, ca, z, cb, slot >= 0 ? h->d_partial : nullptr);
+    count(h, (z ? 32. : 24.) * npts(g));
+    CK(cudaGetLastError());
+    return slot >= 0 ? reduce_to(h, grid.x * grid.y, slot) : MGB_OK;
+}
+
+// out = x + ca (y + cb z); sum out^2 -> d_scal[slot] when slot >= 0
+int kry_xpay(mgb_gmg *h, double *out, const double *x, const double *y, mgb::Coef ca, const double *z, mgb::Coef cb, int slot)
+{
+    const LevelGeom &g = h->lv[0].g;
+    dim3 grid = march_grid(g);
+    mgb::k_xpay<<<grid, mgb::kTPB, 0, h->st>>>(g, h->d_scal, out, x, y, ca, z, cb, slot >= 0 ? h->d_partial : nullptr);
+    count(h, (z ? 32. : 24.) * npts(g));
+    CK(cudaGetLastError());
+    return slot >= 0 ? reduce_to(h, grid.x * grid.y, slot) : MGB_OK;
+}
+
+// z = M src: one cycle of the handle's configuration on the right-hand side `src` (zero initial guess); the result is e of
+// level 0.  `src` takes the place of r of level 0 for the duration of the cycle (the cycle never writes its fine rhs).
+int kry_precond(mgb_gmg *h, int precond, double *&src, double **z)
+{
+    Level &F = h->lv[0];
+    if (precond == MGB_PRECOND_NONE) { *z = src; return MGB_OK; }
+    int rc;
+    std::swap(F.r, src);
+    h->norm_partials = 0;
+    h->r0_ready = h->r1_ready = false;
+    h->skip_restrict_l1 = false;
+    h->no_fused_correction = true;
+    if (h->lv.size() == 1) {               // a single level: the "cycle" is the coarse solve itself
+        rc = host_coarse_solve(h, nullptr, nullptr);
+    } else rc = cycle_core(h, nullptr, nullptr, false);
+    h->no_fused_correction = false;
+    std::swap(F.r, src);
+    *z = F.e;
+    return rc;
+}
+
+int kry_alloc(mgb_gmg *h, int n)
+{
+    Level &F = h->lv[0];
+    for (int i = 0; i < n; ++i) {
+        if (h->kry[i]) continue;
+        CK(cudaMalloc(&h->kry[i], F.elems * sizeof(double)));
+        CK(cudaMemsetAsync(h->kry[i], 0, F.elems * sizeof(double), h->st));
+    }
+    return MGB_OK;
+}
+
+int do_krylov(mgb_gmg *h, int method, int precond, double tol, int maxit, double *hist, int *n_hist)
+{
+    Level &F = h->lv[0];
+    const LevelGeom &g = F.g;
+    const size_t off = (size_t)kHalo * g.pitch;
+    const size_t bytes = F.elems * sizeof(double);
+    int rc, n = 0;
+    double ss = 0.;
+    if ((rc = kry_alloc(h, method == MGB_KRYLOV_CG ? 2 : 5))) return rc;
+    h->u_halo_valid = 0;
+    // the identity rows: u = f on the boundary, so that every residual below vanishes there
+    mgb::k_set_boundary<<<(std::max(g.w, g.rows) + 255) / 256, 256, 0, h->st>>>(g, F.u, F.f);
+    count(h, 0.);
+    if ((rc = do_residual(h, 0, F.u, F.f, F.r, 1))) return rc;          // r = f - A u
+    if ((rc = read_scalar(h, 1, &ss))) return rc;
+    hist[n++] = std::sqrt(ss / h->norm_f);
+    if (hist[0] <= tol || maxit == 0) { *n_hist = n; return MGB_OK; }
+    const mgb::Coef none{0, -1, 0.};
+    if (method == MGB_KRYLOV_CG) {
+        double *p = h->kry[0] + off, *q = h->kry[1] + off, *z = nullptr;
+        if ((rc = kry_precond(h, precond, F.r, &z))) return rc;
+        if ((rc = kry_dot(h, F.r, z, KS_RHO))) return rc;
+        CK(cudaMemcpyAsync(p - off, z - off, bytes, cudaMemcpyDeviceToDevice, h->st));
+        for (int it = 0; it < maxit; ++it) {
+            if ((rc = kry_apply(h, p, q, KS_DEN))) return rc;                                       // q = A p, p.q
+            if ((rc = kry_axpy(h, F.u, p, mgb::Coef{KS_RHO, KS_DEN, 1.}, nullptr, none, -1))) return rc;   // u += alpha p
+            if ((rc = kry_axpy(h, F.r, q, mgb::Coef{KS_RHO, KS_DEN, -1.}, nullptr, none, 1))) return rc;   // r -= alpha q, |r|^2
+            if ((rc = read_scalar(h, 1, &ss))) return rc;
+            hist[n++] = std::sqrt(ss / h->norm_f);
+            if (hist[n - 1] <= tol) break;
+            if ((rc = kry_precond(h, precond, F.r, &z))) return rc;
+            if ((rc = kry_dot(h, F.r, z, KS_RHO_NEW))) return rc;
+            if ((rc = kry_xpay(h, p, z, p, mgb::Coef{KS_RHO_NEW, KS_RHO, 1.}, nullptr, none, -1))) return rc;   // p = z + beta p
+            mgb::k_scal_copy<<<1, 32, 0, h->st>>>(h->d_scal, KS_RHO, KS_RHO_NEW);
+            count(h, 0.);
+        }
+    } else {
+        double *rh = h->kry[0] + off, *p = h->kry[1] + off, *v = h->kry[2] + off, *sv = h->kry[3] + off, *t = h->kry[4] + off;
+        double *y = nullptr, *z = nullptr;
+        CK(cudaMemcpyAsync(rh - off, F.r - off, bytes, cudaMemcpyDeviceToDevice, h->st));          // shadow residual
+        CK(cudaMemcpyAsync(p - off, F.r - off, bytes, cudaMemcpyDeviceToDevice, h->st));
+        mgb::k_scal_copy<<<1, 32, 0, h->st>>>(h->d_scal, KS_RHO, 1);                                 // rho = (rh, r) = |r|^2
+        count(h, 0.);
+        for (int it = 0; it < maxit; ++it) {
+            if ((rc = kry_precond(h, precond, p, &y))) return rc;                                   // y = M p
+            if ((rc = kry_apply(h, y, v, KS_TS))) return rc;                                        // v = A y
+            if ((rc = kry_dot(h, rh, v, KS_DEN))) return rc;
+            k_scal_div<<<1, 32, 0, h->st>>>(h->d_scal, KS_ALPHA, KS_RHO, KS_DEN);                    // alpha = rho / (rh, v)
+            count(h, 0.);
+            if ((rc = kry_axpy(h, F.u, y, mgb::Coef{KS_ALPHA, -1, 1.}, nullptr, none, -1))) return rc;     // u += alpha y
+            if ((rc = kry_xpay(h, sv, F.r, v, mgb::Coef{KS_ALPHA, -1, -1.}, nullptr, none, 1))) return rc; // s = r - alpha v
+            if ((rc = read_scalar(h, 1, &ss))) return rc;
+            if (std::sqrt(ss / h->norm_f) <= tol) { hist[n++] = std::sqrt(ss / h->norm_f); break; }
+            if ((rc = kry_precond(h, precond, sv, &z))) return rc;                                  // z = M s
+            if ((rc = kry_apply(h, z, t, KS_DEN))) return rc;                                       // t = A z
+            if ((rc = kry_dot(h, t, sv, KS_TS))) return rc;
+            if ((rc = kry_dot(h, t, t, KS_TT))) return rc;
+            k_scal_div<<<1, 32, 0, h->st>>>(h->d_scal, KS_OMEGA, KS_TS, KS_TT);                      // omega = (t, s) / (t, t)
+            count(h, 0.);
+            if ((rc = kry_axpy(h, F.u, z, mgb::Coef{KS_OMEGA, -1, 1.}, nullptr, none, -1))) return rc;     // u += omega z
+            if ((rc = kry_xpay(h, F.r, sv, t, mgb::Coef{KS_OMEGA, -1, -1.}, nullptr, none, 1))) return rc; // r = s - omega t
+            if ((rc = read_scalar(h, 1, &ss))) return rc;
+            hist[n++] = std::sqrt(ss / h->norm_f);
+            if (hist[n - 1] <= tol) break;
+            if ((rc = kry_dot(h, rh, F.r, KS_RHO_NEW))) return rc;
+            k_scal_beta<<<1, 32, 0, h->st>>>(h->d_scal, KS_BETA, KS_RHO_NEW, KS_RHO, KS_ALPHA, KS_OMEGA);
+            count(h, 0.);
+            // p = r + beta (p - omega v)
+            if ((rc = kry_xpay(h, p, F.r, p, mgb::Coef{KS_BETA, -1, 1.}, v, mgb::Coef{KS_OMEGA, -1, -1.}, -1))) return rc;
+            mgb::k_scal_copy<<<1, 32, 0, h->st>>>(h->d_scal, KS_RHO, KS_RHO_NEW);
+            count(h, 0.);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->st));
+    *n_hist = n;
     return MGB_OK;
 }
 
@@ -1182,8 +1467,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     }
     h->n_partial = std::max<size_t>(max_partial, 1 << 16);
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));
-    CK(cudaMalloc(&h->d_scal, 80 * sizeof(double)));      // 16 scalars + one part per rank of a sum that rides in an exchange
-    CK(cudaMemsetAsync(h->d_scal, 0, 80 * sizeof(double), h->st));
+    CK(cudaMalloc(&h->d_scal, 96 * sizeof(double)));      // 16 scalars + one part per rank of a sum that rides in an exchange + 16 Krylov scalars
+    CK(cudaMemsetAsync(h->d_scal, 0, 96 * sizeof(double), h->st));
     CK(cudaMallocHost(&h->h_scal, 16 * sizeof(double)));
     CK(cudaStreamSynchronize(h->st));
     guard.h = nullptr;
@@ -1200,6 +1485,7 @@ void mgb_gmg_destroy(mgb_gmg_t h)
     if (h->comm) mgb::nccl().CommDestroy(h->comm);
     for (auto &lv : h->lv)
         for (double *p : lv.base) if (p) cudaFree(p);
+    for (double *p : h->kry) if (p) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_scal) cudaFree(h->d_scal);
     if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -1331,6 +1617,34 @@ int mgb_gmg_set_cycle(mgb_gmg_t h, int smoother, int restriction, int nu, double
     return MGB_OK;
 }
 
+int mgb_gmg_set_cycle_type(mgb_gmg_t h, int cycle_type, int nu_pre, int fmg)
+{
+    if (!h || cycle_type < MGB_CYCLE_SAWTOOTH || cycle_type > MGB_CYCLE_F || nu_pre < 0 || nu_pre > 64)
+        return fail(MGB_ERR_ARG, "bad cycle type / nu_pre");
+    h->cfg.cycle_type = cycle_type; h->cfg.nu_pre = nu_pre; h->cfg.fmg = fmg ? 1 : 0;      // cached iteration graphs are keyed on these
+    return MGB_OK;
+}
+
+int mgb_gmg_fmg(mgb_gmg_t h)
+{
+    if (!h) return fail(MGB_ERR_ARG, "null handle");
+    if (!h->have_rhs) return fail(MGB_ERR_STATE, "set the right-hand side first");
+    CK(cudaSetDevice(h->cfg.device));
+    return do_fmg(h);
+}
+
+int mgb_gmg_krylov(mgb_gmg_t h, int method, int precond, double tol, int maxit, double *hist, int *n_hist)
+{
+    if (!h || !hist || !n_hist || maxit < 0) return fail(MGB_ERR_ARG, "bad argument");
+    if (method != MGB_KRYLOV_CG && method != MGB_KRYLOV_BICGSTAB) return fail(MGB_ERR_ARG, "unknown Krylov method");
+    if (precond != MGB_PRECOND_NONE && precond != MGB_PRECOND_MG) return fail(MGB_ERR_ARG, "unknown preconditioner");
+    if (!h->have_rhs) return fail(MGB_ERR_STATE, "set the right-hand side first");
+    if (precond == MGB_PRECOND_MG && h->cfg.smoother == MGB_SMOOTH_GS_LEX && h->cfg.n_ranks > 1)
+        return fail(MGB_ERR_ARG, "lexicographic GS is sequential across slabs");
+    CK(cudaSetDevice(h->cfg.device));
+    return do_krylov(h, method, precond, tol, maxit, hist, n_hist);
+}
+
 int mgb_gmg_set_defer_norm(mgb_gmg_t h, int defer)
 {
     if (!h) return fail(MGB_ERR_ARG, "null handle");
@@ -1399,7 +1713,13 @@ int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double 
     if ((rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;
     if ((rc = read_scalar(h, 1, &ss))) return rc;
     hist[n++] = std::sqrt(ss / h->norm_f);
+    const bool fmg_first = h->cfg.fmg && maxiter > 0 && hist[0] > tol;
     for (int i = 0; i < maxiter; ++i) {                                   // main.cpp:84-90
+        if (i == 0 && fmg_first) {
+            // the first iteration is one full-multigrid pass (not in the reference) followed by a true residual norm
+            if ((rc = do_fmg(h))) return rc;
+            if ((rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;
+        } else
         if ((rc = one_iteration(h))) return rc;
         if ((i + 1) % check_every == 0 || i + 1 == maxiter) {
             if ((rc = read_scalar(h, 1, &ss))) return rc;

@@ -14,6 +14,9 @@ from ._lib import GmgConfigStruct, GmgStatsStruct, check, load
 GS_LEX, JACOBI, BICGSTAB, GS_RB = 0, 1, 2, 3
 INJECTION, HALF_INJECTION, FULL_WEIGHTING = 0, 1, 2
 VEC_U, VEC_F, VEC_E, VEC_R = 0, 1, 2, 3
+CYCLE_SAWTOOTH, CYCLE_V, CYCLE_W, CYCLE_F = 0, 1, 2, 3
+KRYLOV_CG, KRYLOV_BICGSTAB = 0, 1
+PRECOND_NONE, PRECOND_MG = 0, 1
 
 
 @dataclass
@@ -42,6 +45,9 @@ class GmgConfig:
     fuse_prolong: int = 0
     defer_norm: int = 0
     jacobi_omega: float = 1.0
+    cycle_type: int = CYCLE_SAWTOOTH
+    nu_pre: int = 0
+    fmg: int = 0
 
     @staticmethod
     def fast(n, levels, **kw):
@@ -79,7 +85,7 @@ class Gmg:
         for k in ("n", "levels", "length", "alpha", "smoother", "pre_smoother", "n_pre", "nu",
                   "restriction", "coarse_tol", "coarse_maxit", "device", "rank", "n_ranks",
                   "tail_max_width", "use_graph", "rb_fast_arith", "rb_fused", "fuse_correction", "fuse_residual", "fuse_prolong", "defer_norm",
-                  "jacobi_omega"):
+                  "jacobi_omega", "cycle_type", "nu_pre", "fmg"):
             setattr(c, k, getattr(cfg, k))
         if cfg.nccl_id:
             C.memmove(c.nccl_id, cfg.nccl_id, min(128, len(cfg.nccl_id)))
@@ -181,6 +187,19 @@ class Gmg:
         hist = np.zeros(maxiter + 1)
         n = C.c_int()
         check(self.lib.mgb_gmg_solve(self.h, tol, maxiter, check_every, self._ptr(hist), C.byref(n)))
+        return hist[:n.value].copy()
+
+    def set_cycle_type(self, cycle_type, nu_pre=0, fmg=0):
+        check(self.lib.mgb_gmg_set_cycle_type(self.h, cycle_type, nu_pre, fmg))
+
+    def fmg(self):
+        """one full-multigrid pass on the residual equation, applied to u"""
+        check(self.lib.mgb_gmg_fmg(self.h))
+
+    def krylov(self, method=KRYLOV_CG, precond=PRECOND_MG, tol=1e-11, maxit=200):
+        hist = np.zeros(maxit + 1)
+        n = C.c_int()
+        check(self.lib.mgb_gmg_krylov(self.h, method, precond, tol, maxit, self._ptr(hist), C.byref(n)))
         return hist[:n.value].copy()
 
     def run_cycles(self, cycles, want_relres=True):

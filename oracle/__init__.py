@@ -72,6 +72,16 @@ class GmgOracle:
                                     _dp, _dp, C.c_double, C.c_int, _dp, C.c_void_p, C.c_void_p]
         L.gmgo_solve_ex.restype = C.c_int
         L.gmgo_cycle_set_restriction.argtypes = [C.c_void_p, C.c_int]
+        # textbook cycles / FMG / Krylov (ours)
+        L.gmgo_tb_create.argtypes = [C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_long, C.c_double]
+        L.gmgo_tb_create.restype = C.c_void_p
+        L.gmgo_tb_destroy.argtypes = [C.c_void_p]
+        L.gmgo_tb_set_omega.argtypes = [C.c_void_p, C.c_double]
+        L.gmgo_tb_iteration.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int]
+        L.gmgo_tb_fmg.argtypes = [C.c_void_p, _dp, _dp]
+        L.gmgo_tb_krylov.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int, _dp]
+        L.gmgo_tb_krylov.restype = C.c_int
 
     def level(self, N, length, alpha, level):
         lv = _Level()
@@ -122,6 +132,14 @@ class GmgOracle:
         self.lib.gmgo_cycle_destroy(st)
         return u, info
 
+    def textbook(self, N, length, alpha, L, kind, cycle, bottom, nu_pre=0, nu=5, restrict_mode=2,
+                 coarse_maxit=2000, coarse_tol=0.1, omega=1.0):
+        """state of the V / W / F cycles, FMG and the Krylov solvers (ours, not in the reference); `bottom` = first level of
+        the coarse solver (one sawtooth pass over levels bottom..L-1)"""
+        t = _Textbook(self.lib, N, length, alpha, L, kind, cycle, bottom, nu_pre, nu, restrict_mode, coarse_maxit, coarse_tol)
+        self.lib.gmgo_tb_set_omega(t.st, omega)
+        return t
+
     def solve(self, N, length, alpha, L, smoother, b, u=None, pre_kind=GS, tol=1e-11, maxiter=1000,
               restrict_mode=0, nu=5, coarse_maxit=2000, coarse_tol=0.1):
         u = np.zeros(N * N) if u is None else u
@@ -134,6 +152,38 @@ class GmgOracle:
         if n < 0:
             raise ValueError("bad level count for this N")
         return u, hist[:n].copy(), crel[:n - 1].copy(), cits[:n - 1].copy()
+
+
+class _Textbook:
+    def __init__(self, lib, N, length, alpha, L, kind, cycle, bottom, nu_pre, nu, restrict_mode, coarse_maxit, coarse_tol):
+        self.lib, self.N = lib, N
+        self.st = lib.gmgo_tb_create(N, length, alpha, L, kind, nu_pre, nu, restrict_mode, cycle, bottom, coarse_maxit, coarse_tol)
+        if not self.st:
+            raise ValueError("bad level count / bottom for this N")
+
+    def iteration(self, u, b, pre_kind=RBGS, n_pre=2):
+        self.lib.gmgo_tb_iteration(self.st, u, b, pre_kind, n_pre)
+        return u
+
+    def fmg(self, u, b):
+        self.lib.gmgo_tb_fmg(self.st, u, b)
+        return u
+
+    def krylov(self, method, precond, b, u, tol=1e-11, maxit=200):
+        hist = np.zeros(maxit + 1)
+        n = self.lib.gmgo_tb_krylov(self.st, method, precond, b, u, tol, maxit, hist)
+        return u, hist[:n].copy()
+
+    def close(self):
+        if self.st:
+            self.lib.gmgo_tb_destroy(self.st)
+            self.st = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class GmgReference:

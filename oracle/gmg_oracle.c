@@ -402,3 +402,291 @@ int gmgo_solve_ex(size_t N, double length, double alpha, int L, int smoother, in
     gmgo_cycle_destroy(st);
     return n;
 }
+
+/* =====================================================================================================
+ * Textbook cycle options, full multigrid and Krylov solvers.
+ *
+ * NOT IN THE REFERENCE: its only cycle is the sawtooth above and its BiCGSTAB class is never executed
+ * (src/main.cpp:103-106).  What follows is the CPU statement of the algorithms libmgb200 adds
+ * (include/mgb200.h: mgb_gmg_config.cycle_type / nu_pre / fmg, mgb_gmg_fmg, mgb_gmg_krylov), written
+ * with the reference's per-point formulas (the functions above) so that the CUDA path can be checked
+ * bit for bit (sweeps, residuals, transfers) or to rounding (dot products).  Every level keeps its own
+ * fine-sized strided arrays e_l, r_l: a correction-scheme cycle needs e_l and e_{l+1} at the same time,
+ * which the reference's single shared array cannot hold.
+ * ===================================================================================================== */
+typedef struct {
+    int L, kind, nu1, nu2, restrict_mode, cycle, bottom;
+    long coarse_maxit;
+    double coarse_tol;
+    double omega;              /* weight of the Jacobi smoother (mgb_gmg_config.jacobi_omega); 1 = the reference's */
+    gmgo_level lv[32];
+    double *e[32], *r[32], *d, *temp;
+    size_t n_fine;
+} gmgo_tb;
+
+/* weighted Jacobi (north_star; the reference is omega = 1, solvers.hpp:64-83): u <- u + omega (u_jacobi - u) inside */
+static void wjacobi_sweep(const gmgo_level *lv, double *sol, const double *b, double *temp, double omega)
+{
+    const size_t w = lv->w;
+    for (size_t I = 0; I < w; I++)
+        for (size_t J = 0; J < w; J++) {
+            size_t idx = mask_of(lv, I, J);
+            if (on_boundary(lv, I, J)) { temp[idx] = b[idx]; continue; }
+            double sum = 0;
+            sum += lv->off * sol[mask_of(lv, I - 1, J)];
+            sum += lv->off * sol[mask_of(lv, I, J - 1)];
+            sum += lv->off * sol[mask_of(lv, I, J + 1)];
+            sum += lv->off * sol[mask_of(lv, I + 1, J)];
+            double o = (b[idx] - sum) / lv->diag;
+            temp[idx] = sol[idx] + omega * (o - sol[idx]);
+        }
+    for (size_t I = 0; I < w; I++)
+        for (size_t J = 0; J < w; J++) { size_t idx = mask_of(lv, I, J); sol[idx] = temp[idx]; }
+}
+static void tb_sweep(const gmgo_tb *st, const gmgo_level *lv, double *sol, const double *b, double *temp)
+{
+    if (st->kind == GMGO_JACOBI && st->omega != 1.0) wjacobi_sweep(lv, sol, b, temp, st->omega);
+    else sweep(st->kind, lv, sol, b, temp);
+}
+void gmgo_tb_set_omega(gmgo_tb *st, double omega);
+
+enum { GMGO_SAWTOOTH = 0, GMGO_V = 1, GMGO_W = 2, GMGO_F = 3 };
+
+/* bottom = first level of the coarse solver: levels bottom..L-1 are "solved" by one sawtooth pass
+ * (multigrid.hpp:128-139 applied to r_bottom), which is what the persistent tail kernel does. */
+gmgo_tb *gmgo_tb_create(size_t N, double length, double alpha, int L, int kind, int nu1, int nu2,
+                        int restrict_mode, int cycle, int bottom, long coarse_maxit, double coarse_tol)
+{
+    if (L < 1 || L > 31 || bottom < 0 || bottom >= L) return NULL;
+    gmgo_tb *st = (gmgo_tb *)calloc(1, sizeof(*st));
+    st->L = L; st->kind = kind; st->nu1 = nu1; st->nu2 = nu2; st->restrict_mode = restrict_mode;
+    st->cycle = cycle; st->bottom = bottom; st->coarse_maxit = coarse_maxit; st->coarse_tol = coarse_tol;
+    st->n_fine = N * N;
+    st->omega = 1.0;
+    for (int l = 0; l < L; l++) {
+        if (gmgo_level_init(&st->lv[l], N, length, alpha, l) != 0) { free(st); return NULL; }
+        st->e[l] = (double *)calloc(st->n_fine, sizeof(double));
+        st->r[l] = (double *)calloc(st->n_fine, sizeof(double));
+    }
+    st->d = (double *)calloc(st->n_fine, sizeof(double));
+    st->temp = (double *)calloc(st->n_fine, sizeof(double));
+    return st;
+}
+void gmgo_tb_destroy(gmgo_tb *st)
+{
+    if (!st) return;
+    for (int l = 0; l < st->L; l++) { free(st->e[l]); free(st->r[l]); }
+    free(st->d); free(st->temp); free(st);
+}
+void gmgo_tb_set_omega(gmgo_tb *st, double omega) { st->omega = omega > 0. ? omega : 1.0; }
+double *gmgo_tb_e(gmgo_tb *st, int l) { return st->e[l]; }
+double *gmgo_tb_r(gmgo_tb *st, int l) { return st->r[l]; }
+
+static void level_zero(const gmgo_level *lv, double *v)
+{
+    for (size_t I = 0; I < lv->w; I++)
+        for (size_t J = 0; J < lv->w; J++) v[mask_of(lv, I, J)] = 0.;
+}
+
+/* out (level f = c-1) = bilinear interpolation of ec (level c), the two-stage order of multigrid.cpp:3-27 */
+static void prolong_into(const gmgo_level *c, const gmgo_level *f, const double *ec, double *out)
+{
+    for (size_t I = 0; I < c->w; I++)
+        for (size_t J = 0; J < c->w; J++) out[mask_of(c, I, J)] = ec[mask_of(c, I, J)];
+    gmgo_prolong(c, f, out);
+}
+
+/* restriction used inside the sawtooth pass of the coarse solver and by the cascade of the FMG pass:
+ * full weighting level by level, or injection (half injection scales only the step to level 1) */
+static void restrict_sawtooth(int mode, int l, const gmgo_level *f, const gmgo_level *c, const double *rf, double *rc)
+{
+    if (mode == 2) { restrict_level(2, f, c, rf, rc); return; }
+    for (size_t I = 0; I < c->w; I++)
+        for (size_t J = 0; J < c->w; J++) {
+            size_t ic = mask_of(c, I, J);
+            double scale = (mode == 1 && l == 1) ? 0.5 : 1.0;
+            rc[ic] = on_boundary(c, I, J) ? rf[ic] : scale * rf[ic];
+        }
+}
+
+/* the coarse solver: one sawtooth pass on levels bottom..L-1 from r[bottom]; leaves e[bottom] */
+static void tb_tail(gmgo_tb *st, int restrict_below)
+{
+    const int L = st->L, b = st->bottom;
+    if (restrict_below)
+        for (int l = b + 1; l < L; l++)
+            restrict_sawtooth(st->restrict_mode, l, &st->lv[l - 1], &st->lv[l], st->r[l - 1], st->r[l]);
+    const gmgo_level *C = &st->lv[L - 1];
+    double *ec = st->e[L - 1];
+    const double *rc = st->r[L - 1];
+    level_zero(C, ec);
+    double nb = gmgo_sumsq(C, rc);
+    long its = 0;
+    double norm = gmgo_residual(C, ec, rc, NULL);
+    while (sqrt(norm / nb) > st->coarse_tol && its < st->coarse_maxit) {
+        tb_sweep(st, C, ec, rc, st->temp);
+        its++;
+        norm = gmgo_residual(C, ec, rc, NULL);
+    }
+    for (int l = L - 1; l > b; --l) {
+        prolong_into(&st->lv[l], &st->lv[l - 1], st->e[l], st->e[l - 1]);
+        for (int i = 0; i < st->nu2; i++) tb_sweep(st, &st->lv[l - 1], st->e[l - 1], st->r[l - 1], st->temp);
+    }
+}
+
+static void tb_cycle(gmgo_tb *st, int l, int type, int zero)
+{
+    const gmgo_level *X = &st->lv[l];
+    if (l >= st->bottom) { tb_tail(st, 1); return; }
+    if (zero) level_zero(X, st->e[l]);
+    for (int i = 0; i < st->nu1; i++) tb_sweep(st, X, st->e[l], st->r[l], st->temp);
+    gmgo_residual(X, st->e[l], st->r[l], st->d);
+    {   /* r_{l+1} = R d: full weighting, or injection (half injection halves on EVERY level here) */
+        const gmgo_level *C = &st->lv[l + 1];
+        if (st->restrict_mode == 2) restrict_level(2, X, C, st->d, st->r[l + 1]);
+        else
+            for (size_t I = 0; I < C->w; I++)
+                for (size_t J = 0; J < C->w; J++) {
+                    size_t ic = mask_of(C, I, J);
+                    double scale = st->restrict_mode == 1 ? 0.5 : 1.0;
+                    st->r[l + 1][ic] = on_boundary(C, I, J) ? st->d[ic] : scale * st->d[ic];
+                }
+    }
+    if (type == GMGO_F) {
+        tb_cycle(st, l + 1, GMGO_F, 1);
+        if (l + 1 < st->bottom) tb_cycle(st, l + 1, GMGO_V, 0);
+    } else {
+        int visits = (type == GMGO_W && l + 1 < st->bottom) ? 2 : 1;
+        for (int v = 0; v < visits; v++) tb_cycle(st, l + 1, type, v == 0);
+    }
+    prolong_into(&st->lv[l + 1], X, st->e[l + 1], st->d);
+    for (size_t I = 0; I < X->w; I++)
+        for (size_t J = 0; J < X->w; J++) { size_t i = mask_of(X, I, J); st->e[l][i] = st->e[l][i] + st->d[i]; }
+    for (int i = 0; i < st->nu2; i++) tb_sweep(st, X, st->e[l], st->r[l], st->temp);
+}
+
+/* e_0 ~= A^-1 r_0 with the configured cycle (r_0 = st->r[0] must be set) */
+void gmgo_tb_apply(gmgo_tb *st)
+{
+    if (st->cycle == GMGO_SAWTOOTH) {
+        /* the whole hierarchy as one sawtooth pass */
+        int b = st->bottom;
+        st->bottom = 0;
+        tb_tail(st, 1);
+        st->bottom = b;
+    } else tb_cycle(st, 0, st->cycle, 1);
+}
+
+/* one driver iteration with a textbook cycle: n_pre sweeps on u, r_0 = b - A u, cycle, u += e_0 */
+void gmgo_tb_iteration(gmgo_tb *st, double *u, const double *b, int pre_kind, int n_pre)
+{
+    const gmgo_level *F = &st->lv[0];
+    for (int i = 0; i < n_pre; i++) sweep(pre_kind, F, u, b, st->temp);
+    gmgo_residual(F, u, b, st->r[0]);
+    gmgo_tb_apply(st);
+    for (size_t j = 0; j < st->n_fine; j++) u[j] += st->e[0][j];
+}
+
+/* one full-multigrid pass on the residual equation (mgb_gmg_fmg) */
+void gmgo_tb_fmg(gmgo_tb *st, double *u, const double *b)
+{
+    const gmgo_level *F = &st->lv[0];
+    gmgo_residual(F, u, b, st->r[0]);
+    for (int l = 1; l <= st->bottom; l++)
+        restrict_sawtooth(st->restrict_mode, l, &st->lv[l - 1], &st->lv[l], st->r[l - 1], st->r[l]);
+    tb_tail(st, 1);
+    for (int l = st->bottom - 1; l >= 0; --l) {
+        prolong_into(&st->lv[l + 1], &st->lv[l], st->e[l + 1], st->e[l]);
+        tb_cycle(st, l, GMGO_V, 0);
+    }
+    for (size_t j = 0; j < st->n_fine; j++) u[j] += st->e[0][j];
+}
+
+/* ---- Krylov solvers on the fine level, optionally right-preconditioned by one cycle (mgb_gmg_krylov) ---- */
+static double vdot(size_t n, const double *a, const double *b) { double s = 0; for (size_t i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+/* q = A p on the fine level (identity rows on the boundary), formula of solvers.hpp:278-294 with b = 0, negated */
+static void apply_A(const gmgo_level *F, const double *p, double *q)
+{
+    const size_t w = F->w;
+    for (size_t I = 0; I < w; I++)
+        for (size_t J = 0; J < w; J++) {
+            size_t idx = mask_of(F, I, J);
+            if (on_boundary(F, I, J)) { q[idx] = p[idx]; continue; }
+            double sum = 0;
+            sum += F->off * p[mask_of(F, I - 1, J)];
+            sum += F->off * p[mask_of(F, I, J - 1)];
+            sum += F->diag * p[idx];
+            sum += F->off * p[mask_of(F, I, J + 1)];
+            sum += F->off * p[mask_of(F, I + 1, J)];
+            q[idx] = -(0. - sum);
+        }
+}
+static const double *tb_precond(gmgo_tb *st, int precond, const double *src)
+{
+    if (!precond) return src;
+    memcpy(st->r[0], src, st->n_fine * sizeof(double));
+    if (st->L == 1) tb_tail(st, 0); else gmgo_tb_apply(st);
+    return st->e[0];
+}
+
+/* method 0 = CG, 1 = BiCGSTAB; precond 0 = none, 1 = one cycle.  hist holds maxit+1 doubles; returns the entries written */
+int gmgo_tb_krylov(gmgo_tb *st, int method, int precond, const double *b, double *u, double tol, int maxit, double *hist)
+{
+    const gmgo_level *F = &st->lv[0];
+    const size_t n = st->n_fine, w = F->w;
+    double *r = (double *)calloc(n, sizeof(double)), *p = (double *)calloc(n, sizeof(double));
+    double *q = (double *)calloc(n, sizeof(double)), *rh = (double *)calloc(n, sizeof(double));
+    double *s = (double *)calloc(n, sizeof(double)), *t = (double *)calloc(n, sizeof(double));
+    int k = 0;
+    for (size_t I = 0; I < w; I++)
+        for (size_t J = 0; J < w; J++)
+            if (on_boundary(F, I, J)) u[mask_of(F, I, J)] = b[mask_of(F, I, J)];
+    const double nf = gmgo_sumsq(F, b);
+    double rr = gmgo_residual(F, u, b, r);
+    hist[k++] = sqrt(rr / nf);
+    if (hist[0] > tol && maxit > 0) {
+        if (method == 0) {
+            const double *z = tb_precond(st, precond, r);
+            double rho = vdot(n, r, z);
+            memcpy(p, z, n * sizeof(double));
+            for (int it = 0; it < maxit; it++) {
+                apply_A(F, p, q);
+                double alpha = rho / vdot(n, p, q);
+                for (size_t i = 0; i < n; i++) u[i] += alpha * p[i];
+                for (size_t i = 0; i < n; i++) r[i] -= alpha * q[i];
+                hist[k++] = sqrt(vdot(n, r, r) / nf);
+                if (hist[k - 1] <= tol) break;
+                z = tb_precond(st, precond, r);
+                double rho_new = vdot(n, r, z), beta = rho_new / rho;
+                for (size_t i = 0; i < n; i++) p[i] = z[i] + beta * p[i];
+                rho = rho_new;
+            }
+        } else {
+            memcpy(rh, r, n * sizeof(double));
+            memcpy(p, r, n * sizeof(double));
+            double rho = rr, alpha, omega;
+            for (int it = 0; it < maxit; it++) {
+                const double *y = tb_precond(st, precond, p);
+                apply_A(F, y, q);                                   /* v */
+                alpha = rho / vdot(n, rh, q);
+                for (size_t i = 0; i < n; i++) u[i] += alpha * y[i];
+                for (size_t i = 0; i < n; i++) s[i] = r[i] - alpha * q[i];
+                double ss = vdot(n, s, s);
+                if (sqrt(ss / nf) <= tol) { hist[k++] = sqrt(ss / nf); break; }
+                const double *z = tb_precond(st, precond, s);
+                apply_A(F, z, t);
+                omega = vdot(n, t, s) / vdot(n, t, t);
+                for (size_t i = 0; i < n; i++) u[i] += omega * z[i];
+                for (size_t i = 0; i < n; i++) r[i] = s[i] - omega * t[i];
+                hist[k++] = sqrt(vdot(n, r, r) / nf);
+                if (hist[k - 1] <= tol) break;
+                double rho_new = vdot(n, rh, r);
+                double beta = (rho_new / rho) * (alpha / omega);
+                for (size_t i = 0; i < n; i++) p[i] = r[i] + beta * (p[i] - omega * q[i]);
+                rho = rho_new;
+            }
+        }
+    }
+    free(r); free(p); free(q); free(rh); free(s); free(t);
+    return k;
+}
