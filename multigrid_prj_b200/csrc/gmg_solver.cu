@@ -21,8 +21,10 @@
 #include "gmg_stream2.h"
 #include "gmg_tail.cuh"
 #include "nccl_dyn.h"
+#include "p2p.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -59,7 +61,7 @@ struct Level {
     LevelGeom g{};                    // this rank's view (sharded: its slab; replicated: the whole level)
     bool sharded = false;
     size_t elems = 0;                 // (rows + 2*kHalo) * pitch
-    double *base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // inside the handle's pool
     // pointers to local row 0 of: u, f (level 0 only), e, r, t (ping-pong partner of e in out-of-place sweeps),
     // tu (ping-pong partner of u, level 0 only: two independent pairs keep the buffer rotation at period 2)
     double *u = nullptr, *f = nullptr, *e = nullptr, *r = nullptr, *t = nullptr, *tu = nullptr;
@@ -101,6 +103,33 @@ Part partition(size_t n, int levels, int n_ranks, int rank, int level)
     return p;
 }
 
+// Every rank keeps ALL its level arrays in one device allocation (the pool): [header + device scalars][level 0: u f e r t tu]
+// [level 1: e r t] ...  The layout is a pure function of the configuration and the rank, so every rank knows where a
+// peer keeps a given array inside the peer's pool (mapped here through CUDA IPC, csrc/p2p.cuh).
+constexpr size_t kScalOff = 8192;                    // byte offset of the device scalars inside the pool header
+constexpr size_t kAbsent = ~(size_t)0;
+struct PoolLayout { std::vector<std::array<size_t, 6>> off; size_t total = 0; };
+PoolLayout pool_layout(size_t n, int levels, int n_ranks, int rank)
+{
+    PoolLayout pl;
+    pl.off.resize(levels);
+    size_t cur = mgb::kP2PHeaderBytes, w = n;
+    for (int l = 0; l < levels; ++l) {
+        const Part p = partition(n, levels, n_ranks, rank, l);
+        const size_t pitch = (w + 2 + 15) / 16 * 16;
+        const size_t bytes = ((size_t)(p.rows + 2 * kHalo) * pitch * sizeof(double) + 511) / 512 * 512;
+        for (int v = 0; v < 6; ++v) {
+            if (l > 0 && (v < 2 || v == 5)) { pl.off[l][v] = kAbsent; continue; }     // u, f, tu exist on level 0 only
+            pl.off[l][v] = cur;
+            cur += bytes;
+        }
+        w = (w + 1) / 2;
+    }
+    const size_t MB2 = (size_t)2 << 20;              // whole 2 MB pages, at least two: the allocation is never a sub-block
+    pl.total = std::max((cur + MB2 - 1) / MB2 * MB2, 2 * MB2);
+    return pl;
+}
+
 }  // namespace
 
 // shared with amg_solver.cu: records the thread's last error text and returns the code
@@ -121,6 +150,11 @@ struct mgb_gmg {
     unsigned scal_local = 0;          // bit s: d_scal[s] holds only this rank's part; summed over ranks when it is read
     cudaStream_t st = nullptr;
     mgb::NcclComm comm = nullptr;
+    char *pool = nullptr;             // the one device allocation behind every level array and the device scalars
+    size_t pool_bytes = 0;
+    mgb::P2PComm p2p;                 // peer mappings of the other ranks' pools (slab exchanges over NVLink stores)
+    std::vector<PoolLayout> layouts;  // layouts[r]: where rank r keeps its arrays inside its pool
+    bool p2p_dirty = true;            // an NCCL exchange wrote halo rows since the last peer-store exchange: barrier first
     double *d_partial = nullptr;      // per-CTA partial sums
     size_t n_partial = 0;
     double *d_scal = nullptr;         // device scalars
@@ -194,6 +228,7 @@ int halo_exchange(mgb_gmg *h, int level, double *v, int depth, const double *nor
     const size_t P = (size_t)L.g.pitch;
     depth = std::min(depth, std::min(kHalo, L.g.rows));
     const size_t cnt = (size_t)depth * P;
+    h->p2p_dirty = true;
     NK(N.GroupStart());
     if (r > 0) {
         NK(N.Send(v, cnt, mgb::kNcclFloat64, r - 1, h->comm, h->st));                                   // my top rows
@@ -469,6 +504,7 @@ int allgather_rows(mgb_gmg *h, int level, double *v)
     };
     int my0, myn;
     vslab(me, my0, myn);
+    h->p2p_dirty = true;
     NK(N.GroupStart());
     for (int p = 0; p < n; ++p) {
         if (p == me) continue;
@@ -666,6 +702,80 @@ void trace_flush(mgb_gmg *h)
     h->trace.ev.clear(); h->trace.used = 0;
 }
 
+
+// ---- slab exchanges by direct peer stores (csrc/p2p.cuh) --------------------------------------------------------------
+enum { CH_U = 0, CH_R = 1 };
+
+// row 0 of rank p's copy of a level vector (buffer `vb` of pool_layout) as mapped into this process
+double *peer_vec(mgb_gmg *h, int p, int level, int vb)
+{
+    return h->p2p.at<double>(p, h->layouts[p].off[level][vb]) + (size_t)kHalo * h->lv[level].g.pitch;
+}
+
+int p2p_barrier_if_dirty(mgb_gmg *h)
+{
+    if (!h->p2p.on || !h->p2p_dirty) return MGB_OK;
+    // an NCCL exchange may still be copying into halo rows on a peer: all ranks pass this point before any peer store
+    double *d = h->d_scal + 14;
+    NK(mgb::nccl().AllReduce(d, d, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st));
+    h->p2p_dirty = false;
+    return MGB_OK;
+}
+
+int p2p_launch(mgb_gmg *h, mgb::P2PPushBuilder &b, int channel)
+{
+    if (b.overflow) return fail(MGB_ERR_STATE, "peer exchange: too many segments");
+    const int me = h->cfg.rank, n = h->cfg.n_ranks;
+    mgb::P2PHeader *hd = h->p2p.hdr(me);
+    unsigned mask = 0;
+    for (int p = 0; p < n; ++p) {
+        if (p == me) continue;
+        b.signal(&h->p2p.hdr(p)->flags[me][channel]);       // every exchange signals every rank (and waits for every rank):
+        mask |= 1u << p;                                     // this is what orders the reuse of the halo rows, see below
+    }
+    b.a.seq = &hd->push_seq[channel];
+    b.a.done = &hd->done[channel];
+    const int grid = std::max(1, std::min(b.items, 2 * h->n_sm));
+    mgb::k_p2p_push<<<grid, 256, 0, h->st>>>(b.a);
+    mgb::k_p2p_wait<<<1, 32, 0, h->st>>>(hd, channel, mask);
+    count(h, 0.); count(h, 0.);
+    CK(cudaGetLastError());
+    h->stats.reserved[0]++;
+    return MGB_OK;
+}
+
+// Exchange `depth` halo rows of u (level 0) with the slab neighbours; `norm_local` (optional): this rank's part of a sum
+// goes to slot 16 + rank of every other rank's device scalars.
+// Reuse of the destination rows is safe because the slab iteration alternates the two channels and both are all-to-all:
+// a rank stores into a peer's u halo only after it has seen the peer's signal on CH_R, which the peer posts after the
+// launch that read that halo (the pre-sweeps); likewise for the residual halos and CH_U.
+int p2p_exchange_u(mgb_gmg *h, double *v, int depth, const double *norm_local)
+{
+    Level &L = h->lv[0];
+    const int r = h->cfg.rank, n = h->cfg.n_ranks;
+    const size_t P = (size_t)L.g.pitch;
+    depth = std::min(depth, std::min(kHalo, L.g.rows));
+    const size_t cnt = (size_t)depth * P;
+    const int vb = (v == L.base[0] + (size_t)kHalo * P) ? 0 : 5;
+    mgb::P2PPushBuilder b;
+    if (r > 0) {
+        const Part pp = partition(h->cfg.n, h->cfg.levels, n, r - 1, 0);
+        b.seg(v, peer_vec(h, r - 1, 0, vb) + (size_t)pp.rows * P, cnt);                       // my top rows: halo below the upper slab
+    }
+    if (r < n - 1) b.seg(v + (size_t)(L.g.rows - depth) * P, peer_vec(h, r + 1, 0, vb) - cnt, cnt);   // my bottom rows: halo above the lower slab
+    if (norm_local)
+        for (int p = 0; p < n; ++p)
+            if (p != r) b.seg(norm_local, h->p2p.at<double>(p, kScalOff) + 16 + r, 1);
+    return p2p_launch(h, b, CH_U);
+}
+
+int exchange_u(mgb_gmg *h, double *v, int depth, const double *norm_local = nullptr, double *parts = nullptr)
+{
+    if (!h->p2p.on) return halo_exchange(h, 0, v, depth, norm_local, parts);
+    if (int rc = p2p_barrier_if_dirty(h)) return rc;
+    return p2p_exchange_u(h, v, depth, norm_local);
+}
+
 // fused red-black sweeps whose output also covers `ext_out` halo rows; the input halo is already valid
 int smooth_ca(mgb_gmg *h, int level, int sweeps, double **sol, const double *rhs, double *&scratch, int ext_out,
               double *ucorr = nullptr, double *resid = nullptr, Level *coarse = nullptr)
@@ -700,7 +810,7 @@ int one_iteration_ca(mgb_gmg *h)
     const int dr = ca_resid_depth(h, d);
     const int ext_u = ca_u_depth(h, d);
     trace_mark(h, "start");
-    if (h->u_halo_valid < ext_u && (rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
+    if (h->u_halo_valid < ext_u && (rc = exchange_u(h, F.u, ext_u))) return rc;
     h->u_halo_valid = 0;
     const bool fuse_r1 = ca_fuse_restrict1(h);
     if (fuse_resid(h)) {
@@ -743,7 +853,30 @@ int one_iteration_ca(mgb_gmg *h)
         CK(cudaGetLastError());
     }
     trace_mark(h, "restrict-sharded");
-    // one NCCL group: halo rows of every restricted residual (the smoothers' rhs) + gather of the replicated slab rows
+    // one exchange: halo rows of every restricted residual (the smoothers' rhs) + gather of the replicated slab rows
+    if (h->p2p.on) {
+        if ((rc = p2p_barrier_if_dirty(h))) return rc;
+        const int r = h->cfg.rank, n = h->cfg.n_ranks;
+        mgb::P2PPushBuilder b;
+        for (int l = 1; l <= ls; ++l) {
+            Level &Lv = h->lv[l];
+            const size_t P = (size_t)Lv.g.pitch, cnt = (size_t)d.din[l] * P;
+            if (r > 0) {
+                const Part pp = partition(h->cfg.n, h->cfg.levels, n, r - 1, l);
+                b.seg(Lv.r, peer_vec(h, r - 1, l, 3) + (size_t)pp.rows * P, cnt);
+            }
+            if (r < n - 1) b.seg(Lv.r + (size_t)(Lv.g.rows - d.din[l]) * P, peer_vec(h, r + 1, l, 3) - cnt, cnt);
+        }
+        if (ls + 1 < L) {
+            Level &C = h->lv[ls + 1];
+            const size_t P = (size_t)C.g.pitch;
+            const Part f = partition(h->cfg.n, h->cfg.levels, n, r, ls);
+            const int my0 = (f.row0 + 1) / 2, myn = (f.row0 + f.rows - 1) / 2 - my0 + 1;
+            for (int p = 0; p < n; ++p)
+                if (p != r) b.seg(C.r + (size_t)my0 * P, peer_vec(h, p, ls + 1, 3) + (size_t)my0 * P, (size_t)myn * P);
+        }
+        if ((rc = p2p_launch(h, b, CH_R))) return rc;
+    } else
     {
         const int r = h->cfg.rank, n = h->cfg.n_ranks;
         NK(N.GroupStart());
@@ -824,7 +957,7 @@ int one_iteration_ca(mgb_gmg *h)
         const int np = h->norm_partials;
         h->norm_partials = 0;
         if (h->cfg.defer_norm) {
-            if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;      // for the next iteration's pre-sweeps
+            if ((rc = exchange_u(h, F.u, ext_u))) return rc;            // for the next iteration's pre-sweeps
             h->u_halo_valid = ext_u;
             trace_mark(h, "exchange-u");
             rc = reduce_partials(h, np, 1, true, true);
@@ -834,7 +967,7 @@ int one_iteration_ca(mgb_gmg *h)
             double *local = h->d_scal + 15, *parts = h->d_scal + 16;
             mgb::k_reduce_partials<<<1, 1024, 0, h->st>>>(h->d_partial, np, local);
             count(h, 0.);
-            if ((rc = halo_exchange(h, 0, F.u, ext_u, local, parts))) return rc;
+            if ((rc = exchange_u(h, F.u, ext_u, local, parts))) return rc;
             h->u_halo_valid = ext_u;
             trace_mark(h, "exchange-u+norm");
             mgb::k_sum_ranks<<<1, 32, 0, h->st>>>(parts, local, h->cfg.n_ranks, h->cfg.rank, h->d_scal + 1);
@@ -849,7 +982,7 @@ int one_iteration_ca(mgb_gmg *h)
     if ((rc = finish_cycle(h))) return rc;
     // (6) residual norm of the new iterate (main.cpp:86), all-reduced.  The exchange that feeds it is made deep
     // enough to serve the next iteration's pre-sweeps as well (u does not change in between).
-    if ((rc = halo_exchange(h, 0, F.u, ext_u))) return rc;
+    if ((rc = exchange_u(h, F.u, ext_u))) return rc;
     h->u_halo_valid = ext_u;
     dim3 grid = march_grid(F.g);
     mgb::k_residual<false><<<grid, mgb::kTPB, 0, h->st>>>(F.g, F.u, F.f, nullptr, h->d_partial);
@@ -984,7 +1117,11 @@ int mu_cycle(mgb_gmg *h, int l, int type, bool zero)
 // the configured cycle as an operator on the fine residual: e (level 0) ~= A^-1 r (level 0), r is left untouched
 int cycle_core(mgb_gmg *h, double *coarse_relres, int *coarse_iters, bool fused)
 {
-    if (textbook(h)) return mu_cycle(h, 0, h->cfg.cycle_type, true);
+    if (textbook(h)) {
+        // slabs: the fused smoother reads halo rows of its right-hand side (the sawtooth gets them inside do_restrict)
+        if (int rc = halo_exchange(h, 0, h->lv[0].r, kHalo)) return rc;
+        return mu_cycle(h, 0, h->cfg.cycle_type, true);
+    }
     return sawtooth_core(h, coarse_relres, coarse_iters, fused);
 }
 
@@ -1097,6 +1234,7 @@ int run_iterations(mgb_gmg *h, int cycles)
                 --cycles;
                 continue;
             }
+            if ((rc = p2p_barrier_if_dirty(h))) return rc;       // never inside a capture: the captured exchanges assume clean halos
             auto key = pointer_state(h);
             mgb_gmg::IterGraph *g = nullptr;
             for (auto &c : h->graphs) if (c.key == key) g = &c;
@@ -1431,6 +1569,11 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     size_t w = N;
     const double m_h = cfg->length / (double)(N - 1);                     // domain.cpp:5
     size_t max_partial = 1;
+    for (int r = 0; r < cfg->n_ranks; ++r) h->layouts.push_back(pool_layout(N, L, cfg->n_ranks, r));
+    const PoolLayout &mine = h->layouts[cfg->rank];
+    h->pool_bytes = mine.total;
+    CK(cudaMalloc(&h->pool, h->pool_bytes));
+    CK(cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->st));
     for (int l = 0; l < L; ++l) {
         Level &lv = h->lv[l];
         const double hl = m_h * (double)((size_t)1 << l);                 // domain.hpp:92
@@ -1442,11 +1585,8 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
         lv.g.diag = 4. * cfg->alpha / k;                                  // linear_system.hpp:28
         lv.g.off = -cfg->alpha / k;                                       // linear_system.hpp:38
         lv.elems = (size_t)(lv.g.rows + 2 * kHalo) * lv.g.pitch;
-        for (int v = 0; v < 6; ++v) {
-            if (l > 0 && (v < 2 || v == 5)) continue;                     // u, f, tu exist on level 0 only
-            CK(cudaMalloc(&lv.base[v], lv.elems * sizeof(double)));
-            CK(cudaMemsetAsync(lv.base[v], 0, lv.elems * sizeof(double), h->st));
-        }
+        for (int v = 0; v < 6; ++v)
+            lv.base[v] = mine.off[l][v] == kAbsent ? nullptr : reinterpret_cast<double *>(h->pool + mine.off[l][v]);
         const size_t off = (size_t)kHalo * lv.g.pitch;
         lv.u = lv.base[0] ? lv.base[0] + off : nullptr;
         lv.f = lv.base[1] ? lv.base[1] + off : nullptr;
@@ -1467,10 +1607,18 @@ int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
     }
     h->n_partial = std::max<size_t>(max_partial, 1 << 16);
     CK(cudaMalloc(&h->d_partial, h->n_partial * sizeof(double)));
-    CK(cudaMalloc(&h->d_scal, 96 * sizeof(double)));      // 16 scalars + one part per rank of a sum that rides in an exchange + 16 Krylov scalars
-    CK(cudaMemsetAsync(h->d_scal, 0, 96 * sizeof(double), h->st));
+    // 16 scalars + one part per rank of a sum that rides in an exchange + 16 Krylov scalars: inside the pool header, so that
+    // peers can store their parts of a norm there
+    h->d_scal = reinterpret_cast<double *>(h->pool + kScalOff);
     CK(cudaMallocHost(&h->h_scal, 16 * sizeof(double)));
     CK(cudaStreamSynchronize(h->st));
+    if (cfg->n_ranks > 1) {
+        const char *e = std::getenv("MGB_P2P");
+        if (e && std::atoi(e) == 0) h->p2p.why = "MGB_P2P=0";
+        else h->p2p.init(h->pool, h->pool_bytes, cfg->rank, cfg->n_ranks, h->comm, h->st);
+        if (!h->p2p.on && cfg->rank == 0 && std::getenv("MGB_VERBOSE"))
+            std::fprintf(stderr, "[mgb] slab exchanges use NCCL send/recv (%s)\n", h->p2p.why.c_str());
+    }
     guard.h = nullptr;
     *out = h;
     return MGB_OK;
@@ -1482,12 +1630,17 @@ void mgb_gmg_destroy(mgb_gmg_t h)
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
-    if (h->comm) mgb::nccl().CommDestroy(h->comm);
-    for (auto &lv : h->lv)
-        for (double *p : lv.base) if (p) cudaFree(p);
+    const bool mapped = h->p2p.on;
+    h->p2p.close_peers();
+    if (mapped && h->comm && h->pool) {       // no rank frees its pool while a peer still maps it
+        double *d = reinterpret_cast<double *>(h->pool + kScalOff) + 14;
+        mgb::nccl().AllReduce(d, d, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st);
+        cudaStreamSynchronize(h->st);
+    }
+    if (h->comm) { mgb::nccl().CommDestroy(h->comm); h->comm = nullptr; }
+    if (h->pool) cudaFree(h->pool);
     for (double *p : h->kry) if (p) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
-    if (h->d_scal) cudaFree(h->d_scal);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;

@@ -122,6 +122,30 @@ def main():
             ref.lib.mgb_gmg_set_cycle(ref.h, cfg.smoother, cfg.restriction, cfg.nu, 0.5, 3)
             ref.run_cycles(4)
             report(f"[{mode}] set_cycle(coarse_tol, coarse_maxit) reaches cached graphs", np.array_equal(got, ref.get_u()))
+        g.lib.mgb_gmg_set_cycle(g.h, cfg.smoother, cfg.restriction, cfg.nu, 0.1, 2000)
+        if rank == 0:
+            ref.lib.mgb_gmg_set_cycle(ref.h, cfg.smoother, cfg.restriction, cfg.nu, 0.1, 2000)
+        # (5) the cycle options beyond the sawtooth on slabs: V / W cycles (operator by operator, NCCL halos) and BiCGSTAB
+        # preconditioned by the sawtooth cycle
+        for cyc, name in ((G.CYCLE_V, "V(2,5)"), (G.CYCLE_W, "W(2,5)")):
+            g.set_cycle_type(cyc, 2, 0); g.set_rhs_test(1); g.set_u(None)
+            hist = g.solve(tol=1e-10, maxiter=30)
+            got = assemble(g, n, g.get_u)
+            if rank == 0:
+                ref.set_cycle_type(cyc, 2, 0); ref.set_rhs_test(1); ref.set_u(None)
+                hist_ref = ref.solve(tol=1e-10, maxiter=30)
+                report(f"[{mode}] {name} cycles: solution bit-identical", hist.size == hist_ref.size and np.array_equal(got, ref.get_u()),
+                       f"{hist.size - 1} cycles")
+        g.set_cycle_type(G.CYCLE_SAWTOOTH, 0, 0); g.set_rhs_test(1); g.set_u(None)
+        hist = g.krylov(G.KRYLOV_BICGSTAB, G.PRECOND_MG, tol=1e-10, maxit=20)
+        got = assemble(g, n, g.get_u)
+        if rank == 0:
+            ref.set_cycle_type(G.CYCLE_SAWTOOTH, 0, 0); ref.set_rhs_test(1); ref.set_u(None)
+            hist_ref = ref.krylov(G.KRYLOV_BICGSTAB, G.PRECOND_MG, tol=1e-10, maxit=20)
+            want = ref.get_u()
+            report(f"[{mode}] BiCGSTAB + sawtooth preconditioner: same steps, solution to 1e-9",
+                   hist.size == hist_ref.size and hist[-1] <= 1e-10 and np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want),
+                   f"{hist.size - 1} steps")
         g.close()
         if ref is not None:
             ref.close()
