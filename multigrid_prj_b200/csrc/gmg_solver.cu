@@ -54,8 +54,13 @@ using mgb::LevelGeom;
 
 constexpr int kHalo = 44;            // halo rows kept above and below every slab (deepest need: see plan_depths)
 constexpr int kMaxShardedLevel = 4;  // levels 0..4 may be sharded (see last_sharded_level)
-constexpr int kMinSlabRows = 256;    // a level is sharded while every rank keeps at least this many rows;
-                                     // smaller levels are replicated (cheaper than a latency-bound exchange per operator)
+// a level is sharded while every rank keeps at least this many rows; smaller levels are replicated (cheaper than a
+// latency-bound exchange per operator).  MGB_MIN_SLAB_ROWS overrides (the same value on every rank).
+int min_slab_rows()
+{
+    static const int v = [] { const char *e = std::getenv("MGB_MIN_SLAB_ROWS"); const int x = e ? std::atoi(e) : 0; return x >= 64 ? x : 256; }();
+    return v;
+}
 
 struct Level {
     LevelGeom g{};                    // this rank's view (sharded: its slab; replicated: the whole level)
@@ -77,7 +82,7 @@ int last_sharded_level(size_t n, int levels, int n_ranks)
     int ls = -1;
     size_t w = n;
     for (int l = 0; l < levels; ++l) {
-        if ((w - 1) / (size_t)n_ranks >= (size_t)kMinSlabRows) ls = l; else break;
+        if ((w - 1) / (size_t)n_ranks >= (size_t)min_slab_rows()) ls = l; else break;
         w = (w + 1) / 2;
     }
     // the communication-avoiding schedule recomputes 2^(ls+1) - 1 halo rows of the fine residual for the restriction
@@ -162,7 +167,7 @@ struct mgb_gmg {
     double norm_f = 0.;               // sum f^2 on the fine grid (Residual ctor, solvers.hpp:237-242)
     bool have_rhs = false;
     int n_sm = 148;
-    int stream2_min_rows = 128;       // shortest row chunk the second-generation streaming kernel is used for
+    int stream2_min_rows = 48;        // shortest row chunk the second-generation streaming kernel is used for
     bool no_fused_correction = false; // set while the cycle serves as a preconditioner (its output is e, not u += e)
     double *kry[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fine-level work vectors of mgb_gmg_krylov (allocated on first use)
     int stream_impl = 2;              // generation of the streaming red-black kernel (gmg_stream2.cuh where instantiated; 1 = gmg_kernels.cuh only)
@@ -322,6 +327,13 @@ void pick_chunks(int rows, int nx, int slots, int S, int *rc_out, int *ny_out)
 {
     int rc = rows + (rows & 1), ny = 1;
     double best = 1e300;
+    static const int force_ny = [] { const char *e = std::getenv("MGB_FORCE_NY"); return e ? std::atoi(e) : 0; }();   // measurement only
+    if (force_ny > 0 && rows >= 64 * force_ny) {
+        int c = (rows + force_ny - 1) / force_ny;
+        c += c & 1;
+        *rc_out = c; *ny_out = (rows + c - 1) / c;
+        return;
+    }
     for (int n0 = 1; n0 <= std::max(1, rows / 8); ++n0) {
         int c = (rows + n0 - 1) / n0;
         c += c & 1;

@@ -14,7 +14,14 @@
 //     just updated into slot [s][step mod 3]; half-sweep s+1 reads it two steps later.  Three slots per stage make a
 //     single __syncthreads per row step sufficient (write at step i, read at i+2, overwritten at i+3).
 //   * The right-hand side ring is private to the thread (own column pair only): scaled once on arrival.
-// The first and last few (guarded) steps of a chunk run through the same step function with run-time slot indices.
+// Only the first two steps of a chunk run through the guarded variant of the step function (run-time slot indices).
+// Everything else is the unrolled steady loop, INCLUDING the warm-up and the flush of the pipeline: half-sweeps applied
+// to rows outside the valid trapezoid compute finite garbage (the window, the rhs ring and the landing slots start at
+// zero; rows past the end of the streamed range are re-reads of its last row), and a valid row never reads an invalid
+// one, because garbage moves towards the owned rows by one row per half-sweep -- exactly the S halo rows the chunk
+// streams on either side.  Periods that touch the first or the last row of the domain run a second unrolled variant
+// that knows about Dirichlet rows (BR).  Measured before this change: a chunk paid ~124 steady steps of fixed cost for
+// ~50 guarded steps (profiles/r02_chunk_fit.txt) -- 25 % of a slab launch at 8 GPUs.
 #pragma once
 #include "gmg_common.cuh"
 
@@ -124,7 +131,7 @@ __device__ __forceinline__ double s2_tm_value(uint32_t lo, uint32_t hi)
 // per-thread / per-CTA constants of one launch (all members live in registers or uniform registers)
 struct S2Ctx {
     LevelGeom g, gc;
-    int t, warp, j0, i0, i1, ifirst, ilast, glast, koff, ksteps;
+    int t, warp, j0, i0, i1, ifirst, ilast, glast, koff, ksteps, kend;
     bool first_is_bdry, last_is_bdry, own, bc0, bc1;
     double inv_diag, q0, q1, m0, m1;
     const double *b, *uin;
@@ -155,24 +162,21 @@ template <int S, int MODE, bool PIN>
 __device__ __forceinline__ void s2_issue(const S2Ctx &c, const int k, const int kb, const bool first)
 {
     using L = S2Layout<S, MODE, PIN>;
-    if (k >= c.ksteps) return;
-    const int i = c.ifirst + k;
-    const bool have = i <= c.ilast;
-    if (!have && MODE != 1) return;
+    if (k >= c.kend) return;                         // no step will consume it
+    const int iu = c.ifirst + k;
+    const int i = min(iu, c.ilast);                  // flush steps re-read the last row of the streamed range
     const int slot = kb % kS2D;
     const uint32_t bar = c.sbase + 8u * (uint32_t)(L::off_bar + slot);
-    const uint32_t bytes = (have ? c.f_bytes * (PIN ? 1u : 2u) : 0u) + (MODE == 1 ? c.o_bytes : 0u);
+    const uint32_t bytes = c.f_bytes * (PIN ? 1u : 2u) + (MODE == 1 ? c.o_bytes : 0u);
     s2_mbar_expect_tx(bar, bytes);
-    if (have) {
-        s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lb + slot * kS2TW + c.f_dst), c.b + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
-        if (!PIN)
-            s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lu + slot * kS2TW + c.f_dst), c.uin + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
-    }
+    s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lb + slot * kS2TW + c.f_dst), c.b + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
+    if (!PIN)
+        s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lu + slot * kS2TW + c.f_dst), c.uin + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
     if (MODE == 1) {
-        const int r = min(max(i - 2 * S, c.i0), c.i1 - 1);
+        const int r = min(max(iu - 2 * S, c.i0), c.i1 - 1);
         s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lc + slot * L::OW), c.ucorr + (ptrdiff_t)r * c.P + c.o_lo, c.o_bytes, bar);
     }
-    if (PIN && have) {
+    if (PIN) {
         // coarse row I is first needed by fine row 2I-1 (as its lower neighbour); the very first row also needs its own
         const int gi = c.g.row0 + i;
         const int m = kb >> 1;                       // slot counter of coarse row gi>>1 (koff and the first row are even)
@@ -183,7 +187,7 @@ __device__ __forceinline__ void s2_issue(const S2Ctx &c, const int k, const int 
             s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lu + sc * kS2CW + c.c_dst),
                         c.uin + (ptrdiff_t)((gi >> 1) - c.gc.row0) * c.Pc + c.c_lo, c.c_bytes, barc);
         }
-        if (gi & 1) {
+        if (kb & 1) {                                // parity of the (unclamped) row
             const int sc = (m + 1) % kS2CR;
             const uint32_t barc = c.sbase + 8u * (uint32_t)(L::off_bar + kS2D + sc);
             s2_mbar_expect_tx(barc, c.c_bytes);
@@ -193,19 +197,23 @@ __device__ __forceinline__ void s2_issue(const S2Ctx &c, const int k, const int 
     }
 }
 
-// the same for a row that is known to exist and to need no clamping (every row requested from a steady step)
+// the same from a step of the unrolled loop: every slot index is a compile-time constant
 template <int S, int MODE, bool PIN>
 __device__ __forceinline__ void s2_issue_steady(const S2Ctx &c, const int k, const int kb)
 {
     using L = S2Layout<S, MODE, PIN>;
-    const int i = c.ifirst + k;
+    if (k >= c.kend) return;
+    const int iu = c.ifirst + k;
+    const int i = min(iu, c.ilast);
     const int slot = kb % kS2D;
     const uint32_t bar = c.sbase + 8u * (uint32_t)(L::off_bar + slot);
     s2_mbar_expect_tx(bar, c.f_bytes * (PIN ? 1u : 2u) + (MODE == 1 ? c.o_bytes : 0u));
     s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lb + slot * kS2TW + c.f_dst), c.b + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
     if (!PIN) s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lu + slot * kS2TW + c.f_dst), c.uin + (ptrdiff_t)i * c.P + c.f_lo, c.f_bytes, bar);
-    if (MODE == 1)
-        s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lc + slot * L::OW), c.ucorr + (ptrdiff_t)(i - 2 * S) * c.P + c.o_lo, c.o_bytes, bar);
+    if (MODE == 1) {
+        const int r = min(max(iu - 2 * S, c.i0), c.i1 - 1);
+        s2_bulk_g2s(c.sbase + 8u * (uint32_t)(L::off_lc + slot * L::OW), c.ucorr + (ptrdiff_t)r * c.P + c.o_lo, c.o_bytes, bar);
+    }
     if (PIN && (kb & 1)) {
         const int sc = ((kb >> 1) + 1) % kS2CR;
         const uint32_t barc = c.sbase + 8u * (uint32_t)(L::off_bar + kS2D + sc);
@@ -217,8 +225,9 @@ __device__ __forceinline__ void s2_issue_steady(const S2Ctx &c, const int k, con
 
 // One row step: row i = ifirst + k arrives, half-sweep s (s = 1..S; odd = red, even = black) is applied to row i-2s,
 // row i-2S is final and leaves.  kb = (k + koff) mod R selects every ring slot; in the unrolled steady loop it is a
-// compile-time constant.  GUARD = false: every row touched is an interior row inside the streamed range.
-template <int S, bool EXACT, int MODE, bool PIN, bool GUARD>
+// compile-time constant.  GUARD = false: every half-sweep runs (rows outside the valid trapezoid hold finite garbage that
+// no valid row reads); BR = true adds the test for the first / last row of the domain (Dirichlet rows) to that variant.
+template <int S, bool EXACT, int MODE, bool PIN, bool GUARD, bool BR>
 __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3], double2 (&bw)[kS2TmemB ? 1 : 2 * S + 2], double &acc, uint32_t &phl, uint32_t &phc,
                                         const int k, const int kb, const int kb24, const uint32_t tA, const uint32_t tB)
 {
@@ -248,14 +257,11 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
     }
 
     // ---- the arriving row ----------------------------------------------------------------------------------
-    const bool have = GUARD ? (i <= c.ilast) : true;
     const int sl = kb % kS2D;
-    if (have || MODE == 1) {
-        s2_mbar_wait(c.sbase + 8u * (uint32_t)(L::off_bar + sl), (phl >> sl) & 1u);
-        phl ^= 1u << sl;
-    }
+    s2_mbar_wait(c.sbase + 8u * (uint32_t)(L::off_bar + sl), (phl >> sl) & 1u);
+    phl ^= 1u << sl;
     double2 nb = make_double2(0., 0.), nu = make_double2(0., 0.);
-    if (have) {
+    {
         nb = ld2(sm + L::off_lb + sl * TW + 2 * t);
         if (!PIN) nu = ld2(sm + L::off_lu + sl * TW + 2 * t);
         else {
@@ -274,7 +280,7 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
     }
     if (!EXACT) {
         // the ring holds bq = b/diag (b itself on Dirichlet points): u = bq + q * (sum of neighbours), q = 1/4 or 0
-        if (GUARD) {
+        if (GUARD || BR) {
             const bool brow = (i + g.row0 == 0) || (i == c.glast);
             nb.x = (c.bc0 || brow) ? nb.x : nb.x * c.inv_diag;
             nb.y = (c.bc1 || brow) ? nb.y : nb.y * c.inv_diag;
@@ -354,6 +360,10 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
             act = (r >= vlo) && (r <= vhi);
             brow = (r + g.row0 == 0) || (r == c.glast);
             isb = isb || brow;
+        } else if (BR) {
+            const int r = i - d;
+            brow = (r + g.row0 == 0) || (r == c.glast);
+            isb = isb || brow;
         }
         const double up = which ? uw[d + 1].y : uw[d + 1].x;
         const double dn = which ? uw[d - 1].y : uw[d - 1].x;
@@ -365,7 +375,7 @@ __device__ __forceinline__ void s2_step(const S2Ctx &c, double2 (&uw)[2 * S + 3]
             nv = isb ? bv[s - 1] : nv;
         } else {
             double q = which ? c.q1 : c.q0;
-            if (GUARD) q = brow ? 0. : q;
+            if (GUARD || BR) q = brow ? 0. : q;
             nv = fma(q, (up + dn) + (left + right), bv[s - 1]);
         }
         if (act) {
@@ -518,11 +528,11 @@ k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restri
         const int Jc = min(max(c.j0 >> 1, 0), gc.w - 1), Jc1 = min(Jc + 1, gc.w - 1);
         c.kc0 = Jc - cs_al; c.kc1 = Jc1 - cs_al;
     }
-    // steady steps: every half-sweep row is an interior row inside the streamed range, the arriving row exists
-    const int k_lo = c.first_is_bdry ? 2 * S + 1 : 3 * S;
-    const int k_s0 = k_lo + (k_lo & 1);               // even, so that the row parity is a compile-time constant per unrolled step
-    const int k_hi = c.ilast - 1 - ifirst - (kS2D - 1);    // ... and so does the row requested from it
+    // two guarded steps (the first coarse row of the interpolating variant has its own wait), then whole unrolled periods
+    // until the last row has left; requests stop at kend, so no copy is in flight when the CTA exits
+    const int k_s0 = 2;
     c.koff = (kS2RB - k_s0 % kS2RB) % kS2RB;        // (k + koff) mod 24 = slot of the rhs ring, mod 12 = every other slot
+    c.kend = k_s0 + ((max(c.ksteps - k_s0, 0) + R - 1) / R) * R;
 
     // zero the whole buffer once (pads and the parts of edge tiles that no copy covers must hold finite values)
     for (int x = t; x < L::n_doubles; x += kS2NT) s2_smem[x] = 0.;
@@ -547,6 +557,9 @@ k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restri
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         c.tb = tm_base + ((uint32_t)(t & 96) << 16);      // lanes 32*(warp % 4) .. +31 belong to this warp
+        // the ring starts at zero: the warm-up steps read rows that never arrived
+        for (int x = 0; x < kS2RB; ++x) s2_tm_st4(c.tb + 4u * (uint32_t)x, 0., 0.);
+        s2_tm_wait_st();
     }
 
     double2 uw[2 * S + 3];
@@ -558,16 +571,21 @@ k_rb_stream2(LevelGeom g, const double *__restrict__ uin, const double *__restri
     double acc = 0.;
     uint32_t phl = 0, phc = 0;
     int k = 0;
-    const int k_pro = min(k_s0, c.ksteps);
-    for (; k < k_pro; ++k) s2_step<S, EXACT, MODE, PIN, true>(c, uw, bw, acc, phl, phc, k, (k + c.koff) % R, (k + c.koff) % kS2RB, 0u, 0u);
-    uint32_t tA = c.tb, tB = c.tb;                    // the first steady step has (k + koff) mod 24 == 0
-    for (; k + R - 1 <= k_hi; k += R) {
+    for (; k < k_s0; ++k) s2_step<S, EXACT, MODE, PIN, true, false>(c, uw, bw, acc, phl, phc, k, (k + c.koff) % R, (k + c.koff) % kS2RB, 0u, 0u);
+    uint32_t tA = c.tb, tB = c.tb;                    // the first unrolled step has (k + koff) mod 24 == 0
+    for (; k < c.kend; k += R) {
+        // rows ifirst + k - 2S - 2 .. ifirst + k + R - 1 are touched in this period: does it see a Dirichlet row?
+        const int lo_g = g.row0 + ifirst + k - 2 * S - 2, hi_g = g.row0 + ifirst + k + R - 1;
+        if (lo_g <= 0 || hi_g >= g.w - 1) {
 #pragma unroll
-        for (int cc = 0; cc < R; ++cc) s2_step<S, EXACT, MODE, PIN, false>(c, uw, bw, acc, phl, phc, k + cc, cc, 0, tA, tB);
+            for (int cc = 0; cc < R; ++cc) s2_step<S, EXACT, MODE, PIN, false, true>(c, uw, bw, acc, phl, phc, k + cc, cc, 0, tA, tB);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < R; ++cc) s2_step<S, EXACT, MODE, PIN, false, false>(c, uw, bw, acc, phl, phc, k + cc, cc, 0, tA, tB);
+        }
         tA = (tA == c.tb) ? c.tb + 4u * R : c.tb;
         tB = (tB == c.tb) ? c.tb - 4u * R : c.tb;
     }
-    for (; k < c.ksteps; ++k) s2_step<S, EXACT, MODE, PIN, true>(c, uw, bw, acc, phl, phc, k, (k + c.koff) % R, (k + c.koff) % kS2RB, 0u, 0u);
 
     if (MODE == 1) {
         const double tsum = block_sum(acc, red);
