@@ -271,6 +271,40 @@ def amg_config5(device, peak, side, levels, rank, world, dist, cycles=10, reps=1
     return out
 
 
+def dropin_leg(n, levels, value):
+    """the reference's UNMODIFIED driver (GeometricMultigrid/src/main.cpp, compiled against the facade headers by
+    multigrid_prj_b200/dropin/Makefile) on the same problem, fast mode: DoF/s from its own "Solving elapsed time" line.
+    Its loop runs until 1e-11 or 1000 iterations (main.cpp:80-90); at 8193^2 the fp64 floor of the problem is 6e-11, so it
+    runs all 1000.  The timed region of the driver includes the first-touch upload of f and u from pageable host vectors."""
+    import re
+    import shutil
+    exe = os.path.join(ROOT, "multigrid_prj_b200", "dropin", "_build", "Multigrid")
+    if not os.path.exists(exe):
+        return {"error": "drop-in driver not built (needs the reference sources at build time)"}
+    d = tempfile.mkdtemp(prefix="mgb_dropin_")
+    try:
+        t0 = time.perf_counter()
+        p = subprocess.run([exe, "-n", str(n), "-a", str(int(ALPHA)), "-w", str(int(LENGTH)), "-ml", str(levels), "-test", str(TEST), "-smt", "0"],
+                           cwd=d, capture_output=True, text=True, timeout=600, env=dict(os.environ, MGB_GMG_MODE="fast"))
+        wall = time.perf_counter() - t0
+        if p.returncode != 0:
+            return {"error": f"driver exited with {p.returncode}: {p.stderr[-300:]}"}
+        m = re.search(r"Solving elapsed time: ([0-9.eE+-]+) sec", p.stdout)
+        hist = open(os.path.join(d, "MGGS4.txt")).read().split()
+        iters = int(hist[0]) - 1
+        secs = float(m.group(1))
+        v = float(n) * n * iters / secs
+        return {"value": v, "unit": UNIT, "iterations": iters, "solve_seconds": secs, "wall_seconds": wall, "final_relres": float(hist[-1]),
+                "fraction_of_value": v / value if value else None,
+                "what": f"multigrid_prj_b200/dropin/_build/Multigrid -n {n} -a {int(ALPHA)} -w {int(LENGTH)} -ml {levels} -test {TEST} -smt 0 with "
+                        "MGB_GMG_MODE=fast: the reference's own main.cpp; every `u * GS * GS * MG0; u * RES` of its loop is one "
+                        "mgb_gmg_iterate call (lazy operator queue of the facade), the norm is read back every iteration"}
+    except Exception as e:                                   # noqa: BLE001 -- a reported leg, never fails the bench
+        return {"error": repr(e)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -363,6 +397,7 @@ def main():
     ap.add_argument("--amg-levels", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the single-GPU repeat + checksum comparison")
     ap.add_argument("--no-c4", action="store_true", help="N=1: skip the 16385^2 single-GPU line")
+    ap.add_argument("--no-dropin", action="store_true", help="N=1: skip the run of the reference's own driver against the facade")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -584,6 +619,10 @@ def main():
                   "cycles": args.warmup + 4 + args.steps,
                   "what": "GMG 2D Poisson 16385x16385, L=14 (BASELINE configs[3]) on ONE B200: the N=1 point of the slab runs' grid"}
 
+    dropin = None
+    if rank == 0 and world == 1 and args.mode == "fast" and not args.no_dropin:
+        dropin = dropin_leg(n, L, value)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -598,7 +637,7 @@ def main():
                     "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "parity": parity,
-            "value_deferred_norm": deferred, "c4_single_gpu": c4, "amg": amg,
+            "value_deferred_norm": deferred, "c4_single_gpu": c4, "dropin": dropin, "amg": amg,
         }
         print(json.dumps(line))
     if dist is not None:

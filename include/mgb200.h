@@ -194,6 +194,13 @@ int mgb_gmg_fmg(mgb_gmg_t h);
  * hist[0] = ||f - A u|| / ||f|| on entry, then one entry per iteration (maxit + 1 doubles); stops at hist <= tol. */
 int mgb_gmg_krylov(mgb_gmg_t h, int method, int precond, double tol, int maxit, double *hist, int *n_hist);
 
+/* ONE iteration of the driver loop (main.cpp:84-86: n_pre pre-sweeps, one cycle, the residual norm) as a single cached
+ * CUDA-graph launch on the fast path -- what `u * GS * GS * MG; u * RES; RES.Norm()` amounts to.  *sumsq = sum (f - A u)^2
+ * of the new iterate; on the fused path it is the norm the last launch leaves, and values whose relative size is below
+ * confirm_below are re-evaluated by a true f - A u pass (see mgb_gmg_solve).  *coarse_relres = the value the reference
+ * prints per cycle (multigrid.hpp:131).  The facade's lazy operator queue dispatches to this. */
+int mgb_gmg_iterate(mgb_gmg_t h, double confirm_below, double *sumsq, double *coarse_relres);
+
 /* runs exactly `cycles` driver iterations without any host readback; writes the final relative
  * residual.  This is the timed region of bench.py. */
 int mgb_gmg_run_cycles(mgb_gmg_t h, int cycles, double *final_relres);

@@ -72,6 +72,7 @@ SYMBOLS = {
     "mgb_gmg_cycle": (_i, [_vp, _pd, _pi]),
     "mgb_gmg_fine_leg": (_i, [_vp, _pd]),
     "mgb_gmg_solve": (_i, [_vp, _d, _i, _i, _vp, _pi]),
+    "mgb_gmg_iterate": (_i, [_vp, _d, _pd, _pd]),
     "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),
     "mgb_gmg_checksum": (_i, [_vp, _i, _i, C.POINTER(C.c_uint64)]),
     "mgb_gmg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),

@@ -185,6 +185,13 @@ struct mgb_gmg {
         int end_u_halo_valid; bool end_r0_ready, end_r1_ready;     // host-side state one replay leaves behind
     };
     std::vector<IterGraph> graphs;
+    // graphs of ONE driver iteration (mgb_gmg_iterate): valid in the pointer state `key`, leave the state `end`
+    struct StepGraph {
+        std::vector<const double *> key; cudaGraphExec_t exec; uint64_t launches; double bytes;
+        std::vector<double *> end;              // u, tu, e, t of every level after the iteration
+        bool end_r0_ready, end_r1_ready;
+    };
+    std::vector<StepGraph> step_graphs;
 
     double **vec(int level, int which)
     {
@@ -1474,6 +1481,51 @@ int do_krylov(mgb_gmg *h, int method, int precond, double tol, int maxit, double
     return MGB_OK;
 }
 
+// One driver iteration (main.cpp:84-86) as a cached CUDA graph of exactly one iteration: the out-of-place kernels leave the
+// buffer roles swapped, so a graph is valid in the pointer state it was captured in and moves the handle to the state it
+// recorded; two graphs alternate.  This is what the facade's `u * GS * GS * MG; u * RES` dispatches to.
+int iterate_once(mgb_gmg *h)
+{
+    const bool graph_ok = h->cfg.use_graph && h->lt >= 0 && h->cfg.n_ranks == 1;
+    if (!graph_ok) return one_iteration(h);
+    auto key = pointer_state(h);
+    mgb_gmg::StepGraph *g = nullptr;
+    for (auto &c : h->step_graphs) if (c.key == key) g = &c;
+    auto pointers = [&] {
+        std::vector<double *> v;
+        for (auto &lv : h->lv) { v.push_back(lv.u); v.push_back(lv.tu); v.push_back(lv.e); v.push_back(lv.t); }
+        return v;
+    };
+    if (!g) {
+        const mgb_gmg_stats before = h->stats;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+        const int rc = one_iteration(h);
+        const cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+        mgb_gmg::StepGraph ng{key, nullptr, h->stats.kernel_launches - before.kernel_launches,
+                              h->stats.bytes_algorithmic - before.bytes_algorithmic, pointers(), h->r0_ready, h->r1_ready};
+        h->stats = before;                       // capturing executes nothing
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        CK(cudaGraphInstantiate(&ng.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        h->step_graphs.push_back(ng);
+        g = &h->step_graphs.back();              // the host-side state already is the end state
+    } else {
+        size_t i = 0;
+        for (auto &lv : h->lv) { lv.u = g->end[i++]; lv.tu = g->end[i++]; lv.e = g->end[i++]; lv.t = g->end[i++]; }
+        h->r0_ready = g->end_r0_ready; h->r1_ready = g->end_r1_ready;
+    }
+    CK(cudaGraphLaunch(g->exec, h->st));
+    h->stats.graph_launches++;
+    h->stats.kernel_launches += g->launches;
+    h->stats.bytes_algorithmic += g->bytes;
+    h->stats.cycles += 1;
+    h->u_halo_valid = 0;
+    h->norm_partials = 0;
+    return MGB_OK;
+}
+
 int after_rhs(mgb_gmg *h)
 {
     int rc;
@@ -1642,6 +1694,7 @@ void mgb_gmg_destroy(mgb_gmg_t h)
     cudaSetDevice(h->cfg.device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto &g : h->step_graphs) cudaGraphExecDestroy(g.exec);
     const bool mapped = h->p2p.on;
     h->p2p.close_peers();
     if (mapped && h->comm && h->pool) {       // no rank frees its pool while a peer still maps it
@@ -1900,6 +1953,34 @@ int mgb_gmg_solve(mgb_gmg_t h, double tol, int maxiter, int check_every, double 
         }
     }
     *n_hist = n;
+    return MGB_OK;
+}
+
+int mgb_gmg_iterate(mgb_gmg_t h, double confirm_below, double *sumsq, double *coarse_relres)
+{
+    if (!h) return fail(MGB_ERR_ARG, "null handle");
+    if (!h->have_rhs) return fail(MGB_ERR_STATE, "set the right-hand side first");
+    CK(cudaSetDevice(h->cfg.device));
+    Level &F = h->lv[0];
+    int rc;
+    if ((rc = iterate_once(h))) return rc;
+    double ss = 0.;
+    if (h->scal_local & 2u) {
+        double t = 0.;
+        if ((rc = read_scalar(h, 1, &ss)) || (rc = read_scalar(h, 4, &t))) return rc;
+    } else {
+        // the norm (slot 1) and the tail's coarse residual (slot 4) in one copy and one synchronisation
+        CK(cudaMemcpyAsync(h->h_scal + 1, h->d_scal + 1, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        ss = h->h_scal[1];
+    }
+    // the fused norm under-reports near the rounding floor of f - A u (see mgb_gmg_solve): small values are confirmed
+    if (fuse_corr(h) && std::sqrt(ss / h->norm_f) < confirm_below) {
+        if ((rc = do_residual(h, 0, F.u, F.f, nullptr, 1))) return rc;
+        if ((rc = read_scalar(h, 1, &ss))) return rc;
+    }
+    if (sumsq) *sumsq = ss;
+    if (coarse_relres) *coarse_relres = h->lt >= 0 ? h->h_scal[4] : 0.;
     return MGB_OK;
 }
 

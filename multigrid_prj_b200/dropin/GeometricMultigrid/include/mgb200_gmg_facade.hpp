@@ -14,6 +14,12 @@
 // Set MGB_FACADE_EAGER=1 to copy back after every operator (slow, but valid for callers that read the
 // vector between operator calls).  MGB_GMG_MODE=fast maps Gauss_Seidel_iteration to red-black GS and the
 // cycle's restriction to full weighting (the B200 fast path); the default reproduces the reference.
+//
+// Lazy operator queue (fast mode).  The driver's iteration `u * GS * GS * MG0; u * RES; RES.Norm()` (main.cpp:85-87) is
+// recognised as a whole: the two pre-sweeps and the cycle are only QUEUED, and the residual call that follows dispatches
+// the four operators as ONE library call (mgb_gmg_iterate: fused pre-sweeps + residual + restriction, the cycle with its
+// fused correction + norm, one cached CUDA graph, one 32-byte read-back).  Any other use of the context (another operator,
+// another vector, a download) first runs whatever is queued operator by operator, so results never depend on the queue.
 #ifndef MGB200_GMG_FACADE_HPP
 #define MGB200_GMG_FACADE_HPP
 
@@ -69,6 +75,12 @@ struct Context {
     mgb_gmg_t h = nullptr;
     Slot U, F, E[32], R[32];
     std::vector<double> scratch;
+    // lazy queue (fast mode): pre-sweeps on (U, F) and one cycle waiting for the residual call that completes the iteration
+    int pend_gs = 0;
+    bool pend_mg = false;
+    int pend_kind = 0, pend_restriction = 0;
+    bool res0_stale = false;          // R(0) should hold f - A u of the current u but was not written (fused iteration)
+    bool in_pending = false;
 
     ~Context() { if (h) mgb_gmg_destroy(h); }
 
@@ -78,6 +90,7 @@ struct Context {
     void ensure()
     {
         if (h && levels >= want_levels) return;
+        run_pending();
         flush_all();
         if (h) { mgb_gmg_destroy(h); h = nullptr; U = F = Slot(); for (auto &s : E) s = Slot(); for (auto &s : R) s = Slot(); }
         mgb_gmg_config c;
@@ -87,8 +100,32 @@ struct Context {
         ok(mgb_gmg_create(&c, &h));
         levels = want_levels;
     }
+    // runs the queued operators one by one (the unfused equivalents of what mgb_gmg_iterate would have done)
+    void run_pending()
+    {
+        if (!h || in_pending || (!pend_gs && !pend_mg)) return;
+        in_pending = true;
+        const int n = pend_gs;
+        const bool mg = pend_mg;
+        pend_gs = 0; pend_mg = false;
+        for (int i = 0; i < n; ++i) ok(mgb_gmg_smooth(h, 0, MGB_SMOOTH_GS_RB, 1, MGB_VEC_U, MGB_VEC_F));
+        if (mg) {
+            ok(mgb_gmg_set_cycle(h, pend_kind, pend_restriction, 5, 1.e-1, 2000));
+            double coarse = 0.;
+            ok(mgb_gmg_cycle(h, &coarse, nullptr));
+            std::cout << "Achieved residual on coarse grid: " << coarse << std::endl;      // multigrid.hpp:131
+        }
+        if (n || mg) U.dirty = true;
+        in_pending = false;
+    }
     void download(int which, int level)
     {
+        run_pending();
+        if (which == MGB_VEC_R && level == 0 && res0_stale && h) {
+            double ss = 0.;
+            ok(mgb_gmg_residual(h, 0, MGB_VEC_U, MGB_VEC_F, 1, &ss));
+            res0_stale = false;
+        }
         Slot &s = slot(which, level);
         if (!s.dirty || !s.host) return;
         const size_t w = width(level), st = (size_t)1 << level;
@@ -118,6 +155,7 @@ struct Context {
         ensure();
         Slot &s = slot(which, level);
         if (s.owner == owner) return;
+        run_pending();
         download(which, level);
         upload(which, level, host);
         s.owner = owner; s.host = host; s.dirty = false;
@@ -317,6 +355,12 @@ void smooth(PoissonMatrix<double> &A, Vector &b, std::vector<double> &sol, int k
     c.bind(rhs, l, &b, HostData<Vector>::get(b));
     c.bind(sl, l, &sol, sol.data());
     if (kind == MGB_SMOOTH_GS_LEX && fast_mode()) kind = MGB_SMOOTH_GS_RB;
+    if (fast_mode() && !eager() && kind == MGB_SMOOTH_GS_RB && l == 0 && rhs == MGB_VEC_F && !c.pend_mg && c.pend_gs < 2) {
+        c.pend_gs++;                      // queued: see "Lazy operator queue" above
+        c.slot(sl, l).dirty = true;
+        return;
+    }
+    c.run_pending();
     ok(mgb_gmg_smooth(c.h, l, kind, 1, sl, rhs));
     c.touched(sl, l);
 }
@@ -390,6 +434,7 @@ public:
         const int l = m_A.level();
         const int rhs = (detail::RhsRole<Vector>::which == MGB_VEC_F && l == 0) ? MGB_VEC_F : MGB_VEC_R;
         c.bind(rhs, l, &b, detail::HostData<Vector>::get(b));
+        c.run_pending();
         detail::ok(mgb_gmg_sumsq(c.h, l, rhs, &norm_of_b));
     }
     void apply_iteration_to_vec(std::vector<double> &sol)                                        // solvers.hpp:257-296
@@ -401,6 +446,24 @@ public:
         c.bind(rhs, l, &b, detail::HostData<Vector>::get(b));
         c.bind(sl, l, &sol, sol.data());
         const bool store = saveVector && rhs == MGB_VEC_F;       // the stored residual becomes the level's R vector
+        if (c.pend_mg && c.pend_gs == 2 && l == 0 && rhs == MGB_VEC_F) {
+            // the whole driver iteration in one call: 2 pre-sweeps, the cycle and this norm (main.cpp:85-87)
+            c.pend_gs = 0; c.pend_mg = false;
+            detail::ok(mgb_gmg_set_cycle(c.h, c.pend_kind, c.pend_restriction, 5, 1.e-1, 2000));
+            double coarse = 0.;
+            detail::ok(mgb_gmg_iterate(c.h, 4. * TOL, &norm, &coarse));
+            std::cout << "Achieved residual on coarse grid: " << coarse << std::endl;      // multigrid.hpp:131
+            c.slot(MGB_VEC_U, 0).dirty = true;
+            if (store) {
+                detail::Slot &s = c.slot(MGB_VEC_R, 0);
+                if (s.owner != m_res) { s.owner = m_res; s.host = m_res->data(); }
+                s.dirty = true;
+                c.res0_stale = true;      // written only when somebody asks for it (Context::download)
+            }
+            return;
+        }
+        c.run_pending();
+        if (store) c.res0_stale = false;
         detail::ok(mgb_gmg_residual(c.h, l, sl, rhs, store ? 1 : 0, &norm));
         if (store) {
             detail::Slot &s = c.slot(MGB_VEC_R, l);
@@ -461,6 +524,7 @@ public:
         detail::Context &c = m_A_inf.ctx();
         const int lc = m_A_inf.level();
         c.bind(MGB_VEC_E, lc, &vec, vec.data());
+        c.run_pending();
         detail::ok(mgb_gmg_prolong(c.h, lc));
         detail::Slot &s = c.slot(MGB_VEC_E, lc - 1);
         if (s.owner != &vec) { c.download(MGB_VEC_E, lc - 1); s.owner = &vec; s.host = vec.data(); }
@@ -483,8 +547,11 @@ public:
     SawtoothMGIteration(std::vector<PoissonMatrix<double>> &matrices, Vector &knownVec) : A_level(matrices), b(knownVec)
     {
         // res, err, the per-level smoothers, interpolators and the coarse solver of the reference's constructor
-        // (multigrid.hpp:108-124) all live inside the device hierarchy
-        A_level.front().ctx();
+        // (multigrid.hpp:108-124) all live inside the device hierarchy: it is created here, as the reference builds its
+        // hierarchy here, and the right-hand side goes to the device with it (the driver's "Initialization time")
+        detail::Context &c = A_level.front().ctx();
+        c.want_levels = std::max(c.want_levels, (int)A_level.size());
+        c.bind(MGB_VEC_F, 0, &b, detail::HostData<Vector>::get(b));
     }
     ~SawtoothMGIteration() { detail::flush_everything(); }
     void apply_iteration_to_vec(std::vector<double> &sol)
@@ -496,6 +563,11 @@ public:
         int kind = detail::SmootherKind<Smoother>::value;
         int restriction = MGB_RESTRICT_INJECTION;
         if (detail::fast_mode()) { kind = MGB_SMOOTH_GS_RB; restriction = MGB_RESTRICT_FULL_WEIGHTING; }
+        if (detail::fast_mode() && !detail::eager() && c.pend_gs == 2 && !c.pend_mg) {
+            c.pend_mg = true; c.pend_kind = kind; c.pend_restriction = restriction;   // queued: the residual call dispatches it
+            return;
+        }
+        c.run_pending();
         detail::ok(mgb_gmg_set_cycle(c.h, kind, restriction, 5, 1.e-1, 2000));        // multigrid.hpp:105,123
         double coarse = 0.;
         detail::ok(mgb_gmg_cycle(c.h, &coarse, nullptr));

@@ -202,6 +202,12 @@ class Gmg:
         check(self.lib.mgb_gmg_krylov(self.h, method, precond, tol, maxit, self._ptr(hist), C.byref(n)))
         return hist[:n.value].copy()
 
+    def iterate(self, confirm_below=0.0):
+        """one driver iteration as one library call: (sum of squares of the new residual, coarse relative residual)"""
+        ss, cr = C.c_double(), C.c_double()
+        check(self.lib.mgb_gmg_iterate(self.h, confirm_below, C.byref(ss), C.byref(cr)))
+        return ss.value, cr.value
+
     def run_cycles(self, cycles, want_relres=True):
         rel = C.c_double()
         check(self.lib.mgb_gmg_run_cycles(self.h, cycles, C.byref(rel) if want_relres else None))

@@ -98,3 +98,24 @@ def test_reference_debugtest_driver_two_level_masked_gs(tmp_path):
     assert abs(before - expect) <= 2e-6 * expect, (before, expect)
     assert abs(before - 47.3984) < 0.5            # the value the reference prints (random hierarchy there)
     assert after < 1e-8
+
+
+@pytest.mark.parametrize("n,ml", [(257, 8), (1025, 10)])
+def test_lazy_operator_queue_equals_operator_by_operator(tmp_path, n, ml):
+    """fast mode: `u * GS * GS * MG0; u * RES` dispatched as ONE fused library call (mgb_gmg_iterate) against the same
+    driver with MGB_FACADE_EAGER=1 (every operator its own call): same number of cycles, same printed coarse residuals,
+    histories equal to the 6 digits the files keep (the fused norm differs from the true residual pass by rounding only)"""
+    args = f"-n {n} -a 1 -w 10 -ml {ml} -test 1 -smt 0".split()
+    (tmp_path / "lazy").mkdir(); (tmp_path / "eager").mkdir()
+    out_l, hist_l, x_l = run_gmg(tmp_path / "lazy", args, env={"MGB_GMG_MODE": "fast"})
+    out_e, hist_e, x_e = run_gmg(tmp_path / "eager", args, env={"MGB_GMG_MODE": "fast", "MGB_FACADE_EAGER": "1"})
+    hl = np.array([float(t) for t in hist_l.split()[1:]]); he = np.array([float(t) for t in hist_e.split()[1:]])
+    assert hl.size == he.size and hl[-1] <= 1e-11
+    assert np.allclose(hl[hl > 1e-9], he[he > 1e-9], rtol=2e-5)
+    ul = np.array([float(t) for t in x_l.split()[1:]]); ue = np.array([float(t) for t in x_e.split()[1:]])
+    assert np.allclose(ul, ue, rtol=2e-5, atol=1e-12)
+    cl = [l for l in out_l.splitlines() if l.startswith("Achieved residual")]
+    ce = [l for l in out_e.splitlines() if l.startswith("Achieved residual")]
+    assert len(cl) == len(ce) == hl.size - 1
+    # the printed coarse residual of the first cycles (later ones are ratios of rounding-level numbers)
+    assert all(abs(float(a.split(":")[1]) - float(b.split(":")[1])) <= 1e-3 * float(b.split(":")[1]) + 1e-12 for a, b in zip(cl[:4], ce[:4]))
