@@ -572,9 +572,12 @@ def main():
         g.sync(); barrier()
         t0 = time.perf_counter()
         check(g.lib.mgb_gmg_set_rhs(g.h, fptr))
+        t1 = time.perf_counter()
         check(g.lib.mgb_gmg_set_u(g.h, None))            # u0 = 0 (main.cpp:49): NULL = zero-fill on the device, nothing to upload
         check(g.lib.mgb_gmg_solve(g.h, 0.0, args.steps, 1, hist.ctypes.data_as(C.c_void_p), C.byref(nh)))
+        t2 = time.perf_counter()
         check(g.lib.mgb_gmg_get_u(g.h, uptr))
+        t3 = time.perf_counter()
         barrier()
         dt = time.perf_counter() - t0
         if dist is not None:
@@ -584,7 +587,7 @@ def main():
         slab_bytes = float(rows) * n * 8
         e2e = {"value": dof * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": slab_bytes / args.steps, "d2h_bytes_per_step": slab_bytes / args.steps + 8,
-               "seconds": dt, "pcie_floor_note": "the two slab copies alone take ~2 x slab_bytes / 50 GB/s; the solve is PCIe-bound below ~40 steps",
+               "seconds": dt, "phases_s": {"set_rhs": t1 - t0, "set_u+solve": t2 - t1, "get_u": t3 - t2}, "pcie_floor_note": "the two slab copies alone take ~2 x slab_bytes / 50 GB/s; the solve is PCIe-bound below ~40 steps",
                "what": f"per rank: mgb_gmg_set_rhs (pinned host slab -> HBM), mgb_gmg_set_u(NULL) (u0 = 0: device fill), mgb_gmg_solve with "
                        f"{args.steps} steps each reading its residual norm back, mgb_gmg_get_u (HBM -> pinned host); "
                        f"wall clock, max over ranks; bytes are per rank", "final_relres": float(hist[nh.value - 1])}

@@ -252,9 +252,8 @@ typedef struct mgb_amg_config {
                               multicolour sweep equals the single-GPU sweep bit for bit; 1: once per sweep ("hybrid"
                               Gauss-Seidel: Jacobi-like across block boundaries, one exchange instead of n_colours) */
     int shard_min_rows;    /* a level is cut into row blocks while it keeps at least this many rows per rank; smaller
-                              levels are replicated on every rank (<= 0: 262144).  A ghost exchange costs ~25 us (measured,
-                              2 B200): sharding pays only where half a sweep saves more than that, i.e. above ~0.5 M rows
-                              per rank for the hybrid smoother; the 2-GPU runs of round 1 used 16384 */
+                              levels are replicated on every rank (<= 0: 131072).  A ghost exchange costs ~15 us by peer stores
+                              (p2p = 1) and 40-60 us by NCCL on 8 B200: sharding pays only where the sweep time saved exceeds that */
     double jacobi_omega;   /* MGB_SMOOTH_JACOBI: x <- x + omega (D^-1 (b - (A - D) x) - x); the reference is omega = 1
                               (<= 0 is read as 1) */
     int tail_max_rows;     /* north_star item 3: the trailing levels whose row count is <= this (and that are not sharded)
@@ -277,9 +276,11 @@ typedef struct mgb_amg_config {
                               Multicolour GS / Jacobi-type smoothers only. */
     int coarse_smoother;   /* smoother of the levels >= 1 in mgb_amg_apply / mgb_amg_solve: 0 = the same as `smoother`, else a
                               MGB_SMOOTH_* id (fast path: MGB_SMOOTH_L1_JACOBI -- the Galerkin levels need 13-16 colours) */
-    int p2p;               /* row-block sharded runs: 1 = ghost entries move by direct peer stores over NVLink into the peers'
-                              identically indexed vectors + flag handshakes (one small kernel pair per exchange) instead of
-                              pack / ncclSend / ncclRecv / unpack; needs peer access between all GPUs of the box.  0 = NCCL */
+    int p2p;               /* row-block sharded runs: 1 (default) = ghost entries move by direct peer stores over NVLink into a
+                              double-buffered staging area of the rank that needs them (pools exported through CUDA IPC, one push
+                              kernel + one flag wait + one unpack per exchange, csrc/p2p.cuh) instead of pack / ncclSend /
+                              ncclRecv / unpack; falls back to NCCL when the pools cannot be mapped.  0 = NCCL.
+                              The environment variable MGB_P2P=0 forces NCCL for GMG slabs and AMG row blocks alike */
     int reserved[1];
 } mgb_amg_config;
 

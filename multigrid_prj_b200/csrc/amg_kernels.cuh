@@ -16,6 +16,7 @@
 // Gauss-Seidel from an on-device greedy (Jones-Plassmann) colouring.
 #pragma once
 #include <cooperative_groups.h>
+#include "p2p.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -401,6 +402,78 @@ k_amg_unpack(double *__restrict__ v, const int *__restrict__ idx, const double *
 {
     const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (t < last) v[idx[t]] = buf[t];
+}
+
+// The same exchange over NVLink peer stores (csrc/p2p.cuh): entry t of the send list goes straight into the staging buffer of
+// the rank that needs it -- peer[t] names the rank, off[t] the slot inside that rank's receive list -- and the last CTA
+// publishes this rank's new sequence number in the headers of all peers.  Two staging halves alternate by sequence parity,
+// so a rank that runs one exchange ahead never overwrites entries a peer is still unpacking.
+struct AmgPush {
+    double *stage[kP2PMaxRanks];                  // staging buffer (both halves) of every rank, as mapped here
+    unsigned long long *sig[kP2PMaxRanks];        // flags[this rank][0] in the header of every other rank
+    int n_sig;
+    unsigned long long half;                      // doubles per staging half
+    unsigned long long *seq;                      // this rank's push_seq[0]
+    unsigned int *done;                           // this rank's done[0]
+};
+__global__ void __launch_bounds__(256)
+k_amg_push(const __grid_constant__ AmgPush a, const double *__restrict__ v, const int *__restrict__ idx,
+           const unsigned char *__restrict__ peer, const int *__restrict__ off, int first, int last)
+{
+    const unsigned long long buf = ((*a.seq + 1ull) & 1ull) * a.half;     // read before the last CTA bumps it
+    for (int t = first + blockIdx.x * blockDim.x + threadIdx.x; t < last; t += gridDim.x * blockDim.x)
+        a.stage[peer[t]][buf + (unsigned long long)off[t]] = v[idx[t]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(a.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence_system();
+            *a.done = 0u;
+            const unsigned long long s = *a.seq + 1ull;
+            *a.seq = s;
+            for (int i = 0; i < a.n_sig; ++i) st_release_sys(a.sig[i], s);
+        }
+    }
+}
+// contiguous variant: this rank's block [r0, r1) of a vector goes to slot r0.. of every other rank's staging buffer
+__global__ void __launch_bounds__(256)
+k_amg_push_block(const __grid_constant__ AmgPush a, const double *__restrict__ v, int r0, int r1, int me, int n_ranks)
+{
+    const unsigned long long buf = ((*a.seq + 1ull) & 1ull) * a.half;
+    for (int t = r0 + blockIdx.x * blockDim.x + threadIdx.x; t < r1; t += gridDim.x * blockDim.x) {
+        const double x = v[t];
+        for (int p = 0; p < n_ranks; ++p)
+            if (p != me) a.stage[p][buf + (unsigned long long)t] = x;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(a.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence_system();
+            *a.done = 0u;
+            const unsigned long long s = *a.seq + 1ull;
+            *a.seq = s;
+            for (int i = 0; i < a.n_sig; ++i) st_release_sys(a.sig[i], s);
+        }
+    }
+}
+// after k_p2p_wait: entries [first, last) of the receive list leave the staging half of the exchange just completed
+__global__ void __launch_bounds__(256)
+k_amg_unpack_stage(double *__restrict__ v, const int *__restrict__ idx, const double *__restrict__ stage, unsigned long long half,
+                   const unsigned long long *__restrict__ wait_seq, int first, int last)
+{
+    const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < last) v[idx[t]] = stage[(*wait_seq & 1ull) * half + (unsigned long long)t];
+}
+// the blocks of the other ranks, [0, r0) and [r1, n), from the staging half into the vector
+__global__ void __launch_bounds__(256)
+k_amg_unpack_blocks(double *__restrict__ v, const double *__restrict__ stage, unsigned long long half,
+                    const unsigned long long *__restrict__ wait_seq, int r0, int r1, int n)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && (t < r0 || t >= r1)) v[t] = stage[(*wait_seq & 1ull) * half + (unsigned long long)t];
 }
 
 // ---- on-device greedy colouring (Jones-Plassmann rounds) ------------------------------------------------------------

@@ -257,10 +257,18 @@ struct HaloPlan {
     int n_groups = 1, n_ranks = 1;
     std::vector<int> send_ptr, send_idx, recv_ptr, recv_idx;       // ptr: n_groups * n_ranks + 1
     int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+    // peer-store transport (csrc/p2p.cuh): for every entry of the send list the rank that needs it and its slot in that
+    // rank's receive list
+    unsigned char *d_send_peer = nullptr;
+    int *d_send_off = nullptr;
     int n_send() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
     int n_recv() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
     bool empty() const { return n_send() == 0 && n_recv() == 0; }
-    void release() { cudaFree(d_send_idx); cudaFree(d_recv_idx); d_send_idx = d_recv_idx = nullptr; }
+    void release()
+    {
+        cudaFree(d_send_idx); cudaFree(d_recv_idx); cudaFree(d_send_peer); cudaFree(d_send_off);
+        d_send_idx = d_recv_idx = d_send_off = nullptr; d_send_peer = nullptr;
+    }
 };
 
 void order_segments(int n_groups, int n_ranks, int n_cols, const int *group_of_col, std::vector<int> &entries /* (index) */,
@@ -348,6 +356,11 @@ struct mgb_amg {
     int rank = 0, n_ranks = 1;
     mgb::NcclComm comm = nullptr;
     double *d_send = nullptr, *d_recv = nullptr;      // packed ghost entries
+    // peer-store transport: one exported pool per rank = [header][two staging halves of the receive buffer]
+    char *pool = nullptr;
+    size_t pool_bytes = 0, stage_half = 0;
+    mgb::P2PComm p2p;
+    mgb::AmgPush push{};                              // what every push launch needs: the peers' staging buffers and flags
     double omega = 1.0;
     int lt = -1;                                      // first level of the persistent coarse tail (-1: none)
     int coop_max_blocks = 0;                          // co-resident CTAs of k_amg_sell_gs_sweeps (0: no cooperative launch)
@@ -564,10 +577,110 @@ int upload_plan(HaloPlan &H)
     return MGB_OK;
 }
 
+
+// peer-store transport: where the entries of my send list land in the receive lists of the others.  Segment (g, me) of
+// rank p's receive list holds exactly my send segment (g, p), in the same ascending order (halo_plan), so only the
+// segment offsets of the other ranks are needed: one all-gather of the recv_ptr tables per plan.
+int plan_p2p(mgb_amg *h, HaloPlan &H)
+{
+    const int R = h->n_ranks, me = h->rank;
+    if (H.send_ptr.empty()) return MGB_OK;
+    const int nseg = H.n_groups * R, len = nseg + 1;
+    int *d = nullptr;
+    ACK(cudaMalloc(&d, sizeof(int) * (size_t)len * (R + 1)));
+    ACK(cudaMemcpyAsync(d + (size_t)len * R, H.recv_ptr.data(), sizeof(int) * (size_t)len, cudaMemcpyHostToDevice, h->st));
+    ANK(mgb::nccl().AllGather(d + (size_t)len * R, d, sizeof(int) * (size_t)len, mgb::kNcclUint8, h->comm, h->st));
+    std::vector<int> all((size_t)len * R);
+    ACK(cudaMemcpyAsync(all.data(), d, sizeof(int) * (size_t)len * R, cudaMemcpyDeviceToHost, h->st));
+    ACK(cudaStreamSynchronize(h->st));
+    cudaFree(d);
+    const int ns = H.n_send();
+    std::vector<unsigned char> peer((size_t)std::max(ns, 1));
+    std::vector<int> off((size_t)std::max(ns, 1));
+    for (int g = 0; g < H.n_groups; ++g)
+        for (int p = 0; p < R; ++p) {
+            const int q = g * R + p, cnt = H.send_ptr[q + 1] - H.send_ptr[q];
+            const int *theirs = all.data() + (size_t)p * len;
+            if (cnt != theirs[g * R + me + 1] - theirs[g * R + me])
+                return mgb_set_error(MGB_ERR_STATE, "ghost plans of two ranks disagree");
+            for (int k = 0; k < cnt; ++k) { peer[H.send_ptr[q] + k] = (unsigned char)p; off[H.send_ptr[q] + k] = theirs[g * R + me] + k; }
+        }
+    if (ns) {
+        ACK(cudaMalloc(&H.d_send_peer, (size_t)ns));
+        ACK(cudaMalloc(&H.d_send_off, sizeof(int) * (size_t)ns));
+        ACK(cudaMemcpy(H.d_send_peer, peer.data(), (size_t)ns, cudaMemcpyHostToDevice));
+        ACK(cudaMemcpy(H.d_send_off, off.data(), sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice));
+    }
+    return MGB_OK;
+}
+
+// allocates and exports the pool, maps the peers', prepares every plan; leaves the NCCL transport in place on any failure
+int setup_p2p(mgb_amg *h, size_t max_halo)
+{
+    size_t half = max_halo;
+    for (size_t l = 1; l < h->lv.size(); ++l)
+        if (h->lv[l - 1].sharded && !h->lv[l].sharded) half = std::max(half, (size_t)h->lv[l].A.n_rows);   // all-gathered level
+    half = (half + 63) / 64 * 64;
+    const size_t MB2 = (size_t)2 << 20;
+    h->stage_half = half;
+    h->pool_bytes = std::max((mgb::kP2PHeaderBytes + 2 * half * sizeof(double) + MB2 - 1) / MB2 * MB2, 2 * MB2);
+    ACK(cudaMalloc(&h->pool, h->pool_bytes));
+    ACK(cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->st));
+    h->p2p.init(h->pool, h->pool_bytes, h->rank, h->n_ranks, h->comm, h->st);
+    if (!h->p2p.on) return MGB_OK;
+    mgb::AmgPush &a = h->push;
+    a = mgb::AmgPush{};
+    for (int p = 0; p < h->n_ranks; ++p) {
+        a.stage[p] = h->p2p.at<double>(p, mgb::kP2PHeaderBytes);
+        if (p != h->rank) a.sig[a.n_sig++] = &h->p2p.hdr(p)->flags[h->rank][0];
+    }
+    a.half = half;
+    a.seq = &h->p2p.hdr(h->rank)->push_seq[0];
+    a.done = &h->p2p.hdr(h->rank)->done[0];
+    int rc;
+    for (auto &L : h->lv) {
+        if (!L.sharded) continue;
+        if ((rc = plan_p2p(h, L.haloA)) || (rc = plan_p2p(h, L.haloA_colour)) || (rc = plan_p2p(h, L.haloR)) || (rc = plan_p2p(h, L.haloP))) return rc;
+    }
+    return MGB_OK;
+}
+
 // refresh the ghost entries of `v` listed in groups [g0, g1) of the plan: pack -> grouped ncclSend/ncclRecv -> unpack,
 // all on the compute stream
+// the same over NVLink peer stores: entries go straight into the staging half of the rank that needs them, every rank
+// signals every rank and waits for every rank (no rank runs more than one exchange ahead: two staging halves suffice)
+int p2p_finish(mgb_amg *h)
+{
+    mgb::P2PHeader *hd = h->p2p.hdr(h->rank);
+    unsigned mask = 0;
+    for (int p = 0; p < h->n_ranks; ++p) if (p != h->rank) mask |= 1u << p;
+    mgb::k_p2p_wait<<<1, 32, 0, h->st>>>(hd, 0, mask);
+    h->stats.kernel_launches++;
+    return MGB_OK;
+}
+int exchange_p2p(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
+{
+    const int R = h->n_ranks;
+    const bool have = !H.send_ptr.empty();
+    const int s0 = have ? H.send_ptr[g0 * R] : 0, s1 = have ? H.send_ptr[g1 * R] : 0;
+    const int r0 = have ? H.recv_ptr[g0 * R] : 0, r1 = have ? H.recv_ptr[g1 * R] : 0;
+    const int grid = std::max(1, std::min((s1 - s0 + 255) / 256, 296));
+    mgb::k_amg_push<<<grid, 256, 0, h->st>>>(h->push, v, H.d_send_idx, H.d_send_peer, H.d_send_off, s0, s1);
+    tally(h, 12. * (s1 - s0));
+    p2p_finish(h);
+    if (r1 > r0) {
+        mgb::k_amg_unpack_stage<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
+                                                                         (unsigned long long)h->stage_half,
+                                                                         &h->p2p.hdr(h->rank)->wait_seq[0], r0, r1);
+        tally(h, 12. * (r1 - r0));
+    }
+    ACK(cudaGetLastError());
+    return MGB_OK;
+}
+
 int exchange(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
 {
+    if (h->n_ranks > 1 && h->p2p.on) return exchange_p2p(h, H, g0, g1, v);
     if (h->n_ranks == 1 || H.empty()) return MGB_OK;
     const int R = H.n_ranks;
     const int s0 = H.send_ptr[g0 * R], s1 = H.send_ptr[g1 * R], r0 = H.recv_ptr[g0 * R], r1 = H.recv_ptr[g1 * R];
@@ -604,6 +717,18 @@ int allgather_blocks(mgb_amg *h, int n, double *v)
     if (h->n_ranks == 1) return MGB_OK;
     auto &N = mgb::nccl();
     const Block mine = block_of(n, h->n_ranks, h->rank);
+    if (h->p2p.on && (size_t)n <= h->stage_half) {
+        const int grid = std::max(1, std::min((mine.size() + 255) / 256, 296));
+        mgb::k_amg_push_block<<<grid, 256, 0, h->st>>>(h->push, v, mine.r0, mine.r1, h->rank, h->n_ranks);
+        tally(h, 8. * mine.size() * (h->n_ranks - 1));
+        p2p_finish(h);
+        mgb::k_amg_unpack_blocks<<<(n + 255) / 256, 256, 0, h->st>>>(v, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
+                                                                    (unsigned long long)h->stage_half, &h->p2p.hdr(h->rank)->wait_seq[0],
+                                                                    mine.r0, mine.r1, n);
+        tally(h, 16. * (n - mine.size()));
+        ACK(cudaGetLastError());
+        return MGB_OK;
+    }
     ANK(N.GroupStart());
     for (int p = 0; p < h->n_ranks; ++p) {
         if (p == h->rank) continue;
@@ -884,7 +1009,7 @@ int build_levels_device(mgb_amg *h, size_t &max_blocks, size_t &max_halo)
 {
     const mgb_amg_config *cfg = &h->cfg;
     const int n_ranks = h->n_ranks, rank = h->rank;
-    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 262144;
+    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 131072;
     if (cfg->exact_order) return mgb_set_error(MGB_ERR_ARG, "device_setup = 1 runs the fast kernels only (exact_order = 0)");
     if (cfg->smoother == MGB_SMOOTH_GS_LEX)
         return mgb_set_error(MGB_ERR_ARG, "device_setup = 1: lexicographic Gauss-Seidel needs the host-built level schedule");
@@ -1024,7 +1149,7 @@ int build_levels_host(mgb_amg *h, size_t n, const int64_t *ptr, const int64_t *c
 {
     const mgb_amg_config *cfg = &h->cfg;
     const int n_ranks = h->n_ranks, rank = h->rank;
-    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 262144;
+    const int min_rows = cfg->shard_min_rows > 0 ? cfg->shard_min_rows : 131072;
     h->lv.resize(cfg->levels);
     // level 0: CSRMatrix::copy_from drops exact zeros (CSRMatrix.cpp:13-14); rows must be column-sorted (they come from a map)
     {
@@ -1164,6 +1289,12 @@ int create_common(const mgb_amg_config *cfg, int rank, int n_ranks, const unsign
     if (n_ranks > 1) {
         ACK(cudaMalloc(&h->d_send, sizeof(double) * max_halo));
         ACK(cudaMalloc(&h->d_recv, sizeof(double) * max_halo));
+        const char *e = std::getenv("MGB_P2P");
+        if (cfg->p2p && !(e && std::atoi(e) == 0)) {
+            if (int rc = setup_p2p(h, max_halo)) return rc;
+            if (!h->p2p.on && rank == 0 && std::getenv("MGB_VERBOSE"))
+                std::fprintf(stderr, "[mgb] AMG ghost exchanges use NCCL send/recv (%s)\n", h->p2p.why.c_str());
+        }
     }
     ACK(cudaMalloc(&h->d_partial, sizeof(double) * max_blocks));
     ACK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
@@ -1188,7 +1319,8 @@ void mgb_amg_config_default(mgb_amg_config *c)
     c->device = 0;
     for (int i = 0; i < 16; ++i) c->start_index[i] = -1;                   // -1: n/2 (the reference draws it at random)
     c->hybrid_gs = 0;
-    c->shard_min_rows = 262144;
+    c->p2p = 1;                     // ghost exchanges by NVLink peer stores where the pools can be mapped (else NCCL)
+    c->shard_min_rows = 131072;     // an exchange costs ~15 us by peer stores (~60 us by NCCL: then 262144 pays better)
     c->jacobi_omega = 1.0;                                                 // the reference's smoothers are unweighted
     c->tail_max_rows = 4000;
 }
@@ -1276,7 +1408,17 @@ void mgb_amg_destroy(mgb_amg_t h)
         L.haloA.release(); L.haloA_colour.release(); L.haloR.release(); L.haloP.release();
         cudaFree(L.diag); cudaFree(L.x); cudaFree(L.b); cudaFree(L.tmp); cudaFree(L.dl1); cudaFree(L.b0); cudaFree(L.d_colour); cudaFree(L.d_cf);
     }
-    cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFree(h->d_send); cudaFree(h->d_recv);
+    cudaFree(h->d_partial); cudaFree(h->d_send); cudaFree(h->d_recv);
+    {
+        const bool mapped = h->p2p.on;
+        h->p2p.close_peers();
+        if (mapped && h->comm && h->d_scal) {     // no rank frees its pool while a peer still maps it
+            mgb::nccl().AllReduce(h->d_scal + 3, h->d_scal + 3, 1, mgb::kNcclFloat64, mgb::kNcclSum, h->comm, h->st);
+            cudaStreamSynchronize(h->st);
+        }
+        if (h->pool) cudaFree(h->pool);
+    }
+    cudaFree(h->d_scal);
     if (h->comm) mgb::nccl().CommDestroy(h->comm);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->st) cudaStreamDestroy(h->st);

@@ -63,7 +63,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_p2p_push(const __grid_constant__ P2PPush a)
 {
     const int total = a.first_item[a.nseg];
@@ -98,7 +98,7 @@ k_p2p_push(const __grid_constant__ P2PPush a)
 }
 
 // waits until flags[src][channel] >= (++wait_seq[channel]) for every src in `mask`
-__global__ void k_p2p_wait(P2PHeader *h, int channel, unsigned int mask)
+static __global__ void k_p2p_wait(P2PHeader *h, int channel, unsigned int mask)
 {
     const int src = threadIdx.x;
     const unsigned long long expect = h->wait_seq[channel] + 1ull;

@@ -16,7 +16,7 @@ def _ngpu():
     return load().mgb_device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_results_equal_single_rank(world):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
