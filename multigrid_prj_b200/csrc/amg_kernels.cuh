@@ -404,76 +404,99 @@ k_amg_unpack(double *__restrict__ v, const int *__restrict__ idx, const double *
     if (t < last) v[idx[t]] = buf[t];
 }
 
-// The same exchange over NVLink peer stores (csrc/p2p.cuh): entry t of the send list goes straight into the staging buffer of
-// the rank that needs it -- peer[t] names the rank, off[t] the slot inside that rank's receive list -- and the last CTA
-// publishes this rank's new sequence number in the headers of all peers.  Two staging halves alternate by sequence parity,
-// so a rank that runs one exchange ahead never overwrites entries a peer is still unpacking.
+// The same exchange over NVLink peer stores (csrc/p2p.cuh), neighbour to neighbour: entry t of the send list goes straight
+// into the staging buffer of the rank that needs it -- peer[t] names the rank, off[t] the slot inside that rank's receive
+// list.  Two ranks are PEERS of an exchange when either sends the other anything in it; every rank signals its peers (an
+// empty signal where it has nothing to send) and waits for them, nobody else.  Each directed pair counts its messages:
+// the count is the flag value, and its parity selects the staging half, so a rank that runs one exchange ahead of a peer
+// writes the half the peer is not unpacking; it cannot run two ahead, because the peer's next signal comes after its unpack.
 struct AmgPush {
     double *stage[kP2PMaxRanks];                  // staging buffer (both halves) of every rank, as mapped here
-    unsigned long long *sig[kP2PMaxRanks];        // flags[this rank][0] in the header of every other rank
-    int n_sig;
+    unsigned long long *sig[kP2PMaxRanks];        // flags[this rank][0] in the header of rank p
     unsigned long long half;                      // doubles per staging half
-    unsigned long long *seq;                      // this rank's push_seq[0]
+    unsigned long long *pair_push;                // this rank's pair_push[]
     unsigned int *done;                           // this rank's done[0]
+    int n_ranks, me;
 };
-__global__ void __launch_bounds__(256)
-k_amg_push(const __grid_constant__ AmgPush a, const double *__restrict__ v, const int *__restrict__ idx,
-           const unsigned char *__restrict__ peer, const int *__restrict__ off, int first, int last)
+__device__ __forceinline__ void amg_push_tail(const AmgPush &a, unsigned mask)
 {
-    const unsigned long long buf = ((*a.seq + 1ull) & 1ull) * a.half;     // read before the last CTA bumps it
-    for (int t = first + blockIdx.x * blockDim.x + threadIdx.x; t < last; t += gridDim.x * blockDim.x)
-        a.stage[peer[t]][buf + (unsigned long long)off[t]] = v[idx[t]];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(a.done, 1u);
-        if (prev == gridDim.x - 1) {
+        if (prev == gridDim.x - 1) {              // the last CTA: every CTA's stores are fenced before its atomicAdd
             __threadfence_system();
             *a.done = 0u;
-            const unsigned long long s = *a.seq + 1ull;
-            *a.seq = s;
-            for (int i = 0; i < a.n_sig; ++i) st_release_sys(a.sig[i], s);
+            for (int p = 0; p < a.n_ranks; ++p)
+                if ((mask >> p) & 1u) {
+                    const unsigned long long s = a.pair_push[p] + 1ull;
+                    a.pair_push[p] = s;
+                    st_release_sys(a.sig[p], s);
+                }
         }
     }
+}
+__global__ void __launch_bounds__(256)
+k_amg_push(const __grid_constant__ AmgPush a, const double *__restrict__ v, const int *__restrict__ idx,
+           const unsigned char *__restrict__ peer, const int *__restrict__ off, int first, int last, unsigned mask)
+{
+    for (int t = first + blockIdx.x * blockDim.x + threadIdx.x; t < last; t += gridDim.x * blockDim.x) {
+        const int p = peer[t];
+        const unsigned long long buf = ((a.pair_push[p] + 1ull) & 1ull) * a.half;     // read before the last CTA bumps it
+        a.stage[p][buf + (unsigned long long)off[t]] = v[idx[t]];
+    }
+    amg_push_tail(a, mask);
 }
 // contiguous variant: this rank's block [r0, r1) of a vector goes to slot r0.. of every other rank's staging buffer
 __global__ void __launch_bounds__(256)
-k_amg_push_block(const __grid_constant__ AmgPush a, const double *__restrict__ v, int r0, int r1, int me, int n_ranks)
+k_amg_push_block(const __grid_constant__ AmgPush a, const double *__restrict__ v, int r0, int r1, unsigned mask)
 {
-    const unsigned long long buf = ((*a.seq + 1ull) & 1ull) * a.half;
     for (int t = r0 + blockIdx.x * blockDim.x + threadIdx.x; t < r1; t += gridDim.x * blockDim.x) {
         const double x = v[t];
-        for (int p = 0; p < n_ranks; ++p)
-            if (p != me) a.stage[p][buf + (unsigned long long)t] = x;
+        for (int p = 0; p < a.n_ranks; ++p)
+            if (p != a.me) a.stage[p][((a.pair_push[p] + 1ull) & 1ull) * a.half + (unsigned long long)t] = x;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(a.done, 1u);
-        if (prev == gridDim.x - 1) {
-            __threadfence_system();
-            *a.done = 0u;
-            const unsigned long long s = *a.seq + 1ull;
-            *a.seq = s;
-            for (int i = 0; i < a.n_sig; ++i) st_release_sys(a.sig[i], s);
+    amg_push_tail(a, mask);
+}
+// waits for one more message from every rank in `mask`
+__global__ void k_amg_wait(P2PHeader *h, unsigned mask)
+{
+    const int src = threadIdx.x;
+    if (src < kP2PMaxRanks && ((mask >> src) & 1u)) {
+        const unsigned long long expect = h->pair_wait[src] + 1ull;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned int spins = 0;
+        while (ld_acquire_sys(&h->flags[src][0]) < expect) {
+            if ((++spins & 1023u) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) { atomicExch(&h->error, 1u + (unsigned)src); break; }
+            }
         }
+        h->pair_wait[src] = expect;
     }
 }
-// after k_p2p_wait: entries [first, last) of the receive list leave the staging half of the exchange just completed
+// after k_amg_wait: entries [first, last) of the receive list leave the staging half their sender used (src[t] = the sender)
 __global__ void __launch_bounds__(256)
-k_amg_unpack_stage(double *__restrict__ v, const int *__restrict__ idx, const double *__restrict__ stage, unsigned long long half,
-                   const unsigned long long *__restrict__ wait_seq, int first, int last)
+k_amg_unpack_stage(double *__restrict__ v, const int *__restrict__ idx, const unsigned char *__restrict__ src,
+                   const double *__restrict__ stage, unsigned long long half, const unsigned long long *__restrict__ pair_wait,
+                   int first, int last)
 {
     const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < last) v[idx[t]] = stage[(*wait_seq & 1ull) * half + (unsigned long long)t];
+    if (t < last) v[idx[t]] = stage[(pair_wait[src[t]] & 1ull) * half + (unsigned long long)t];
 }
-// the blocks of the other ranks, [0, r0) and [r1, n), from the staging half into the vector
+// the blocks of the other ranks from the staging halves into the vector; start[p] = first entry of rank p's block
+struct AmgBlocks { int start[kP2PMaxRanks + 1]; };
 __global__ void __launch_bounds__(256)
 k_amg_unpack_blocks(double *__restrict__ v, const double *__restrict__ stage, unsigned long long half,
-                    const unsigned long long *__restrict__ wait_seq, int r0, int r1, int n)
+                    const unsigned long long *__restrict__ pair_wait, const __grid_constant__ AmgBlocks b, int n_ranks, int me)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n && (t < r0 || t >= r1)) v[t] = stage[(*wait_seq & 1ull) * half + (unsigned long long)t];
+    if (t >= b.start[n_ranks]) return;
+    int p = 0;
+    while (t >= b.start[p + 1]) ++p;
+    if (p != me) v[t] = stage[(pair_wait[p] & 1ull) * half + (unsigned long long)t];
 }
 
 // ---- on-device greedy colouring (Jones-Plassmann rounds) ------------------------------------------------------------

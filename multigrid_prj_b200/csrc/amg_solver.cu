@@ -259,15 +259,15 @@ struct HaloPlan {
     int *d_send_idx = nullptr, *d_recv_idx = nullptr;
     // peer-store transport (csrc/p2p.cuh): for every entry of the send list the rank that needs it and its slot in that
     // rank's receive list
-    unsigned char *d_send_peer = nullptr;
+    unsigned char *d_send_peer = nullptr, *d_recv_src = nullptr;
     int *d_send_off = nullptr;
     int n_send() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
     int n_recv() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
     bool empty() const { return n_send() == 0 && n_recv() == 0; }
     void release()
     {
-        cudaFree(d_send_idx); cudaFree(d_recv_idx); cudaFree(d_send_peer); cudaFree(d_send_off);
-        d_send_idx = d_recv_idx = d_send_off = nullptr; d_send_peer = nullptr;
+        cudaFree(d_send_idx); cudaFree(d_recv_idx); cudaFree(d_send_peer); cudaFree(d_send_off); cudaFree(d_recv_src);
+        d_send_idx = d_recv_idx = d_send_off = nullptr; d_send_peer = d_recv_src = nullptr;
     }
 };
 
@@ -605,6 +605,15 @@ int plan_p2p(mgb_amg *h, HaloPlan &H)
                 return mgb_set_error(MGB_ERR_STATE, "ghost plans of two ranks disagree");
             for (int k = 0; k < cnt; ++k) { peer[H.send_ptr[q] + k] = (unsigned char)p; off[H.send_ptr[q] + k] = theirs[g * R + me] + k; }
         }
+    const int nr = H.n_recv();
+    if (nr) {
+        std::vector<unsigned char> src((size_t)nr);
+        for (int g = 0; g < H.n_groups; ++g)
+            for (int p = 0; p < R; ++p)
+                for (int k = H.recv_ptr[g * R + p]; k < H.recv_ptr[g * R + p + 1]; ++k) src[k] = (unsigned char)p;
+        ACK(cudaMalloc(&H.d_recv_src, (size_t)nr));
+        ACK(cudaMemcpy(H.d_recv_src, src.data(), (size_t)nr, cudaMemcpyHostToDevice));
+    }
     if (ns) {
         ACK(cudaMalloc(&H.d_send_peer, (size_t)ns));
         ACK(cudaMalloc(&H.d_send_off, sizeof(int) * (size_t)ns));
@@ -632,11 +641,12 @@ int setup_p2p(mgb_amg *h, size_t max_halo)
     a = mgb::AmgPush{};
     for (int p = 0; p < h->n_ranks; ++p) {
         a.stage[p] = h->p2p.at<double>(p, mgb::kP2PHeaderBytes);
-        if (p != h->rank) a.sig[a.n_sig++] = &h->p2p.hdr(p)->flags[h->rank][0];
+        a.sig[p] = &h->p2p.hdr(p)->flags[h->rank][0];
     }
     a.half = half;
-    a.seq = &h->p2p.hdr(h->rank)->push_seq[0];
+    a.pair_push = h->p2p.hdr(h->rank)->pair_push;
     a.done = &h->p2p.hdr(h->rank)->done[0];
+    a.n_ranks = h->n_ranks; a.me = h->rank;
     int rc;
     for (auto &L : h->lv) {
         if (!L.sharded) continue;
@@ -647,31 +657,28 @@ int setup_p2p(mgb_amg *h, size_t max_halo)
 
 // refresh the ghost entries of `v` listed in groups [g0, g1) of the plan: pack -> grouped ncclSend/ncclRecv -> unpack,
 // all on the compute stream
-// the same over NVLink peer stores: entries go straight into the staging half of the rank that needs them, every rank
-// signals every rank and waits for every rank (no rank runs more than one exchange ahead: two staging halves suffice)
-int p2p_finish(mgb_amg *h)
-{
-    mgb::P2PHeader *hd = h->p2p.hdr(h->rank);
-    unsigned mask = 0;
-    for (int p = 0; p < h->n_ranks; ++p) if (p != h->rank) mask |= 1u << p;
-    mgb::k_p2p_wait<<<1, 32, 0, h->st>>>(hd, 0, mask);
-    h->stats.kernel_launches++;
-    return MGB_OK;
-}
+// the same over NVLink peer stores, neighbour to neighbour (amg_kernels.cuh: k_amg_push / k_amg_wait / k_amg_unpack_stage)
 int exchange_p2p(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
 {
     const int R = h->n_ranks;
-    const bool have = !H.send_ptr.empty();
-    const int s0 = have ? H.send_ptr[g0 * R] : 0, s1 = have ? H.send_ptr[g1 * R] : 0;
-    const int r0 = have ? H.recv_ptr[g0 * R] : 0, r1 = have ? H.recv_ptr[g1 * R] : 0;
+    if (H.send_ptr.empty()) return MGB_OK;                    // no plan: no rank has one
+    const int s0 = H.send_ptr[g0 * R], s1 = H.send_ptr[g1 * R], r0 = H.recv_ptr[g0 * R], r1 = H.recv_ptr[g1 * R];
+    unsigned mask = 0;                                         // peers: either direction carries something in these groups
+    for (int g = g0; g < g1; ++g)
+        for (int p = 0; p < R; ++p) {
+            const int q = g * R + p;
+            if (H.send_ptr[q + 1] > H.send_ptr[q] || H.recv_ptr[q + 1] > H.recv_ptr[q]) mask |= 1u << p;
+        }
+    if (!mask) return MGB_OK;
     const int grid = std::max(1, std::min((s1 - s0 + 255) / 256, 296));
-    mgb::k_amg_push<<<grid, 256, 0, h->st>>>(h->push, v, H.d_send_idx, H.d_send_peer, H.d_send_off, s0, s1);
+    mgb::k_amg_push<<<grid, 256, 0, h->st>>>(h->push, v, H.d_send_idx, H.d_send_peer, H.d_send_off, s0, s1, mask);
     tally(h, 12. * (s1 - s0));
-    p2p_finish(h);
+    mgb::P2PHeader *hd = h->p2p.hdr(h->rank);
+    mgb::k_amg_wait<<<1, 32, 0, h->st>>>(hd, mask);
+    h->stats.kernel_launches++;
     if (r1 > r0) {
-        mgb::k_amg_unpack_stage<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
-                                                                         (unsigned long long)h->stage_half,
-                                                                         &h->p2p.hdr(h->rank)->wait_seq[0], r0, r1);
+        mgb::k_amg_unpack_stage<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, H.d_recv_src, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
+                                                                         (unsigned long long)h->stage_half, hd->pair_wait, r0, r1);
         tally(h, 12. * (r1 - r0));
     }
     ACK(cudaGetLastError());
@@ -718,13 +725,18 @@ int allgather_blocks(mgb_amg *h, int n, double *v)
     auto &N = mgb::nccl();
     const Block mine = block_of(n, h->n_ranks, h->rank);
     if (h->p2p.on && (size_t)n <= h->stage_half) {
+        unsigned mask = 0;
+        mgb::AmgBlocks bl{};
+        for (int p = 0; p < h->n_ranks; ++p) { if (p != h->rank) mask |= 1u << p; bl.start[p] = block_of(n, h->n_ranks, p).r0; }
+        bl.start[h->n_ranks] = n;
         const int grid = std::max(1, std::min((mine.size() + 255) / 256, 296));
-        mgb::k_amg_push_block<<<grid, 256, 0, h->st>>>(h->push, v, mine.r0, mine.r1, h->rank, h->n_ranks);
+        mgb::k_amg_push_block<<<grid, 256, 0, h->st>>>(h->push, v, mine.r0, mine.r1, mask);
         tally(h, 8. * mine.size() * (h->n_ranks - 1));
-        p2p_finish(h);
+        mgb::P2PHeader *hd = h->p2p.hdr(h->rank);
+        mgb::k_amg_wait<<<1, 32, 0, h->st>>>(hd, mask);
+        h->stats.kernel_launches++;
         mgb::k_amg_unpack_blocks<<<(n + 255) / 256, 256, 0, h->st>>>(v, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
-                                                                    (unsigned long long)h->stage_half, &h->p2p.hdr(h->rank)->wait_seq[0],
-                                                                    mine.r0, mine.r1, n);
+                                                                    (unsigned long long)h->stage_half, hd->pair_wait, bl, h->n_ranks, h->rank);
         tally(h, 16. * (n - mine.size()));
         ACK(cudaGetLastError());
         return MGB_OK;

@@ -37,6 +37,10 @@ struct P2PHeader {                        // at offset 0 of every rank's pool
     unsigned int done[kP2PChannels];
     unsigned int error;
     unsigned long long magic;
+    // neighbour-only protocol (AMG ghost exchanges): messages sent to / consumed from every other rank so far; the flag a
+    // rank publishes in flags[src][0] of a peer is its pair_push count for that peer
+    unsigned long long pair_push[kP2PMaxRanks];
+    unsigned long long pair_wait[kP2PMaxRanks];
 };
 static_assert(sizeof(P2PHeader) <= 4096, "header layout");
 
