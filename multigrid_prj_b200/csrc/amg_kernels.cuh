@@ -408,10 +408,11 @@ k_amg_unpack(double *__restrict__ v, const int *__restrict__ idx, const double *
 // into the staging buffer of the rank that needs it -- peer[t] names the rank, off[t] the slot inside that rank's receive
 // list.  Two ranks are PEERS of an exchange when either sends the other anything in it; every rank signals its peers (an
 // empty signal where it has nothing to send) and waits for them, nobody else.  Each directed pair counts its messages:
-// the count is the flag value, and its parity selects the staging half, so a rank that runs one exchange ahead of a peer
-// writes the half the peer is not unpacking; it cannot run two ahead, because the peer's next signal comes after its unpack.
+// the count is the flag value, and its parity selects the half of the staging REGION THAT BELONGS TO THAT PAIR (every
+// receiver keeps one region per sender), so a rank that runs one message ahead of a peer writes the half the peer is not
+// unpacking; it cannot run two ahead, because the peer's next signal to it comes after that unpack.
 struct AmgPush {
-    double *stage[kP2PMaxRanks];                  // staging buffer (both halves) of every rank, as mapped here
+    double *stage[kP2PMaxRanks];                  // the region of rank p's staging buffer that receives from THIS rank (both halves)
     unsigned long long *sig[kP2PMaxRanks];        // flags[this rank][0] in the header of rank p
     unsigned long long half;                      // doubles per staging half
     unsigned long long *pair_push;                // this rank's pair_push[]
@@ -454,7 +455,7 @@ k_amg_push_block(const __grid_constant__ AmgPush a, const double *__restrict__ v
     for (int t = r0 + blockIdx.x * blockDim.x + threadIdx.x; t < r1; t += gridDim.x * blockDim.x) {
         const double x = v[t];
         for (int p = 0; p < a.n_ranks; ++p)
-            if (p != a.me) a.stage[p][((a.pair_push[p] + 1ull) & 1ull) * a.half + (unsigned long long)t] = x;
+            if (p != a.me) a.stage[p][((a.pair_push[p] + 1ull) & 1ull) * a.half + (unsigned long long)(t - r0)] = x;
     }
     amg_push_tail(a, mask);
 }
@@ -477,14 +478,17 @@ __global__ void k_amg_wait(P2PHeader *h, unsigned mask)
         h->pair_wait[src] = expect;
     }
 }
-// after k_amg_wait: entries [first, last) of the receive list leave the staging half their sender used (src[t] = the sender)
+// after k_amg_wait: entries [first, last) of the receive list leave the region of their sender src[t] (slot pos[t] of the message)
 __global__ void __launch_bounds__(256)
 k_amg_unpack_stage(double *__restrict__ v, const int *__restrict__ idx, const unsigned char *__restrict__ src,
-                   const double *__restrict__ stage, unsigned long long half, const unsigned long long *__restrict__ pair_wait,
+                   const int *__restrict__ pos, const double *__restrict__ stage, unsigned long long half, const unsigned long long *__restrict__ pair_wait,
                    int first, int last)
 {
     const int t = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < last) v[idx[t]] = stage[(pair_wait[src[t]] & 1ull) * half + (unsigned long long)t];
+    if (t < last) {
+        const unsigned long long p = src[t];
+        v[idx[t]] = stage[(2ull * p + (pair_wait[p] & 1ull)) * half + (unsigned long long)pos[t]];
+    }
 }
 // the blocks of the other ranks from the staging halves into the vector; start[p] = first entry of rank p's block
 struct AmgBlocks { int start[kP2PMaxRanks + 1]; };
@@ -496,7 +500,7 @@ k_amg_unpack_blocks(double *__restrict__ v, const double *__restrict__ stage, un
     if (t >= b.start[n_ranks]) return;
     int p = 0;
     while (t >= b.start[p + 1]) ++p;
-    if (p != me) v[t] = stage[(pair_wait[p] & 1ull) * half + (unsigned long long)t];
+    if (p != me) v[t] = stage[(2ull * (unsigned long long)p + (pair_wait[p] & 1ull)) * half + (unsigned long long)(t - b.start[p])];
 }
 
 // ---- on-device greedy colouring (Jones-Plassmann rounds) ------------------------------------------------------------

@@ -260,14 +260,14 @@ struct HaloPlan {
     // peer-store transport (csrc/p2p.cuh): for every entry of the send list the rank that needs it and its slot in that
     // rank's receive list
     unsigned char *d_send_peer = nullptr, *d_recv_src = nullptr;
-    int *d_send_off = nullptr;
+    int *d_send_off = nullptr, *d_recv_pos = nullptr;
     int n_send() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
     int n_recv() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
     bool empty() const { return n_send() == 0 && n_recv() == 0; }
     void release()
     {
-        cudaFree(d_send_idx); cudaFree(d_recv_idx); cudaFree(d_send_peer); cudaFree(d_send_off); cudaFree(d_recv_src);
-        d_send_idx = d_recv_idx = d_send_off = nullptr; d_send_peer = d_recv_src = nullptr;
+        cudaFree(d_send_idx); cudaFree(d_recv_idx); cudaFree(d_send_peer); cudaFree(d_send_off); cudaFree(d_recv_src); cudaFree(d_recv_pos);
+        d_send_idx = d_recv_idx = d_send_off = d_recv_pos = nullptr; d_send_peer = d_recv_src = nullptr;
     }
 };
 
@@ -603,16 +603,19 @@ int plan_p2p(mgb_amg *h, HaloPlan &H)
             const int *theirs = all.data() + (size_t)p * len;
             if (cnt != theirs[g * R + me + 1] - theirs[g * R + me])
                 return mgb_set_error(MGB_ERR_STATE, "ghost plans of two ranks disagree");
-            for (int k = 0; k < cnt; ++k) { peer[H.send_ptr[q] + k] = (unsigned char)p; off[H.send_ptr[q] + k] = theirs[g * R + me] + k; }
+            for (int k = 0; k < cnt; ++k) { peer[H.send_ptr[q] + k] = (unsigned char)p; off[H.send_ptr[q] + k] = k; }   // slot inside my message to p
         }
     const int nr = H.n_recv();
     if (nr) {
         std::vector<unsigned char> src((size_t)nr);
+        std::vector<int> pos((size_t)nr);
         for (int g = 0; g < H.n_groups; ++g)
             for (int p = 0; p < R; ++p)
-                for (int k = H.recv_ptr[g * R + p]; k < H.recv_ptr[g * R + p + 1]; ++k) src[k] = (unsigned char)p;
+                for (int k = H.recv_ptr[g * R + p]; k < H.recv_ptr[g * R + p + 1]; ++k) { src[k] = (unsigned char)p; pos[k] = k - H.recv_ptr[g * R + p]; }
         ACK(cudaMalloc(&H.d_recv_src, (size_t)nr));
+        ACK(cudaMalloc(&H.d_recv_pos, sizeof(int) * (size_t)nr));
         ACK(cudaMemcpy(H.d_recv_src, src.data(), (size_t)nr, cudaMemcpyHostToDevice));
+        ACK(cudaMemcpy(H.d_recv_pos, pos.data(), sizeof(int) * (size_t)nr, cudaMemcpyHostToDevice));
     }
     if (ns) {
         ACK(cudaMalloc(&H.d_send_peer, (size_t)ns));
@@ -626,13 +629,25 @@ int plan_p2p(mgb_amg *h, HaloPlan &H)
 // allocates and exports the pool, maps the peers', prepares every plan; leaves the NCCL transport in place on any failure
 int setup_p2p(mgb_amg *h, size_t max_halo)
 {
+    // staging: one region per sending rank, two halves each; a half holds the largest message one rank can send another
+    // (never more than a whole receive list) or one rank's block of the all-gathered first replicated level
     size_t half = max_halo;
     for (size_t l = 1; l < h->lv.size(); ++l)
-        if (h->lv[l - 1].sharded && !h->lv[l].sharded) half = std::max(half, (size_t)h->lv[l].A.n_rows);   // all-gathered level
+        if (h->lv[l - 1].sharded && !h->lv[l].sharded) half = std::max(half, (size_t)h->lv[l].A.n_rows / h->n_ranks + 2);
+    {   // the same value on every rank: a sender addresses the receiver's regions with it
+        double *d = nullptr, v = (double)half;
+        ACK(cudaMalloc(&d, sizeof(double)));
+        ACK(cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, h->st));
+        ANK(mgb::nccl().AllReduce(d, d, 1, mgb::kNcclFloat64, mgb::kNcclMax, h->comm, h->st));
+        ACK(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        ACK(cudaStreamSynchronize(h->st));
+        cudaFree(d);
+        half = (size_t)v;
+    }
     half = (half + 63) / 64 * 64;
     const size_t MB2 = (size_t)2 << 20;
     h->stage_half = half;
-    h->pool_bytes = std::max((mgb::kP2PHeaderBytes + 2 * half * sizeof(double) + MB2 - 1) / MB2 * MB2, 2 * MB2);
+    h->pool_bytes = std::max((mgb::kP2PHeaderBytes + 2 * half * sizeof(double) * h->n_ranks + MB2 - 1) / MB2 * MB2, 2 * MB2);
     ACK(cudaMalloc(&h->pool, h->pool_bytes));
     ACK(cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->st));
     h->p2p.init(h->pool, h->pool_bytes, h->rank, h->n_ranks, h->comm, h->st);
@@ -640,7 +655,7 @@ int setup_p2p(mgb_amg *h, size_t max_halo)
     mgb::AmgPush &a = h->push;
     a = mgb::AmgPush{};
     for (int p = 0; p < h->n_ranks; ++p) {
-        a.stage[p] = h->p2p.at<double>(p, mgb::kP2PHeaderBytes);
+        a.stage[p] = h->p2p.at<double>(p, mgb::kP2PHeaderBytes) + 2 * half * (size_t)h->rank;     // my region in rank p's buffer
         a.sig[p] = &h->p2p.hdr(p)->flags[h->rank][0];
     }
     a.half = half;
@@ -662,6 +677,7 @@ int exchange_p2p(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
 {
     const int R = h->n_ranks;
     if (H.send_ptr.empty()) return MGB_OK;                    // no plan: no rank has one
+    if (g1 != g0 + 1) return mgb_set_error(MGB_ERR_STATE, "peer-store exchange moves one group of a plan at a time");
     const int s0 = H.send_ptr[g0 * R], s1 = H.send_ptr[g1 * R], r0 = H.recv_ptr[g0 * R], r1 = H.recv_ptr[g1 * R];
     unsigned mask = 0;                                         // peers: either direction carries something in these groups
     for (int g = g0; g < g1; ++g)
@@ -677,7 +693,7 @@ int exchange_p2p(mgb_amg *h, const HaloPlan &H, int g0, int g1, double *v)
     mgb::k_amg_wait<<<1, 32, 0, h->st>>>(hd, mask);
     h->stats.kernel_launches++;
     if (r1 > r0) {
-        mgb::k_amg_unpack_stage<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, H.d_recv_src, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
+        mgb::k_amg_unpack_stage<<<(r1 - r0 + 255) / 256, 256, 0, h->st>>>(v, H.d_recv_idx, H.d_recv_src, H.d_recv_pos, reinterpret_cast<double *>(h->pool + mgb::kP2PHeaderBytes),
                                                                          (unsigned long long)h->stage_half, hd->pair_wait, r0, r1);
         tally(h, 12. * (r1 - r0));
     }
@@ -724,7 +740,7 @@ int allgather_blocks(mgb_amg *h, int n, double *v)
     if (h->n_ranks == 1) return MGB_OK;
     auto &N = mgb::nccl();
     const Block mine = block_of(n, h->n_ranks, h->rank);
-    if (h->p2p.on && (size_t)n <= h->stage_half) {
+    if (h->p2p.on && (size_t)mine.size() <= h->stage_half && (size_t)n / h->n_ranks + 2 <= h->stage_half) {
         unsigned mask = 0;
         mgb::AmgBlocks bl{};
         for (int p = 0; p < h->n_ranks; ++p) { if (p != h->rank) mask |= 1u << p; bl.start[p] = block_of(n, h->n_ranks, p).r0; }

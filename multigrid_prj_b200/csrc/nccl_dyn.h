@@ -14,7 +14,7 @@ namespace mgb {
 
 struct NcclUniqueId { char internal[128]; };      // NCCL_UNIQUE_ID_BYTES
 typedef struct ncclComm *NcclComm;
-enum { kNcclSuccess = 0, kNcclSum = 0, kNcclUint8 = 1, kNcclUint64 = 5, kNcclFloat64 = 8 };
+enum { kNcclSuccess = 0, kNcclSum = 0, kNcclMax = 2, kNcclUint8 = 1, kNcclUint64 = 5, kNcclFloat64 = 8 };
 
 struct NcclApi {
     void *lib = nullptr;
