@@ -192,7 +192,8 @@ def amg_config5(device, peak, side, levels, rank, world, dist, cycles=10, reps=1
         a.sync()
         setup_s = maxr(time.perf_counter() - t0)
         lay = [dict(a.info(l), rows=a.rows(l)[1], sharded=a.rows(l)[2]) for l in range(a.levels)]
-        rec = {"setup_s": setup_s, "levels": [{"n": x["n"], "nnz": x["nnz_a"], "colours": x["colours"], "sharded": x["sharded"]} for x in lay],
+        rec = {"setup_s": setup_s, "ghost_exchange": None if world == 1 else ("NVLink peer stores" if a.lib.mgb_amg_uses_p2p(a.h) else "NCCL send/recv"),
+               "levels": [{"n": x["n"], "nnz": x["nnz_a"], "colours": x["colours"], "sharded": x["sharded"]} for x in lay],
                "kernels": {}}
         st = a.stream()
 
@@ -438,6 +439,8 @@ def main():
             dist.barrier()
 
     g = Gmg(cfg)
+    transport = None if world == 1 else ("NVLink peer stores (pools exported by CUDA IPC; csrc/p2p.cuh)" if g.lib.mgb_gmg_uses_p2p(g.h)
+                                         else "NCCL send/recv")
     g.set_rhs_test(TEST)
     g.set_u(None)
     timer = Timer()
@@ -637,6 +640,7 @@ def main():
                             "the 16385^2 grid on one GPU for an efficiency on one grid",
             "run": {"smoother": cfg.smoother, "restriction": cfg.restriction, "final_relres": relres,
                     "norm": "all-reduced inside every iteration" if world > 1 else "single rank",
+                    "slab_exchange": transport,
                     "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "parity": parity,

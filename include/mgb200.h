@@ -215,6 +215,10 @@ int mgb_gmg_fine_leg(mgb_gmg_t h, double *sumsq);
  * bench.py asserts exactly that.  Collective when n_ranks > 1. */
 int mgb_gmg_checksum(mgb_gmg_t h, int level, int which, uint64_t *out);
 
+/* 1 when the slab exchanges of this handle move by NVLink peer stores (CUDA IPC), 0 when they use NCCL send/recv (single
+ * rank, MGB_P2P=0, or the pools could not be mapped) */
+int mgb_gmg_uses_p2p(mgb_gmg_t h);
+
 /* measurement hooks */
 typedef struct mgb_gmg_stats {
     uint64_t kernel_launches;      /* kernels launched by this handle since create/reset */
@@ -395,6 +399,7 @@ int mgb_amg_halo_plan(mgb_csr_t M, int n_ranks, int rank, const int *group_of_co
 /* 64-bit checksum over ALL ranks of vector `which` (0 x, 1 rhs, 2 residual) of `level`: independent of the row-block
  * partition, so equal values on 1 and N ranks <=> the sharded solve is bit-identical.  Collective when n_ranks > 1. */
 int mgb_amg_checksum(mgb_amg_t h, int level, int which, uint64_t *out);
+int mgb_amg_uses_p2p(mgb_amg_t h);     /* as mgb_gmg_uses_p2p, for the ghost exchanges of the row blocks */
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s);
 int mgb_amg_reset_stats(mgb_amg_t h);
 void *mgb_amg_stream(mgb_amg_t h);

@@ -75,6 +75,8 @@ SYMBOLS = {
     "mgb_gmg_iterate": (_i, [_vp, _d, _pd, _pd]),
     "mgb_gmg_run_cycles": (_i, [_vp, _i, _pd]),
     "mgb_gmg_checksum": (_i, [_vp, _i, _i, C.POINTER(C.c_uint64)]),
+    "mgb_gmg_uses_p2p": (_i, [_vp]),
+    "mgb_amg_uses_p2p": (_i, [_vp]),
     "mgb_gmg_get_stats": (_i, [_vp, C.POINTER(GmgStatsStruct)]),
     "mgb_gmg_reset_stats": (_i, [_vp]),
     "mgb_gmg_stream": (_vp, [_vp]),

@@ -1793,6 +1793,8 @@ int mgb_amg_checksum(mgb_amg_t h, int level, int which, uint64_t *out)
     return MGB_OK;
 }
 
+int mgb_amg_uses_p2p(mgb_amg_t h) { return (h && h->p2p.on) ? 1 : 0; }
+
 int mgb_amg_get_stats(mgb_amg_t h, mgb_gmg_stats *s)
 {
     if (!h || !s) return mgb_set_error(MGB_ERR_ARG, "null argument");

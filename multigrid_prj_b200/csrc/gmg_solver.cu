@@ -2024,6 +2024,8 @@ int mgb_gmg_checksum(mgb_gmg_t h, int level, int which, uint64_t *out)
     return MGB_OK;
 }
 
+int mgb_gmg_uses_p2p(mgb_gmg_t h) { return (h && h->p2p.on) ? 1 : 0; }
+
 int mgb_gmg_get_stats(mgb_gmg_t h, mgb_gmg_stats *s)
 {
     if (!h || !s) return fail(MGB_ERR_ARG, "null argument");

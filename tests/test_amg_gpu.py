@@ -128,7 +128,9 @@ def test_fast_path_pass_on_mesh1():
         res = a.apply()
     print(f"mesh1 one pass: reference (lexicographic GS) {c['res']:.4f}, multicolour GS {res:.4f}, initial {c['res0']:.4f}")
     assert res < 0.15 * c["res0"]
-    assert abs(res - c["res"]) < 0.5 * c["res"]
+    # the colouring is deterministic (hash priorities): the post-pass residual of the multicolour ordering is a fixed
+    # number, 2.196 against the lexicographic ordering's 1.7035 -- a broken smoother does not land within 1 % of it
+    assert abs(res - 2.196) < 0.02, res
 
 
 @pytest.mark.parametrize("fast", [False, True])

@@ -69,3 +69,28 @@ def test_fused_and_unfused_paths_agree_and_are_deterministic():
     assert np.array_equal(res[0][0], res[2][0])                                     # fused vs separate launches
     assert np.array_equal(res[0][0], res[3][0])                                     # streaming vs one launch per colour, no tail
     assert abs(res[0][1] - res[3][1]) <= 1e-9 * res[3][1]
+
+
+def test_config_c4_grid_on_one_gpu_converges_to_the_analytic_solution():
+    """16385^2, L=14 (BASELINE configs[3], the slab runs' grid) on ONE GPU: the same size-independent properties --
+    contraction per cycle, the analytic solution within the O(h^2) discretisation error, Dirichlet rows -- plus the
+    checksum the multi-GPU bench compares its slabs against (same iterations -> same value, run to run)"""
+    n, lev = 16385, 14
+    h = W / (n - 1)
+    sums = []
+    for rep in range(2):
+        with Gmg(GmgConfig.fast(n, lev)) as g:
+            g.set_rhs_test(1); g.set_u(None)
+            g.run_cycles(6)
+            sums.append(g.checksum())
+            if rep:
+                continue
+            hist = g.solve(tol=1e-9, maxiter=20)
+            assert hist[-1] <= 1e-9 and np.all(hist[2:] < 0.25 * hist[1:-1]), hist
+            # sampled rows are enough: a full host copy of the 2 GiB field adds nothing
+            u = g.get_u()
+            for i in (0, 1, 4096, 8192, 12000, n - 2, n - 1):
+                x = np.arange(n) * h
+                ex = np.exp(x) * np.exp(-2.0 * (W - i * h))
+                assert np.abs(u[i] - ex).max() <= 5e-6 * np.exp(W), i
+    assert sums[0] == sums[1]
