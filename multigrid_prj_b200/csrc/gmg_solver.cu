@@ -167,7 +167,7 @@ struct mgb_gmg {
     double norm_f = 0.;               // sum f^2 on the fine grid (Residual ctor, solvers.hpp:237-242)
     bool have_rhs = false;
     int n_sm = 148;
-    int stream2_min_rows = 48;        // shortest row chunk the second-generation streaming kernel is used for
+    int stream2_min_rows = 32;        // shortest row chunk the second-generation streaming kernel is used for
     bool no_fused_correction = false; // set while the cycle serves as a preconditioner (its output is e, not u += e)
     double *kry[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fine-level work vectors of mgb_gmg_krylov (allocated on first use)
     int stream_impl = 2;              // generation of the streaming red-black kernel (gmg_stream2.cuh where instantiated; 1 = gmg_kernels.cuh only)
