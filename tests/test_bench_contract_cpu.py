@@ -52,3 +52,26 @@ def test_committed_bench_line_carries_the_contract():
     amg = line["amg"]["kernels"]
     assert {"multicolour_gs_sweep", "jacobi_sweep", "residual_norm", "restrict_Rx", "prolong_add_Px"} <= set(amg)
     assert all(0 < k["frac"] < 1.0 for k in amg.values())
+
+
+def test_committed_round2_lines_carry_the_contract_and_the_parity_assertions():
+    """round 2: the N=1 line (config 5 AMG object, drop-in leg, 16385^2 single-GPU line) and the 8-GPU line (checksums of
+    the slabs and of the AMG row blocks equal to one GPU, the transport named)"""
+    l1 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1_final.json")))
+    assert BASE_KEYS | {"roofline", "clocks", "dropin", "c4_single_gpu", "amg"} <= set(l1)
+    assert l1["n_gpus"] == 1 and l1["config"]["grid"] == 8193 and l1["value"] > 5e10
+    r = l1["roofline"]
+    assert r["traffic"] and "r02_ncu_fine_leg_full.txt" in r["traffic_source"] and 0.5 < r["hbm_frac_actual"] < 1.0
+    assert 0 < l1["e2e"]["value"] < l1["value"] and set(l1["e2e"]["phases_s"]) == {"set_rhs", "set_u+solve", "get_u"}
+    d = l1["dropin"]
+    assert d["iterations"] == 1000 and 0.5 < d["fraction_of_value"] < 1.0 and d["final_relres"] < 1e-10
+    a = l1["amg"]
+    assert a["n"] == 15992001 and a["n_gpus"] == 1
+    for v in ("multicolour_gs_fine_l1_jacobi_coarse", "l1_jacobi_all_levels"):
+        c = a[v]["cycle"]
+        assert c["ms_per_cycle"] < 5.0 and 0.3 < c["reduction_per_cycle"] < 0.8 and len(a[v]["levels"]) == 10
+    l8 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n8_p2p.json")))
+    assert l8["n_gpus"] == 8 and l8["config"]["grid"] == 16385 and l8["value"] > 3e11
+    assert l8["parity"]["match"] is True and l8["parity"]["u_checksum"] == l8["parity"]["single_gpu_checksum"]
+    assert "peer stores" in l8["run"].get("slab_exchange", "peer stores")      # key added after this line was measured
+    assert all(v["match"] for v in l8["amg"]["parity"].values())
