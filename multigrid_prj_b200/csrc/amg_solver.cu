@@ -1813,6 +1813,11 @@ int mgb_amg_sync(mgb_amg_t h)
     if (!h) return mgb_set_error(MGB_ERR_ARG, "null handle");
     ACK(cudaSetDevice(h->cfg.device));
     ACK(cudaStreamSynchronize(h->st));
+    if (h->p2p.on) {                  // a wait kernel that gave up (20 s without a peer's signal) leaves a mark instead of hanging
+        unsigned int err = 0;
+        ACK(cudaMemcpy(&err, &h->p2p.hdr(h->rank)->error, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return mgb_set_error(MGB_ERR_NCCL, "peer-store exchange timed out waiting for rank " + std::to_string((int)err - 1));
+    }
     return MGB_OK;
 }
 

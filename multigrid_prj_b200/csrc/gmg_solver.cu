@@ -2044,6 +2044,11 @@ int mgb_gmg_sync(mgb_gmg_t h)
     if (!h) return fail(MGB_ERR_ARG, "null handle");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->st));
+    if (h->p2p.on) {                  // a wait kernel that gave up (20 s without a peer's signal) leaves a mark instead of hanging
+        unsigned int err = 0;
+        CK(cudaMemcpy(&err, &h->p2p.hdr(h->cfg.rank)->error, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return fail(MGB_ERR_NCCL, "peer-store exchange timed out waiting for rank " + std::to_string((int)err - 1));
+    }
     return MGB_OK;
 }
 
