@@ -125,6 +125,12 @@ void mgb_gmg_destroy(mgb_gmg_t h);
  * either sharded (rank owns rows [row0,row0+rows)) or replicated on every rank (row0 = 0, rows = width). */
 int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, int *sharded, size_t *row0, size_t *rows);
 
+/* Where rank `rank` keeps vector `which_buffer` (0 u, 1 f, 2 e, 3 r, 4 t, 5 tu: the ping-pong partners included) of `level`
+ * inside its device pool: byte offset of the allocation that holds the vector with its halo rows (SIZE_MAX when the level
+ * has no such vector) and the pool's total size.  Every rank evaluates this for every OTHER rank to address the peers'
+ * halo rows in the peer-store exchanges (csrc/p2p.cuh), so it must be a pure function of its arguments: host-only. */
+int mgb_gmg_pool_layout(size_t n, int levels, int n_ranks, int rank, int level, int which_buffer, size_t *offset, size_t *total);
+
 /* geometry queries (domain.hpp:82,90,94) */
 int mgb_gmg_level_width(mgb_gmg_t h, int level, size_t *width);
 /* local slab of level `level`: first global row and number of rows owned by this rank */

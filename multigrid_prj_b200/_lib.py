@@ -50,6 +50,7 @@ SYMBOLS = {
     "mgb_gmg_create": (_i, [C.POINTER(GmgConfigStruct), C.POINTER(_vp)]),
     "mgb_gmg_destroy": (None, [_vp]),
     "mgb_gmg_partition": (_i, [C.c_size_t, _i, _i, _i, _i, _pi, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mgb_gmg_pool_layout": (_i, [C.c_size_t, _i, _i, _i, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mgb_gmg_level_width": (_i, [_vp, _i, C.POINTER(C.c_size_t)]),
     "mgb_gmg_level_rows": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mgb_gmg_set_rhs": (_i, [_vp, _vp]),

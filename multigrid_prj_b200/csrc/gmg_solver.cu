@@ -1590,6 +1590,17 @@ int mgb_gmg_partition(size_t n, int levels, int n_ranks, int rank, int level, in
     return MGB_OK;
 }
 
+int mgb_gmg_pool_layout(size_t n, int levels, int n_ranks, int rank, int level, int which_buffer, size_t *offset, size_t *total)
+{
+    if (n < 3 || levels < 1 || levels > 30 || level < 0 || level >= levels || n_ranks < 1 || rank < 0 || rank >= n_ranks ||
+        which_buffer < 0 || which_buffer > 5 || (n - 1) % ((size_t)1 << (levels - 1)) != 0)
+        return fail(MGB_ERR_ARG, "bad layout query");
+    const PoolLayout pl = pool_layout(n, levels, n_ranks, rank);
+    if (offset) *offset = pl.off[level][which_buffer];
+    if (total) *total = pl.total;
+    return MGB_OK;
+}
+
 int mgb_gmg_create(const mgb_gmg_config *cfg, mgb_gmg_t *out)
 {
     if (!cfg || !out) return fail(MGB_ERR_ARG, "null argument");
