@@ -270,6 +270,15 @@ k_axpy_rows(LevelGeom g, double *__restrict__ u, const double *__restrict__ e)
     }
 }
 
+// ---- rows of a pitched level vector packed back to back (w doubles per row): a contiguous device-to-host copy follows ---
+__global__ void __launch_bounds__(256)
+k_pack_rows(LevelGeom g, const double *__restrict__ v, double *__restrict__ packed)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.w) return;
+    for (int i = blockIdx.y; i < g.rows; i += gridDim.y) packed[(size_t)i * g.w + j] = v[(size_t)i * g.pitch + j];
+}
+
 // ---- lexicographic Gauss-Seidel, exact order (solvers.hpp:33-48) -------------------------------------
 // Parity mode.  One CTA sweeps a band of <= 1024 rows as a skewed wavefront: thread t owns row
 // band0+t and at step s updates column s-t, so (i-1,j) and (i,j-1) are already new and (i,j+1),

@@ -1758,7 +1758,20 @@ int mgb_gmg_get_level(mgb_gmg_t h, int level, int which, double *host)
     double **p = h->vec(level, which);
     if (!p) return fail(MGB_ERR_ARG, "vector does not exist on this level");
     CK(cudaSetDevice(h->cfg.device));
-    return copy_2d(h, h->lv[level].g, *p, host, false);
+    Level &L = h->lv[level];
+    static const int packed = [] { const char *e = std::getenv("MGB_PACKED_D2H"); return e ? std::atoi(e) : 1; }();   // 0: pitched 2-D copy
+    if (packed && level == 0 && which == MGB_VEC_U && L.tu && (size_t)L.g.rows * L.g.w >= ((size_t)1 << 20)) {
+        // the solution of a large grid: rows packed back to back into the free ping-pong partner of u (it is scratch between
+        // calls), then ONE contiguous copy instead of a pitched 2-D copy
+        double *scratch = L.tu - (size_t)kHalo * L.g.pitch;
+        mgb::k_pack_rows<<<dim3((L.g.w + 255) / 256, std::min(L.g.rows, 2048)), 256, 0, h->st>>>(L.g, *p, scratch);
+        count(h, 16. * npts(L.g));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host + (size_t)L.g.row0 * L.g.w, scratch, (size_t)L.g.rows * L.g.w * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        return MGB_OK;
+    }
+    return copy_2d(h, L.g, *p, host, false);
 }
 
 int mgb_gmg_set_rhs(mgb_gmg_t h, const double *b_host) { return mgb_gmg_set_level(h, 0, MGB_VEC_F, b_host); }

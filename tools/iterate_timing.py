@@ -1,5 +1,5 @@
 import sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from multigrid_prj_b200 import Gmg, GmgConfig
 g = Gmg(GmgConfig.fast(8193, 13))
 g.set_rhs_test(1); g.set_u(None)
