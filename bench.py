@@ -398,6 +398,7 @@ def main():
     ap.add_argument("--amg-levels", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the single-GPU repeat + checksum comparison")
     ap.add_argument("--no-c4", action="store_true", help="N=1: skip the 16385^2 single-GPU line")
+    ap.add_argument("--no-convergence", action="store_true", help="N=1: skip the time-to-tolerance leg (cycle shapes, Krylov)")
     ap.add_argument("--no-dropin", action="store_true", help="N=1: skip the run of the reference's own driver against the facade")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -604,6 +605,33 @@ def main():
                "sample": f"{cc} driver iterations of the reference's GS solver on {cn}^2, L={cl} ({dt:.1f} s); "
                          f"lexicographic GS is serial, only the residual loops use the {cores} OpenMP threads"}
 
+    # ---- time to tolerance (N=1): DoF/s per iteration says nothing about how many iterations an algorithm needs; the cycle
+    # shapes and the Krylov solver the library offers on the same handle, each from u = 0 to a relative residual of 1e-9
+    convergence = None
+    if rank == 0 and world == 1 and args.mode == "fast" and not args.no_convergence:
+        convergence = {"tolerance": 1e-9, "what": "wall time of one solve call from u = 0 (norm read back every iteration / step), same grid"}
+        try:
+            def timed_solve(label, fn):
+                g.set_u(None); g.sync()
+                t0 = time.perf_counter()
+                hist = fn()
+                dt = time.perf_counter() - t0
+                convergence[label] = {"iterations": int(hist.size - 1), "seconds": dt, "final_relres": float(hist[-1])}
+            timed_solve("sawtooth (2 pre-sweeps + cycle, the reference's shape; fast path)", lambda: g.solve(tol=1e-9, maxiter=40))
+            g.set_cycle_type(G.CYCLE_V, 2, 0)
+            timed_solve("V(2,5) cycles", lambda: g.solve(tol=1e-9, maxiter=40))
+            g.set_cycle_type(G.CYCLE_W, 2, 0)
+            timed_solve("W(2,5) cycles", lambda: g.solve(tol=1e-9, maxiter=40))
+            g.set_cycle_type(G.CYCLE_SAWTOOTH, 0, 0)
+            timed_solve("BiCGSTAB preconditioned by the sawtooth cycle", lambda: g.krylov(G.KRYLOV_BICGSTAB, G.PRECOND_MG, tol=1e-9, maxit=40))
+        except Exception as e:                               # noqa: BLE001 -- a reported leg, never fails the bench
+            convergence["error"] = repr(e)
+        finally:
+            try:
+                g.set_cycle_type(G.CYCLE_SAWTOOTH, 0, 0)
+            except Exception:                                # noqa: BLE001
+                pass
+
     # ---- like for like (N=1): the REFERENCE'S algorithm on the GPU (exact lexicographic GS + injection: bit-identical to the
     # reference, tests/test_gmg_gpu.py) on the cpu_baseline's own configuration, so that one ratio compares the same arithmetic
     same_alg = None
@@ -661,7 +689,7 @@ def main():
                     "norm": "all-reduced inside every iteration" if world > 1 else "single rank",
                     "slab_exchange": transport,
                     "extra_warmup": "4 untimed steps after --warmup during which the CUDA graph of the iteration is captured"},
-            "roofline": roofline, "cpu_baseline": cpu, "same_algorithm_on_gpu": same_alg, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "same_algorithm_on_gpu": same_alg, "convergence": convergence, "e2e": e2e,
             "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks, "parity": parity,
             "value_deferred_norm": deferred, "c4_single_gpu": c4, "dropin": dropin, "amg": amg,
         }
