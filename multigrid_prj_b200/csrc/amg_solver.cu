@@ -285,12 +285,14 @@ void order_segments(int n_groups, int n_ranks, int n_cols, const int *group_of_c
     (void)n_cols;
 }
 
-HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_col, int n_groups)
+// the ghost entries of one rank, before any grouping: what it receives (with the owner of each entry) and what it sends
+// (with the rank that needs each entry).  The scans over the matrix happen here, once; a plan is an ordering of these lists.
+struct HaloEntries { std::vector<int> recv, recv_peer, send, send_peer; };
+
+HaloEntries halo_entries(const HostCsr &M, int n_ranks, int rank)
 {
-    HaloPlan H;
-    H.n_groups = std::max(n_groups, 1); H.n_ranks = n_ranks;
+    HaloEntries E;
     const Block mine_rows = block_of(M.n_rows, n_ranks, rank), mine_cols = block_of(M.n_cols, n_ranks, rank);
-    std::vector<int> entries, peer;
     // receive: columns outside my block that my rows reference (ascending, hence ascending per peer)
     {
         std::vector<unsigned char> need(M.n_cols, 0);
@@ -299,12 +301,10 @@ HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_
                 const int j = M.col[k];
                 if (j < mine_cols.r0 || j >= mine_cols.r1) need[j] = 1;
             }
-        for (int j = 0; j < M.n_cols; ++j) if (need[j]) { entries.push_back(j); peer.push_back(owner_of(M.n_cols, n_ranks, j)); }
-        order_segments(H.n_groups, n_ranks, M.n_cols, group_of_col, entries, peer, H.recv_ptr, H.recv_idx);
+        for (int j = 0; j < M.n_cols; ++j) if (need[j]) { E.recv.push_back(j); E.recv_peer.push_back(owner_of(M.n_cols, n_ranks, j)); }
     }
     // send: my entries that the rows of rank q reference, q by q (the same ascending order q derives for its receive list)
     {
-        entries.clear(); peer.clear();
         std::vector<int> stamp(std::max(mine_cols.size(), 1), -1);
         for (int q = 0; q < n_ranks; ++q) {
             if (q == rank) continue;
@@ -316,11 +316,26 @@ HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_
                     if (j >= mine_cols.r0 && j < mine_cols.r1 && stamp[j - mine_cols.r0] != q) { stamp[j - mine_cols.r0] = q; hit.push_back(j); }
                 }
             std::sort(hit.begin(), hit.end());
-            for (int j : hit) { entries.push_back(j); peer.push_back(q); }
+            for (int j : hit) { E.send.push_back(j); E.send_peer.push_back(q); }
         }
-        order_segments(H.n_groups, n_ranks, M.n_cols, group_of_col, entries, peer, H.send_ptr, H.send_idx);
     }
+    return E;
+}
+
+HaloPlan plan_of(const HaloEntries &E, int n_cols, int n_ranks, const int *group_of_col, int n_groups)
+{
+    HaloPlan H;
+    H.n_groups = std::max(n_groups, 1); H.n_ranks = n_ranks;
+    std::vector<int> entries = E.recv;
+    order_segments(H.n_groups, n_ranks, n_cols, group_of_col, entries, E.recv_peer, H.recv_ptr, H.recv_idx);
+    entries = E.send;
+    order_segments(H.n_groups, n_ranks, n_cols, group_of_col, entries, E.send_peer, H.send_ptr, H.send_idx);
     return H;
+}
+
+HaloPlan halo_plan(const HostCsr &M, int n_ranks, int rank, const int *group_of_col, int n_groups)
+{
+    return plan_of(halo_entries(M, n_ranks, rank), M.n_cols, n_ranks, group_of_col, n_groups);
 }
 
 struct AmgLevel {
@@ -1130,12 +1145,13 @@ int build_levels_device(mgb_amg *h, size_t &max_blocks, size_t &max_halo)
         if (Lv.sharded) {
             HostCsr hAm;
             if ((rc = download(Lv.A, hAm))) return rc;
-            Lv.haloA = halo_plan(hAm, n_ranks, rank, nullptr, 1);
+            const HaloEntries EA = halo_entries(hAm, n_ranks, rank);          // one pass over the matrix serves both orderings
+            Lv.haloA = plan_of(EA, hAm.n_cols, n_ranks, nullptr, 1);
             if ((rc = upload_plan(Lv.haloA))) return rc;
             if (coloured) {
                 Lv.colour.h_group.assign((size_t)nl, 0);
                 ACK(cudaMemcpy(Lv.colour.h_group.data(), Lv.d_colour, sizeof(int) * (size_t)nl, cudaMemcpyDeviceToHost));
-                Lv.haloA_colour = halo_plan(hAm, n_ranks, rank, Lv.colour.h_group.data(), Lv.colour.n_groups);
+                Lv.haloA_colour = plan_of(EA, hAm.n_cols, n_ranks, Lv.colour.h_group.data(), Lv.colour.n_groups);
                 if ((rc = upload_plan(Lv.haloA_colour))) return rc;
             }
             max_halo = std::max<size_t>(max_halo, std::max(Lv.haloA.n_send(), Lv.haloA.n_recv()));
@@ -1267,8 +1283,9 @@ int build_levels_host(mgb_amg *h, size_t n, const int64_t *ptr, const int64_t *c
         if ((rc = build_sell(h, L))) return rc;
         if (!cfg->exact_order && (rc = build_sell_natural(L))) return rc;
         if (L.sharded) {
-            L.haloA = halo_plan(L.hA, n_ranks, rank, nullptr, 1);
-            L.haloA_colour = halo_plan(L.hA, n_ranks, rank, L.colour.h_group.data(), L.colour.n_groups);
+            const HaloEntries EA = halo_entries(L.hA, n_ranks, rank);         // one pass over the matrix serves both orderings
+            L.haloA = plan_of(EA, L.hA.n_cols, n_ranks, nullptr, 1);
+            L.haloA_colour = plan_of(EA, L.hA.n_cols, n_ranks, L.colour.h_group.data(), L.colour.n_groups);
             if ((rc = upload_plan(L.haloA))) return rc;
             if ((rc = upload_plan(L.haloA_colour))) return rc;
             max_halo = std::max<size_t>(max_halo, std::max(L.haloA.n_send(), L.haloA.n_recv()));
