@@ -23,6 +23,7 @@
 #ifndef MGB200_GMG_FACADE_HPP
 #define MGB200_GMG_FACADE_HPP
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdlib>
@@ -388,16 +389,39 @@ public:
     int kind() const override { return MGB_SMOOTH_JACOBI; }
 };
 
-// The reference constructs BiCGSTAB objects but its driver never runs them (main.cpp:103-106 routes
-// `-smt 2` to the Jacobi cycle); the library routes this id to Jacobi in the same way.
+// The reference constructs BiCGSTAB objects but its driver never runs them (main.cpp:103-106 routes `-smt 2` to the Jacobi
+// cycle), and the body it would run indexes its work vectors with an unchecked neighbour list (solvers.hpp:122,153: undefined
+// behaviour on the first boundary row).  Applied to the fine level with the forcing vector -- `u * BICG`, the one use that is
+// well defined -- the facade runs the library's BiCGSTAB (mgb_gmg_krylov, unpreconditioned, the same recurrences:
+// solvers.hpp:115-200) with the reference's console lines and its absolute tolerance; inside a cycle (the template argument
+// of SawtoothMGIteration) and on coarse levels the id is routed to Jacobi exactly as the driver does.
 template <class Vector>
 class BiCGSTAB : public SmootherClass<Vector> {
     PoissonMatrix<double> &m_A;
     Vector &b;
+    double tol;
 
 public:
-    BiCGSTAB(PoissonMatrix<double> &A, Vector &f, double = TOL) : m_A(A), b(f) {}
-    void apply_iteration_to_vec(std::vector<double> &sol) override { detail::smooth(m_A, b, sol, MGB_SMOOTH_BICGSTAB); }
+    BiCGSTAB(PoissonMatrix<double> &A, Vector &f, double tolerance = TOL) : m_A(A), b(f), tol(tolerance) {}
+    void apply_iteration_to_vec(std::vector<double> &sol) override
+    {
+        if (m_A.level() != 0 || detail::RhsRole<Vector>::which != MGB_VEC_F) { detail::smooth(m_A, b, sol, MGB_SMOOTH_BICGSTAB); return; }
+        detail::Context &c = m_A.ctx();
+        c.bind(MGB_VEC_F, 0, &b, detail::HostData<Vector>::get(b));
+        c.bind(MGB_VEC_U, 0, &sol, sol.data());
+        c.run_pending();
+        std::cout << "Avviamento del metodo BiCGSTAB." << std::endl;                             // solvers.hpp:117
+        double nb = 0.;
+        for (size_t i = 0; i < b.size(); i++) { const double v = b[i]; nb += v * v; }
+        nb = std::sqrt(nb);
+        const int maxit = (int)std::min<size_t>(m_A.rows(), 10000);                             // solvers.hpp:141: at most `size` steps
+        std::vector<double> hist((size_t)maxit + 1, 0.);
+        int n = 0;
+        detail::ok(mgb_gmg_krylov(c.h, MGB_KRYLOV_BICGSTAB, MGB_PRECOND_NONE, nb > 0. ? tol / nb : tol, maxit, hist.data(), &n));
+        for (int k = 1; k < n; ++k) std::cout << "Norma del residuo: " << hist[k] * nb << std::endl;   // solvers.hpp:200
+        if (n > 0 && hist[n - 1] * nb < tol) std::cout << "Convergenza raggiunta." << std::endl;
+        c.touched(MGB_VEC_U, 0);
+    }
     int kind() const override { return MGB_SMOOTH_BICGSTAB; }
 };
 

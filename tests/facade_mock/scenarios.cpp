@@ -43,6 +43,10 @@ int main(int argc, char **argv)
         other * GS;
         sync_to_host(&u); sync_to_host(&other);
         std::cout << "u0 " << u[0] << " other0 " << other[0] << std::endl;
+    } else if (what == "bicgstab") {              // the reference's BiCGSTAB class applied to the fine system
+        MultiGrid::BiCGSTAB<DataVector<double>> BICG(matrici.front(), fvec, 1e-6);   // (the enum SMOOTHERS has a BiCGSTAB too)
+        u * GS * GS;
+        u * BICG;
     } else if (what == "residual_of_other") {     // the residual call that follows is about ANOTHER vector: no fusion
         u * GS * GS * MG0;
         other * RES;

@@ -77,3 +77,12 @@ def test_another_vector_flushes_the_queue_first(exe):
     ops = [l.split()[0] for l in body]
     assert "iterate" not in ops and ops.index("cycle") < ops.index("residual"), body
     assert body[-1] == "u0 102"
+
+
+def test_bicgstab_class_dispatches_to_the_krylov_solver_with_the_reference_console_lines(exe):
+    body, out = calls(exe, "bicgstab")
+    ops = [l.split()[0] for l in body]
+    assert ops[:4] == ["upload", "smooth", "smooth", "Avviamento"], body          # queued sweeps first, then the solver
+    assert "krylov method=1 precond=0 maxit=289" in body                          # unpreconditioned, at most `size` steps (17^2)
+    assert sum(l.startswith("Norma del residuo: ") for l in body) == 2
+    assert body[-2:] == ["Convergenza raggiunta.", "download level=0 which=0"]    # the operator object goes out of scope: u comes home
